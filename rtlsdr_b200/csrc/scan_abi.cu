@@ -1,0 +1,1219 @@
+/*
+ * scan_abi.cu -- implementation of include/rtlsdr_gpu_scan.h on CUDA (sm_100a).
+ *
+ * Host responsibilities kept here (no DSP on the CPU):
+ *  - host-built tables exactly as the reference builds them
+ *    (sine_table rtl_power.c:247-261, window_coefs :985-988),
+ *  - the pinned, double-buffered staging ring that submit() copies into
+ *    (async buffers are re-armed right after the callback, librtlsdr.c:2705-2707),
+ *  - grouping the submitted reads by hop into segments so that one CTA
+ *    accumulates many reads of a hop in registers before a single flush,
+ *  - tunes[i].samples bookkeeping (rtl_power.c:717, :435): deterministic from
+ *    the number of reads, so it is counted on the host.
+ */
+#include "../../include/rtlsdr_gpu_scan.h"
+#include "scan_kernels.cuh"
+#include "scan_large.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace rscan;
+
+namespace {
+
+constexpr int kDescSlots = 4;
+constexpr size_t kDefaultRing = 32u << 20;
+constexpr size_t kScratchBudget = 512ull << 20; /* device bytes for decimation / large-FFT scratch */
+
+enum Path { PATH_RMS, PATH_SMALL_U8, PATH_SMALL_DECIM, PATH_LARGE };
+
+struct DescSlot {
+	void *h = nullptr; /* pinned */
+	void *d = nullptr;
+	size_t cap = 0;
+	cudaEvent_t done = nullptr;
+	bool used = false;
+};
+
+struct RegularKey {
+	const void *base = nullptr;
+	int hop_first = -1, hop_count = 0, passes = 0;
+	long long pass_stride = 0, hop_stride = 0;
+	bool valid = false;
+	int n_reads = 0, n_segs = 0;
+	bool operator==(const RegularKey &o) const
+	{
+		return valid && o.valid && base == o.base && hop_first == o.hop_first && hop_count == o.hop_count &&
+		       passes == o.passes && pass_stride == o.pass_stride && hop_stride == o.hop_stride;
+	}
+};
+
+} // namespace
+
+struct rtlsdr_gpu_scan {
+	rtlsdr_gpu_scan_cfg_t cfg;
+	int N = 1;
+	Path path = PATH_SMALL_U8;
+	int l_len = 0, n_blocks = 0, units_per_read = 1, samples_per_read = 0;
+	long long image_stride = 0; /* c16 per decimated image */
+	int db_i1 = 0, db_i2 = 0, db_count = 2;
+	int num_sms = 148, ctas_per_sm = 2;
+
+	cudaStream_t own_stream = nullptr, stream = nullptr;
+	cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+
+	long long *d_avg = nullptr;
+	int2 *d_tw = nullptr;
+	uint16_t *d_win = nullptr;
+	double *d_db = nullptr;
+	int *d_samples = nullptr;
+	int *h_samples_pinned = nullptr;
+	std::vector<int> samples;
+	PassTw tw0;
+	std::vector<int2> tw_host;
+
+	/* staging ring: two halves, each host pinned + device mirror */
+	size_t ring_bytes = 0;
+	int ring_reads = 0; /* reads per half */
+	uint8_t *h_ring[2] = { nullptr, nullptr };
+	uint8_t *d_ring[2] = { nullptr, nullptr };
+	cudaEvent_t ring_done[2] = { nullptr, nullptr };
+	bool ring_busy[2] = { false, false };
+	int cur_half = 0;
+	std::vector<int> ring_hops;
+
+	DescSlot desc[kDescSlots];
+	int desc_next = 0;
+	/* cached descriptors of the last regular device-resident batch */
+	RegularKey reg_key;
+	void *d_reg_desc = nullptr;
+	size_t reg_desc_cap = 0;
+
+	/* scratch for decimation and the large-FFT path */
+	uint8_t *d_scratch = nullptr;
+	size_t scratch_bytes = 0;
+
+	/* bulk H2D staging for submit_batch */
+	uint8_t *d_bulk = nullptr;
+	size_t bulk_bytes = 0;
+
+	uint64_t launches = 0, h2d = 0, d2h = 0;
+	/* timing of the transform kernels */
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
+	std::vector<cudaEvent_t> ev_pool;
+	bool timing = false;
+
+	std::string last_error;
+};
+
+namespace {
+
+#define CU(call)                                                                                 \
+	do {                                                                                         \
+		cudaError_t _e = (call);                                                                 \
+		if (_e != cudaSuccess) {                                                                 \
+			h->last_error = std::string(#call) + ": " + cudaGetErrorString(_e);                  \
+			return RTLSDR_GPU_ERR_CUDA;                                                          \
+		}                                                                                        \
+	} while (0)
+
+int check_launch(rtlsdr_gpu_scan *h, const char *what)
+{
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) {
+		h->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+		return RTLSDR_GPU_ERR_CUDA;
+	}
+	h->launches++;
+	return 0;
+}
+
+/* ---- host tables (reference expressions, see header) ------------------- */
+
+void host_sine_table(int m, int16_t *out)
+{
+	const int n = 1 << m, count = n * 3 / 4;
+	for (int i = 0; i < count; i++) {
+		double d = (double)i * 2.0 * M_PI / n;
+		out[i] = (int16_t)(int)round(32767 * sin(d));
+	}
+}
+
+typedef double (*window_fn)(int, int);
+double win_rectangle(int, int) { return 1.0; }
+double win_hamming(int i, int n)
+{
+	double a = 25.0 / 46.0, b = 21.0 / 46.0, n1 = (double)(n - 1);
+	return a - b * cos(2 * i * M_PI / n1);
+}
+double win_blackman(int i, int n)
+{
+	double a0 = 7938.0 / 18608.0, a1 = 9240.0 / 18608.0, a2 = 1430.0 / 18608.0, n1 = (double)(n - 1);
+	return a0 - a1 * cos(2 * i * M_PI / n1) + a2 * cos(4 * i * M_PI / n1);
+}
+double win_blackman_harris(int i, int n)
+{
+	double a0 = 0.35875, a1 = 0.48829, a2 = 0.14128, a3 = 0.01168, n1 = (double)(n - 1);
+	return a0 - a1 * cos(2 * i * M_PI / n1) + a2 * cos(4 * i * M_PI / n1) - a3 * cos(6 * i * M_PI / n1);
+}
+double win_hann_poisson(int i, int n)
+{
+	double a = 2.0, n1 = (double)(n - 1);
+	return 0.5 * (1 - cos(2 * M_PI * i / n1)) * pow(M_E, (-a * (double)abs((int)(n1 - 1 - 2 * i))) / n1);
+}
+double win_youssef(int i, int n)
+{
+	double a = 0.0025, n1 = (double)(n - 1);
+	double w = win_blackman_harris(i, n);
+	w *= pow(M_E, (-a * (double)abs((int)(n1 - 1 - 2 * i))) / n1);
+	return w;
+}
+double win_bartlett(int i, int n)
+{
+	double l = (double)n, n1 = l - 1;
+	double w = (i - n1 / 2) / (l / 2);
+	if (w < 0)
+		w = -w;
+	return 1 - w;
+}
+
+/* cic_9_tables rows (rtl_power.c:219-232), entries [1..5] */
+const int kCic9[11][5] = {
+	{ 0, 0, 0, 0, 0 },
+	{ -156, -97, 2798, -15489, 61019 },
+	{ -128, -568, 5593, -24125, 74126 },
+	{ -129, -639, 6187, -26281, 77511 },
+	{ -122, -612, 6082, -26353, 77818 },
+	{ -120, -602, 6015, -26269, 77757 },
+	{ -120, -582, 5951, -26128, 77542 },
+	{ -119, -580, 5931, -26094, 77505 },
+	{ -119, -578, 5921, -26077, 77484 },
+	{ -119, -577, 5917, -26067, 77473 },
+	{ -199, -362, 5303, -25505, 77489 },
+};
+
+/* ---- events for kernel timing ----------------------------------------- */
+
+cudaEvent_t get_event(rtlsdr_gpu_scan *h)
+{
+	cudaEvent_t e = nullptr;
+	if (!h->ev_pool.empty()) {
+		e = h->ev_pool.back();
+		h->ev_pool.pop_back();
+		return e;
+	}
+	if (cudaEventCreate(&e) != cudaSuccess)
+		return nullptr;
+	return e;
+}
+
+struct TimedScope {
+	rtlsdr_gpu_scan *h;
+	cudaEvent_t a = nullptr, b = nullptr;
+	explicit TimedScope(rtlsdr_gpu_scan *hh) : h(hh)
+	{
+		if (!h->timing)
+			return;
+		a = get_event(h);
+		b = get_event(h);
+		if (a && b)
+			cudaEventRecord(a, h->stream);
+	}
+	~TimedScope()
+	{
+		if (a && b) {
+			cudaEventRecord(b, h->stream);
+			h->timed.push_back({ a, b });
+		}
+	}
+};
+
+/* ---- descriptor upload ------------------------------------------------- */
+
+int desc_acquire(rtlsdr_gpu_scan *h, size_t bytes, DescSlot **out)
+{
+	DescSlot &s = h->desc[h->desc_next];
+	h->desc_next = (h->desc_next + 1) % kDescSlots;
+	if (s.used)
+		CU(cudaEventSynchronize(s.done));
+	if (s.cap < bytes) {
+		size_t cap = std::max(bytes, (size_t)1 << 16);
+		if (s.h)
+			cudaFreeHost(s.h);
+		if (s.d)
+			cudaFree(s.d);
+		s.h = s.d = nullptr;
+		s.cap = 0;
+		CU(cudaMallocHost(&s.h, cap));
+		CU(cudaMalloc(&s.d, cap));
+		s.cap = cap;
+	}
+	if (!s.done)
+		CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+	*out = &s;
+	return 0;
+}
+
+int ensure_scratch(rtlsdr_gpu_scan *h, size_t bytes)
+{
+	if (h->scratch_bytes >= bytes)
+		return 0;
+	if (h->d_scratch) {
+		CU(cudaStreamSynchronize(h->stream));
+		cudaFree(h->d_scratch);
+		h->d_scratch = nullptr;
+		h->scratch_bytes = 0;
+	}
+	if (cudaMalloc(&h->d_scratch, bytes) != cudaSuccess) {
+		cudaGetLastError();
+		h->last_error = "cudaMalloc(scratch) failed";
+		return RTLSDR_GPU_ERR_NOMEM;
+	}
+	h->scratch_bytes = bytes;
+	return 0;
+}
+
+/* Layout of a descriptor blob: [read_off: n_reads x int64][segs: n_segs x int4][hop_of: n_reads x int] */
+struct DescLayout {
+	size_t off_reads, off_segs, off_hops, bytes;
+	DescLayout(int n_reads, int n_segs)
+	{
+		off_reads = 0;
+		off_segs = ((size_t)n_reads * 8 + 15) & ~(size_t)15;
+		off_hops = off_segs + (size_t)n_segs * 16;
+		bytes = off_hops + (size_t)n_reads * 4;
+	}
+};
+
+/*
+ * Sort the batch's reads by hop and cut each hop's run into segments of about
+ * `total / target` reads.  Returns segment count.
+ */
+int build_desc(rtlsdr_gpu_scan *h, const std::vector<long long> &offs, const std::vector<int> &hops,
+	       std::vector<long long> &s_offs, std::vector<int> &s_hops, std::vector<int4> &segs)
+{
+	const int n = (int)offs.size(), tc = h->cfg.tune_count;
+	std::vector<int> count(tc + 1, 0);
+	for (int i = 0; i < n; i++)
+		count[hops[i] + 1]++;
+	for (int i = 0; i < tc; i++)
+		count[i + 1] += count[i];
+	s_offs.resize(n);
+	s_hops.resize(n);
+	std::vector<int> cursor(count.begin(), count.end() - 1);
+	for (int i = 0; i < n; i++) {
+		int p = cursor[hops[i]]++;
+		s_offs[p] = offs[i];
+		s_hops[p] = hops[i];
+	}
+	const int target = std::max(1, h->num_sms * h->ctas_per_sm);
+	const int chunk = std::max(1, (n + target - 1) / target);
+	segs.clear();
+	for (int hp = 0; hp < tc; hp++) {
+		int lo = count[hp], hi = count[hp + 1];
+		int cnt = hi - lo;
+		if (cnt <= 0)
+			continue;
+		int pieces = (cnt + chunk - 1) / chunk;
+		for (int k = 0; k < pieces; k++) {
+			int a = lo + (int)((long long)cnt * k / pieces), b = lo + (int)((long long)cnt * (k + 1) / pieces);
+			if (b > a)
+				segs.push_back(make_int4(hp, a, b - a, 0));
+		}
+	}
+	return (int)segs.size();
+}
+
+/* ---- kernel dispatch --------------------------------------------------- */
+
+int large_process(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_offs, const int *d_hops, int n_reads);
+
+template <int L, bool PEAK, bool IN16>
+int launch_small_t(rtlsdr_gpu_scan *h, const SmallParams &prm)
+{
+	auto kern = scan_small_kernel<L, PEAK, IN16>;
+	const int smem = SmallSmem<L>::bytes;
+	CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+	const int grid = std::min(prm.n_segs, h->num_sms * 8);
+	kern<<<grid, kThreads, smem, h->stream>>>(prm);
+	return check_launch(h, "scan_small_kernel");
+}
+
+template <int L>
+int launch_small_l(rtlsdr_gpu_scan *h, const SmallParams &prm, bool in16)
+{
+	if (h->cfg.peak_hold)
+		return in16 ? launch_small_t<L, true, true>(h, prm) : launch_small_t<L, true, false>(h, prm);
+	return in16 ? launch_small_t<L, false, true>(h, prm) : launch_small_t<L, false, false>(h, prm);
+}
+
+int launch_small(rtlsdr_gpu_scan *h, const SmallParams &prm, bool in16)
+{
+	switch (h->cfg.bin_e) {
+	case 1: return launch_small_l<1>(h, prm, in16);
+	case 2: return launch_small_l<2>(h, prm, in16);
+	case 3: return launch_small_l<3>(h, prm, in16);
+	case 4: return launch_small_l<4>(h, prm, in16);
+	case 5: return launch_small_l<5>(h, prm, in16);
+	case 6: return launch_small_l<6>(h, prm, in16);
+	case 7: return launch_small_l<7>(h, prm, in16);
+	case 8: return launch_small_l<8>(h, prm, in16);
+	case 9: return launch_small_l<9>(h, prm, in16);
+	case 10: return launch_small_l<10>(h, prm, in16);
+	case 11: return launch_small_l<11>(h, prm, in16);
+	case 12: return launch_small_l<12>(h, prm, in16);
+	default: break;
+	}
+	return RTLSDR_GPU_ERR_CONFIG;
+}
+
+/*
+ * Decimate entries [e0, e0+n) (u8 reads at base + d_offs[e]) into c16 images in
+ * scratch and compute their DC sums.  Scratch layout for n entries:
+ *   [images n x image_stride c16][bufA n x pairs/2 c16][bufB n x pairs/4 c16][sums n x 2 int64]
+ */
+struct DecimScratch {
+	c16 *img, *a, *b;
+	long long *sums;
+	static size_t per_entry(const rtlsdr_gpu_scan *h)
+	{
+		size_t pairs = (size_t)h->cfg.buf_len / 2;
+		return (size_t)h->image_stride * 4 + (pairs / 2) * 4 + (pairs / 4 + 4) * 4 + 16;
+	}
+	DecimScratch(const rtlsdr_gpu_scan *h, int n)
+	{
+		size_t pairs = (size_t)h->cfg.buf_len / 2;
+		uint8_t *p = h->d_scratch;
+		img = (c16 *)p;
+		p += (size_t)n * h->image_stride * 4;
+		a = (c16 *)p;
+		p += (size_t)n * (pairs / 2) * 4;
+		b = (c16 *)p;
+		p += (size_t)n * (pairs / 4 + 4) * 4;
+		p = (uint8_t *)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+		sums = (long long *)p;
+	}
+};
+
+int run_decimators(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_offs, int n, const DecimScratch &sc)
+{
+	const int pairs = h->cfg.buf_len / 2;
+	const int img_count = (int)h->image_stride;
+	int rc;
+	if (h->cfg.boxcar && h->cfg.downsample > 1) {
+		DecimParams p;
+		p.base = base;
+		p.read_off = d_offs;
+		p.n_reads = n;
+		p.pairs = pairs;
+		p.ds = h->cfg.downsample;
+		p.out = sc.img;
+		p.out_stride = h->image_stride;
+		p.out_count = img_count;
+		dim3 grid((img_count + 255) / 256, n);
+		boxcar_kernel<<<grid, 256, 0, h->stream>>>(p);
+		if ((rc = check_launch(h, "boxcar_kernel")))
+			return rc;
+	} else {
+		const int passes = h->cfg.downsample_passes;
+		const c16 *cur = nullptr;
+		long long cur_stride = 0;
+		int count = pairs;
+		for (int j = 0; j < passes; j++) {
+			HalfbandParams p;
+			c16 *dst = (j & 1) ? sc.b : sc.a;
+			long long dst_stride = (j & 1) ? (pairs / 4 + 4) : (pairs / 2);
+			p.in = j == 0 ? (const void *)base : (const void *)cur;
+			p.read_off = d_offs;
+			p.in_stride = cur_stride;
+			p.out = dst;
+			p.out_stride = dst_stride;
+			p.n_out = count / 2;
+			dim3 grid((p.n_out + 255) / 256, n);
+			if (j == 0)
+				halfband_kernel<true><<<grid, 256, 0, h->stream>>>(p);
+			else
+				halfband_kernel<false><<<grid, 256, 0, h->stream>>>(p);
+			if ((rc = check_launch(h, "halfband_kernel")))
+				return rc;
+			cur = dst;
+			cur_stride = dst_stride;
+			count /= 2;
+		}
+		FirParams f;
+		f.in = cur;
+		f.in_stride = cur_stride;
+		f.out = sc.img;
+		f.out_stride = h->image_stride;
+		f.count = count;
+		f.use_fir = (h->cfg.comp_fir_size == 9 && passes <= 10) ? 1 : 0;
+		const int *row = kCic9[passes <= 10 ? passes : 0];
+		f.f1 = row[0]; f.f2 = row[1]; f.f3 = row[2]; f.f4 = row[3]; f.f5 = row[4];
+		dim3 grid((count + 255) / 256, n);
+		fir9_kernel<<<grid, 256, 0, h->stream>>>(f);
+		if ((rc = check_launch(h, "fir9_kernel")))
+			return rc;
+	}
+	CU(cudaMemsetAsync(sc.sums, 0, (size_t)n * 16, h->stream));
+	DcSumParams d;
+	d.img = sc.img;
+	d.stride = h->image_stride;
+	d.l_len = h->l_len;
+	d.sums = sc.sums;
+	int nI = (h->l_len + 1) / 2;
+	dim3 grid(std::max(1, std::min((nI + 1023) / 1024, 64)), n);
+	dc_sums_c16_kernel<<<grid, 256, 0, h->stream>>>(d);
+	return check_launch(h, "dc_sums_c16_kernel");
+}
+
+/*
+ * Process one batch of reads already on the device.  `d_desc` holds the
+ * descriptor blob (sorted read offsets, segments, hop per read).
+ */
+int launch_batch(rtlsdr_gpu_scan *h, const uint8_t *base, const uint8_t *d_desc, int n_reads, int n_segs,
+		 const std::vector<int4> *segs_host)
+{
+	DescLayout lay(n_reads, n_segs);
+	const long long *d_offs = (const long long *)(d_desc + lay.off_reads);
+	const int4 *d_segs = (const int4 *)(d_desc + lay.off_segs);
+	const int *d_hops = (const int *)(d_desc + lay.off_hops);
+	int rc = 0;
+
+	if (h->path == PATH_RMS) {
+		RmsParams p;
+		p.base = base;
+		p.read_off = d_offs;
+		p.hop_of = d_hops;
+		p.buf_len = h->cfg.buf_len;
+		p.peak = h->cfg.peak_hold;
+		p.avg = h->d_avg;
+		TimedScope ts(h);
+		rms_kernel<<<n_reads, 256, 0, h->stream>>>(p);
+		return check_launch(h, "rms_kernel");
+	}
+
+	if (h->path == PATH_SMALL_U8) {
+		SmallParams p;
+		memset(&p, 0, sizeof(p));
+		p.base = base;
+		p.read_off = d_offs;
+		p.segs = d_segs;
+		p.n_segs = n_segs;
+		p.avg = h->d_avg;
+		p.tw = h->d_tw;
+		p.win = h->d_win;
+		p.units_per_read = 1;
+		p.tw0 = h->tw0;
+		TimedScope ts(h);
+		return launch_small(h, p, false);
+	}
+
+	if (h->path == PATH_SMALL_DECIM) {
+		/* entries are processed in chunks bounded by the scratch budget; segments
+		 * never straddle a chunk because chunks are cut at segment boundaries */
+		const size_t per = DecimScratch::per_entry(h);
+		const int max_entries = (int)std::max<size_t>(1, kScratchBudget / per);
+		if (!segs_host)
+			return RTLSDR_GPU_ERR_CONFIG;
+		size_t si = 0;
+		while (si < segs_host->size()) {
+			size_t sj = si;
+			int e0 = (*segs_host)[si].y, cnt = 0;
+			while (sj < segs_host->size() && (cnt == 0 || cnt + (*segs_host)[sj].z <= max_entries)) {
+				cnt += (*segs_host)[sj].z;
+				sj++;
+			}
+			if ((rc = ensure_scratch(h, per * (size_t)cnt + 256)))
+				return rc;
+			DecimScratch sc(h, cnt);
+			TimedScope ts(h);
+			if ((rc = run_decimators(h, base, d_offs + e0, cnt, sc)))
+				return rc;
+			SmallParams p;
+			memset(&p, 0, sizeof(p));
+			p.base = (const uint8_t *)sc.img;
+			p.read_off = nullptr; /* images are regular: entry e at (e - e0) * image bytes */
+			p.regular_stride = h->image_stride * 4;
+			p.entry_base = e0;
+			p.segs = d_segs + si;
+			p.n_segs = (int)(sj - si);
+			p.avg = h->d_avg;
+			p.tw = h->d_tw;
+			p.win = h->d_win;
+			p.dc_sums = sc.sums;
+			p.l_len = h->l_len;
+			p.n_blocks = h->n_blocks;
+			p.units_per_read = h->units_per_read;
+			p.tw0 = h->tw0;
+			if ((rc = launch_small(h, p, true)))
+				return rc;
+			si = sj;
+		}
+		return 0;
+	}
+
+	/* PATH_LARGE */
+	{
+		TimedScope ts(h);
+		return large_process(h, base, d_offs, d_hops, n_reads);
+	}
+}
+
+int process_batch(rtlsdr_gpu_scan *h, const uint8_t *base, const std::vector<long long> &offs,
+		  const std::vector<int> &hops)
+{
+	const int n = (int)offs.size();
+	if (n == 0)
+		return 0;
+	std::vector<long long> s_offs;
+	std::vector<int> s_hops;
+	std::vector<int4> segs;
+	int n_segs = build_desc(h, offs, hops, s_offs, s_hops, segs);
+	DescLayout lay(n, n_segs);
+	DescSlot *slot;
+	int rc = desc_acquire(h, lay.bytes, &slot);
+	if (rc)
+		return rc;
+	uint8_t *hp = (uint8_t *)slot->h;
+	memcpy(hp + lay.off_reads, s_offs.data(), (size_t)n * 8);
+	memcpy(hp + lay.off_segs, segs.data(), (size_t)n_segs * 16);
+	memcpy(hp + lay.off_hops, s_hops.data(), (size_t)n * 4);
+	CU(cudaMemcpyAsync(slot->d, slot->h, lay.bytes, cudaMemcpyHostToDevice, h->stream));
+	rc = launch_batch(h, base, (const uint8_t *)slot->d, n, n_segs, &segs);
+	CU(cudaEventRecord(slot->done, h->stream));
+	slot->used = true;
+	if (rc)
+		return rc;
+	for (int i = 0; i < n; i++)
+		h->samples[hops[i]] += h->samples_per_read;
+	return 0;
+}
+
+int flush_ring(rtlsdr_gpu_scan *h)
+{
+	const int half = h->cur_half;
+	const int n = (int)h->ring_hops.size();
+	if (n == 0)
+		return 0;
+	const size_t B = (size_t)h->cfg.buf_len;
+	CU(cudaMemcpyAsync(h->d_ring[half], h->h_ring[half], (size_t)n * B, cudaMemcpyHostToDevice, h->stream));
+	h->h2d += (uint64_t)n * B;
+	std::vector<long long> offs(n);
+	for (int i = 0; i < n; i++)
+		offs[i] = (long long)i * (long long)B;
+	int rc = process_batch(h, h->d_ring[half], offs, h->ring_hops);
+	CU(cudaEventRecord(h->ring_done[half], h->stream));
+	h->ring_busy[half] = true;
+	h->ring_hops.clear();
+	h->cur_half ^= 1;
+	if (rc)
+		return rc;
+	if (h->ring_busy[h->cur_half]) {
+		CU(cudaEventSynchronize(h->ring_done[h->cur_half]));
+		h->ring_busy[h->cur_half] = false;
+	}
+	return 0;
+}
+
+int regular_offsets(const rtlsdr_gpu_scan *h, int hop_first, int hop_count, int passes, long long pass_stride,
+		    long long hop_stride, std::vector<long long> &offs, std::vector<int> &hops)
+{
+	if (hop_first < 0 || hop_count <= 0 || hop_first + hop_count > h->cfg.tune_count)
+		return RTLSDR_GPU_ERR_HOP;
+	if (passes <= 0)
+		return RTLSDR_GPU_ERR_CONFIG;
+	offs.resize((size_t)passes * hop_count);
+	hops.resize(offs.size());
+	size_t i = 0;
+	for (int p = 0; p < passes; p++)
+		for (int k = 0; k < hop_count; k++, i++) {
+			offs[i] = (long long)p * pass_stride + (long long)k * hop_stride;
+			hops[i] = hop_first + k;
+		}
+	return 0;
+}
+
+void free_all(rtlsdr_gpu_scan *h)
+{
+	if (!h)
+		return;
+	cudaSetDevice(h->cfg.device);
+	if (h->stream)
+		cudaStreamSynchronize(h->stream);
+	cudaFree(h->d_avg);
+	cudaFree(h->d_tw);
+	cudaFree(h->d_win);
+	cudaFree(h->d_db);
+	cudaFree(h->d_samples);
+	cudaFree(h->d_scratch);
+	cudaFree(h->d_bulk);
+	cudaFree(h->d_reg_desc);
+	if (h->h_samples_pinned)
+		cudaFreeHost(h->h_samples_pinned);
+	for (int i = 0; i < 2; i++) {
+		if (h->h_ring[i])
+			cudaFreeHost(h->h_ring[i]);
+		cudaFree(h->d_ring[i]);
+		if (h->ring_done[i])
+			cudaEventDestroy(h->ring_done[i]);
+	}
+	for (auto &s : h->desc) {
+		if (s.h)
+			cudaFreeHost(s.h);
+		cudaFree(s.d);
+		if (s.done)
+			cudaEventDestroy(s.done);
+	}
+	for (auto &p : h->timed) {
+		cudaEventDestroy(p.first);
+		cudaEventDestroy(p.second);
+	}
+	for (auto e : h->ev_pool)
+		cudaEventDestroy(e);
+	if (h->ev_a)
+		cudaEventDestroy(h->ev_a);
+	if (h->ev_b)
+		cudaEventDestroy(h->ev_b);
+	if (h->own_stream)
+		cudaStreamDestroy(h->own_stream);
+	delete h;
+}
+
+int run_epilogue(rtlsdr_gpu_scan *h, int hop0, int nhops)
+{
+	/* samples for the dB division */
+	memcpy(h->h_samples_pinned, h->samples.data(), (size_t)h->cfg.tune_count * sizeof(int));
+	CU(cudaMemcpyAsync(h->d_samples, h->h_samples_pinned, (size_t)h->cfg.tune_count * sizeof(int),
+			   cudaMemcpyHostToDevice, h->stream));
+	EpilogueParams p;
+	p.avg = h->d_avg;
+	p.samples = h->d_samples;
+	p.db = h->d_db;
+	p.bin_e = h->cfg.bin_e;
+	p.i1 = h->db_i1;
+	p.i2 = h->db_i2;
+	p.rate = h->cfg.rate;
+	p.hop0 = hop0;
+	dim3 grid((h->db_count + 255) / 256, nhops);
+	epilogue_kernel<<<grid, 256, 0, h->stream>>>(p);
+	return check_launch(h, "epilogue_kernel");
+}
+
+} // namespace
+
+/* large-FFT path needs the handle definition */
+#include "scan_large_host.inl"
+
+extern "C" {
+
+const char *rtlsdr_gpu_scan_strerror(int err)
+{
+	switch (err) {
+	case RTLSDR_GPU_OK: return "success";
+	case RTLSDR_GPU_ERR_NULL: return "null handle or argument";
+	case RTLSDR_GPU_ERR_CONFIG: return "invalid or unsupported configuration";
+	case RTLSDR_GPU_ERR_HOP: return "hop index out of range";
+	case RTLSDR_GPU_ERR_LENGTH: return "buffer length does not match buf_len";
+	case RTLSDR_GPU_ERR_NO_DEVICE: return "no usable sm_100 CUDA device";
+	case RTLSDR_GPU_ERR_CUDA: return "CUDA error";
+	case RTLSDR_GPU_ERR_NOMEM: return "out of memory";
+	case RTLSDR_GPU_ERR_ALIGN: return "device buffer or stride not 16-byte aligned";
+	default: return "unknown error";
+	}
+}
+
+const char *rtlsdr_gpu_scan_last_cuda_error(const rtlsdr_gpu_scan_t *h)
+{
+	return h ? h->last_error.c_str() : "";
+}
+
+void rtlsdr_gpu_scan_sine_table(int bin_e, int16_t *out)
+{
+	if (out && bin_e >= 0 && bin_e <= 24)
+		host_sine_table(bin_e, out);
+}
+
+int rtlsdr_gpu_scan_window(const char *name, int n, int32_t *out)
+{
+	static const struct { const char *name; window_fn fn; } tab[] = {
+		{ "rectangle", win_rectangle }, { "hamming", win_hamming }, { "blackman", win_blackman },
+		{ "blackman-harris", win_blackman_harris }, { "hann-poisson", win_hann_poisson },
+		{ "youssef", win_youssef }, { "kaiser", win_rectangle }, { "bartlett", win_bartlett },
+	};
+	window_fn fn = win_rectangle;
+	int rc = -1;
+	if (!out || n <= 0)
+		return RTLSDR_GPU_ERR_NULL;
+	for (size_t i = 0; name && i < sizeof(tab) / sizeof(tab[0]); i++)
+		if (strcmp(name, tab[i].name) == 0) {
+			fn = tab[i].fn;
+			rc = 0;
+		}
+	for (int i = 0; i < n; i++)
+		out[i] = (int32_t)(256 * fn(i, n));
+	return rc;
+}
+
+void *rtlsdr_gpu_scan_host_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+		cudaGetLastError();
+		return nullptr;
+	}
+	return p;
+}
+
+void rtlsdr_gpu_scan_host_free(void *p)
+{
+	if (p)
+		cudaFreeHost(p);
+}
+
+int rtlsdr_gpu_scan_init(const rtlsdr_gpu_scan_cfg_t *cfg, rtlsdr_gpu_scan_t **out)
+{
+	if (!cfg || !out)
+		return RTLSDR_GPU_ERR_NULL;
+	*out = nullptr;
+	if (cfg->struct_size != sizeof(rtlsdr_gpu_scan_cfg_t))
+		return RTLSDR_GPU_ERR_CONFIG;
+	if (cfg->tune_count <= 0 || cfg->tune_count > 3000 /* MAX_TUNES, rtl_power.c:113 */ ||
+	    cfg->bin_e < 0 || cfg->bin_e > 21 /* rtl_power.c:483 */ || cfg->downsample < 1 ||
+	    cfg->downsample_passes < 0 || cfg->downsample_passes > 20 || cfg->buf_len < 16 ||
+	    (cfg->buf_len & 15) || cfg->rate <= 0 || !(cfg->crop >= 0.0 && cfg->crop <= 1.0))
+		return RTLSDR_GPU_ERR_CONFIG;
+	const int N = 1 << cfg->bin_e;
+	const bool box = cfg->boxcar && cfg->downsample > 1;
+	const bool hb = !box && cfg->downsample_passes > 0;
+	if (hb && cfg->downsample != (1 << cfg->downsample_passes))
+		return RTLSDR_GPU_ERR_CONFIG;
+	if (hb && ((cfg->buf_len >> cfg->downsample_passes) < 24 || (cfg->buf_len & ((4 << cfg->downsample_passes) - 1))))
+		return RTLSDR_GPU_ERR_CONFIG;
+	if (!box && !hb && cfg->downsample != 1 && cfg->bin_e > 0) {
+		/* ds > 1 without a decimator: the reference would still divide lengths by ds
+		 * (rtl_power.c:692-695); the planner never produces this, reject it */
+		return RTLSDR_GPU_ERR_CONFIG;
+	}
+
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
+		cudaGetLastError();
+		return RTLSDR_GPU_ERR_NO_DEVICE;
+	}
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10) {
+		cudaGetLastError();
+		return RTLSDR_GPU_ERR_NO_DEVICE;
+	}
+	if (cudaSetDevice(cfg->device) != cudaSuccess) {
+		cudaGetLastError();
+		return RTLSDR_GPU_ERR_NO_DEVICE;
+	}
+
+	rtlsdr_gpu_scan *h = new (std::nothrow) rtlsdr_gpu_scan();
+	if (!h)
+		return RTLSDR_GPU_ERR_NOMEM;
+	h->cfg = *cfg;
+	h->cfg.window_coefs = nullptr;
+	h->cfg.sinewave = nullptr;
+	h->N = N;
+	h->num_sms = prop.multiProcessorCount;
+	h->samples.assign(cfg->tune_count, 0);
+
+	/* geometry of one read (rtl_power.c:692-695, 717) */
+	if (cfg->bin_e == 0) {
+		h->path = PATH_RMS;
+		h->samples_per_read = 1;
+	} else {
+		h->l_len = cfg->buf_len / cfg->downsample;
+		h->n_blocks = (h->l_len + 2 * N - 1) / (2 * N);
+		h->samples_per_read = h->n_blocks * cfg->downsample;
+		if (cfg->bin_e <= 12) {
+			if (!box && !hb) {
+				if (cfg->buf_len != kStageBytes) {
+					delete h;
+					return RTLSDR_GPU_ERR_CONFIG; /* planner gives 16384 whenever 2N <= 16384 (rtl_power.c:501-504) */
+				}
+				h->path = PATH_SMALL_U8;
+			} else {
+				h->path = PATH_SMALL_DECIM;
+				h->units_per_read = (int)(((long long)h->n_blocks * N + kWS - 1) / kWS);
+				h->image_stride = (long long)h->units_per_read * kWS;
+			}
+		} else {
+			h->path = PATH_LARGE;
+			if (h->n_blocks != 1 || (box || hb ? h->l_len != 2 * N : cfg->buf_len != 2 * N)) {
+				delete h;
+				return RTLSDR_GPU_ERR_CONFIG; /* 2N*ds >= 16384 always holds here, so one block per read */
+			}
+			h->image_stride = N;
+		}
+	}
+	/* what csv_dbm prints (rtl_power.c:741-748) */
+	h->db_i1 = 0 + (int)((double)N * cfg->crop * 0.5);
+	h->db_i2 = (N - 1) - (int)((double)N * cfg->crop * 0.5);
+	if (h->db_i2 < h->db_i1) {
+		delete h;
+		return RTLSDR_GPU_ERR_CONFIG;
+	}
+	h->db_count = h->db_i2 - h->db_i1 + 2;
+
+	int rc = RTLSDR_GPU_ERR_CUDA;
+	do {
+		if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+			break;
+		h->stream = h->own_stream;
+		const size_t avg_bytes = (size_t)cfg->tune_count * N * sizeof(long long);
+		if (cudaMalloc(&h->d_avg, avg_bytes) != cudaSuccess ||
+		    cudaMalloc(&h->d_db, (size_t)cfg->tune_count * h->db_count * sizeof(double)) != cudaSuccess ||
+		    cudaMalloc(&h->d_samples, (size_t)cfg->tune_count * sizeof(int)) != cudaSuccess ||
+		    cudaMallocHost(&h->h_samples_pinned, (size_t)cfg->tune_count * sizeof(int)) != cudaSuccess) {
+			rc = RTLSDR_GPU_ERR_NOMEM;
+			break;
+		}
+		if (cudaMemsetAsync(h->d_avg, 0, avg_bytes, h->stream) != cudaSuccess)
+			break;
+
+		if (cfg->bin_e > 0) {
+			/* twiddles: wr = Sinewave[j+N/4] >> 1, wi = (-Sinewave[j]) >> 1 (rtl_power.c:305-308) */
+			std::vector<int16_t> sine((size_t)N * 3 / 4 + 4, 0);
+			if (cfg->sinewave)
+				memcpy(sine.data(), cfg->sinewave, ((size_t)N * 3 / 4) * sizeof(int16_t));
+			else
+				host_sine_table(cfg->bin_e, sine.data());
+			const int half = std::max(N / 2, 1);
+			h->tw_host.resize(half);
+			for (int j = 0; j < half; j++) {
+				int16_t wr = (int16_t)(sine[j + N / 4] >> 1);
+				int16_t wi = (int16_t)((int16_t)(-sine[j]) >> 1);
+				h->tw_host[j] = make_int2(wr, wi);
+			}
+			memset(&h->tw0, 0, sizeof(h->tw0));
+			for (int b = 0; b < 4 && b < cfg->bin_e; b++)
+				for (int g = 0; g < (1 << b); g++)
+					h->tw0.w[(1 << b) - 1 + g] = h->tw_host[(size_t)g << (cfg->bin_e - 1 - b)];
+			std::vector<uint16_t> win(N);
+			for (int i = 0; i < N; i++)
+				win[i] = (uint16_t)((cfg->window_coefs ? cfg->window_coefs[i] : 256) & 0xFFFF);
+			if (cudaMalloc(&h->d_tw, (size_t)half * sizeof(int2)) != cudaSuccess ||
+			    cudaMalloc(&h->d_win, (size_t)N * sizeof(uint16_t)) != cudaSuccess) {
+				rc = RTLSDR_GPU_ERR_NOMEM;
+				break;
+			}
+			if (cudaMemcpy(h->d_tw, h->tw_host.data(), (size_t)half * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess ||
+			    cudaMemcpy(h->d_win, win.data(), (size_t)N * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess)
+				break;
+		}
+
+		/* staging ring */
+		size_t ring = cfg->ring_bytes ? cfg->ring_bytes : kDefaultRing;
+		const size_t B = (size_t)cfg->buf_len;
+		h->ring_reads = (int)std::max<size_t>(1, ring / B);
+		h->ring_bytes = (size_t)h->ring_reads * B;
+		bool ok = true;
+		for (int i = 0; i < 2 && ok; i++) {
+			ok = cudaMallocHost(&h->h_ring[i], h->ring_bytes) == cudaSuccess &&
+			     cudaMalloc(&h->d_ring[i], h->ring_bytes) == cudaSuccess &&
+			     cudaEventCreateWithFlags(&h->ring_done[i], cudaEventDisableTiming) == cudaSuccess;
+		}
+		if (!ok) {
+			rc = RTLSDR_GPU_ERR_NOMEM;
+			break;
+		}
+		h->ring_hops.reserve(h->ring_reads);
+		if (cudaStreamSynchronize(h->stream) != cudaSuccess)
+			break;
+		rc = 0;
+	} while (0);
+	if (rc) {
+		cudaGetLastError();
+		free_all(h);
+		return rc;
+	}
+	*out = h;
+	return 0;
+}
+
+void rtlsdr_gpu_scan_close(rtlsdr_gpu_scan_t *h)
+{
+	free_all(h);
+}
+
+int rtlsdr_gpu_scan_set_stream(rtlsdr_gpu_scan_t *h, void *cuda_stream)
+{
+	if (!h)
+		return RTLSDR_GPU_ERR_NULL;
+	CU(cudaSetDevice(h->cfg.device));
+	CU(cudaStreamSynchronize(h->stream));
+	h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+	return 0;
+}
+
+int rtlsdr_gpu_scan_submit(rtlsdr_gpu_scan_t *h, int hop, const uint8_t *buf, uint32_t len)
+{
+	if (!h || !buf)
+		return RTLSDR_GPU_ERR_NULL;
+	if (hop < 0 || hop >= h->cfg.tune_count)
+		return RTLSDR_GPU_ERR_HOP;
+	if (len != (uint32_t)h->cfg.buf_len)
+		return RTLSDR_GPU_ERR_LENGTH;
+	const size_t B = (size_t)h->cfg.buf_len;
+	memcpy(h->h_ring[h->cur_half] + h->ring_hops.size() * B, buf, B);
+	h->ring_hops.push_back(hop);
+	if ((int)h->ring_hops.size() >= h->ring_reads) {
+		CU(cudaSetDevice(h->cfg.device));
+		return flush_ring(h);
+	}
+	return 0;
+}
+
+int rtlsdr_gpu_scan_flush(rtlsdr_gpu_scan_t *h)
+{
+	if (!h)
+		return RTLSDR_GPU_ERR_NULL;
+	CU(cudaSetDevice(h->cfg.device));
+	return flush_ring(h);
+}
+
+int rtlsdr_gpu_scan_sync(rtlsdr_gpu_scan_t *h)
+{
+	if (!h)
+		return RTLSDR_GPU_ERR_NULL;
+	CU(cudaSetDevice(h->cfg.device));
+	int rc = flush_ring(h);
+	if (rc)
+		return rc;
+	CU(cudaStreamSynchronize(h->stream));
+	return 0;
+}
+
+int rtlsdr_gpu_scan_submit_device(rtlsdr_gpu_scan_t *h, int hop_first, int hop_count, int passes,
+				  const void *dev_buf, int64_t pass_stride, int64_t hop_stride)
+{
+	if (!h || !dev_buf)
+		return RTLSDR_GPU_ERR_NULL;
+	if (((uintptr_t)dev_buf & 15) || (pass_stride & 15) || (hop_stride & 15))
+		return RTLSDR_GPU_ERR_ALIGN;
+	CU(cudaSetDevice(h->cfg.device));
+	int rc = flush_ring(h); /* keep submission order */
+	if (rc)
+		return rc;
+
+	RegularKey key;
+	key.base = dev_buf;
+	key.hop_first = hop_first;
+	key.hop_count = hop_count;
+	key.passes = passes;
+	key.pass_stride = pass_stride;
+	key.hop_stride = hop_stride;
+	key.valid = true;
+	const bool cacheable = h->path != PATH_SMALL_DECIM; /* decim path re-walks host segments */
+	if (cacheable && key == h->reg_key) {
+		rc = launch_batch(h, (const uint8_t *)dev_buf, (const uint8_t *)h->d_reg_desc, h->reg_key.n_reads,
+				  h->reg_key.n_segs, nullptr);
+		if (rc)
+			return rc;
+		for (int k = 0; k < hop_count; k++)
+			h->samples[hop_first + k] += h->samples_per_read * passes;
+		return 0;
+	}
+	std::vector<long long> offs;
+	std::vector<int> hops;
+	rc = regular_offsets(h, hop_first, hop_count, passes, pass_stride, hop_stride, offs, hops);
+	if (rc)
+		return rc;
+	if (!cacheable)
+		return process_batch(h, (const uint8_t *)dev_buf, offs, hops);
+
+	std::vector<long long> s_offs;
+	std::vector<int> s_hops;
+	std::vector<int4> segs;
+	const int n = (int)offs.size();
+	const int n_segs = build_desc(h, offs, hops, s_offs, s_hops, segs);
+	DescLayout lay(n, n_segs);
+	if (h->reg_desc_cap < lay.bytes) {
+		CU(cudaStreamSynchronize(h->stream));
+		cudaFree(h->d_reg_desc);
+		h->d_reg_desc = nullptr;
+		h->reg_desc_cap = 0;
+		CU(cudaMalloc(&h->d_reg_desc, lay.bytes));
+		h->reg_desc_cap = lay.bytes;
+	}
+	h->reg_key.valid = false;
+	DescSlot *slot;
+	if ((rc = desc_acquire(h, lay.bytes, &slot)))
+		return rc;
+	uint8_t *hp = (uint8_t *)slot->h;
+	memcpy(hp + lay.off_reads, s_offs.data(), (size_t)n * 8);
+	memcpy(hp + lay.off_segs, segs.data(), (size_t)n_segs * 16);
+	memcpy(hp + lay.off_hops, s_hops.data(), (size_t)n * 4);
+	CU(cudaMemcpyAsync(h->d_reg_desc, slot->h, lay.bytes, cudaMemcpyHostToDevice, h->stream));
+	CU(cudaEventRecord(slot->done, h->stream));
+	slot->used = true;
+	key.n_reads = n;
+	key.n_segs = n_segs;
+	h->reg_key = key;
+	rc = launch_batch(h, (const uint8_t *)dev_buf, (const uint8_t *)h->d_reg_desc, n, n_segs, &segs);
+	if (rc)
+		return rc;
+	for (int i = 0; i < n; i++)
+		h->samples[hops[i]] += h->samples_per_read;
+	return 0;
+}
+
+int rtlsdr_gpu_scan_submit_batch(rtlsdr_gpu_scan_t *h, int hop_first, int hop_count, int passes,
+				 const uint8_t *buf, int64_t pass_stride, int64_t hop_stride)
+{
+	if (!h || !buf)
+		return RTLSDR_GPU_ERR_NULL;
+	if ((pass_stride & 15) || (hop_stride & 15) || ((uintptr_t)buf & 15))
+		return RTLSDR_GPU_ERR_ALIGN;
+	if (hop_first < 0 || hop_count <= 0 || hop_first + hop_count > h->cfg.tune_count)
+		return RTLSDR_GPU_ERR_HOP;
+	if (passes <= 0 || pass_stride < 0 || hop_stride < 0)
+		return RTLSDR_GPU_ERR_CONFIG;
+	CU(cudaSetDevice(h->cfg.device));
+	/* extent of the strided region */
+	const size_t B = (size_t)h->cfg.buf_len;
+	const size_t extent = (size_t)(passes - 1) * (size_t)pass_stride + (size_t)(hop_count - 1) * (size_t)hop_stride + B;
+	if (h->bulk_bytes < extent) {
+		CU(cudaStreamSynchronize(h->stream));
+		cudaFree(h->d_bulk);
+		h->d_bulk = nullptr;
+		h->bulk_bytes = 0;
+		if (cudaMalloc(&h->d_bulk, extent) != cudaSuccess) {
+			cudaGetLastError();
+			return RTLSDR_GPU_ERR_NOMEM;
+		}
+		h->bulk_bytes = extent;
+		h->reg_key.valid = false;
+	}
+	int rc = flush_ring(h);
+	if (rc)
+		return rc;
+	CU(cudaMemcpyAsync(h->d_bulk, buf, extent, cudaMemcpyHostToDevice, h->stream));
+	h->h2d += extent;
+	return rtlsdr_gpu_scan_submit_device(h, hop_first, hop_count, passes, h->d_bulk, pass_stride, hop_stride);
+}
+
+int rtlsdr_gpu_scan_db_count(const rtlsdr_gpu_scan_t *h)
+{
+	return h ? h->db_count : RTLSDR_GPU_ERR_NULL;
+}
+
+static int collect_range(rtlsdr_gpu_scan_t *h, int hop0, int nhops, int64_t *avg, int *samples, double *db)
+{
+	CU(cudaSetDevice(h->cfg.device));
+	int rc = flush_ring(h);
+	if (rc)
+		return rc;
+	const size_t N = (size_t)h->N;
+	if (db) {
+		if ((rc = run_epilogue(h, hop0, nhops)))
+			return rc;
+		CU(cudaMemcpyAsync(db, h->d_db + (size_t)hop0 * h->db_count, (size_t)nhops * h->db_count * sizeof(double),
+				   cudaMemcpyDeviceToHost, h->stream));
+		h->d2h += (uint64_t)nhops * h->db_count * sizeof(double);
+	}
+	if (avg) {
+		CU(cudaMemcpyAsync(avg, h->d_avg + (size_t)hop0 * N, (size_t)nhops * N * sizeof(long long),
+				   cudaMemcpyDeviceToHost, h->stream));
+		h->d2h += (uint64_t)nhops * N * sizeof(long long);
+	}
+	CU(cudaMemsetAsync(h->d_avg + (size_t)hop0 * N, 0, (size_t)nhops * N * sizeof(long long), h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	for (int i = 0; i < nhops; i++) {
+		if (samples)
+			samples[i] = h->samples[hop0 + i];
+		h->samples[hop0 + i] = 0;
+	}
+	return 0;
+}
+
+int rtlsdr_gpu_scan_collect(rtlsdr_gpu_scan_t *h, int hop, int64_t *avg, int *samples, double *db)
+{
+	if (!h)
+		return RTLSDR_GPU_ERR_NULL;
+	if (hop < 0 || hop >= h->cfg.tune_count)
+		return RTLSDR_GPU_ERR_HOP;
+	return collect_range(h, hop, 1, avg, samples, db);
+}
+
+int rtlsdr_gpu_scan_collect_all(rtlsdr_gpu_scan_t *h, int64_t *avg, int *samples, double *db)
+{
+	if (!h)
+		return RTLSDR_GPU_ERR_NULL;
+	return collect_range(h, 0, h->cfg.tune_count, avg, samples, db);
+}
+
+int rtlsdr_gpu_scan_collect_device(rtlsdr_gpu_scan_t *h, void *dev_avg, void *dev_samples, void *dev_db)
+{
+	if (!h)
+		return RTLSDR_GPU_ERR_NULL;
+	CU(cudaSetDevice(h->cfg.device));
+	int rc = flush_ring(h);
+	if (rc)
+		return rc;
+	const size_t N = (size_t)h->N, tc = (size_t)h->cfg.tune_count;
+	if ((rc = run_epilogue(h, 0, (int)tc)))
+		return rc;
+	if (dev_db)
+		CU(cudaMemcpyAsync(dev_db, h->d_db, tc * h->db_count * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+	if (dev_samples)
+		CU(cudaMemcpyAsync(dev_samples, h->d_samples, tc * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+	if (dev_avg)
+		CU(cudaMemcpyAsync(dev_avg, h->d_avg, tc * N * sizeof(long long), cudaMemcpyDeviceToDevice, h->stream));
+	CU(cudaMemsetAsync(h->d_avg, 0, tc * N * sizeof(long long), h->stream));
+	std::fill(h->samples.begin(), h->samples.end(), 0);
+	return 0;
+}
+
+int rtlsdr_gpu_scan_stats(const rtlsdr_gpu_scan_t *h, uint64_t *kernel_launches, uint64_t *h2d_bytes, uint64_t *d2h_bytes)
+{
+	if (!h)
+		return RTLSDR_GPU_ERR_NULL;
+	if (kernel_launches)
+		*kernel_launches = h->launches;
+	if (h2d_bytes)
+		*h2d_bytes = h->h2d;
+	if (d2h_bytes)
+		*d2h_bytes = h->d2h;
+	return 0;
+}
+
+int rtlsdr_gpu_scan_kernel_time(rtlsdr_gpu_scan_t *h, double *ms, uint64_t *launches)
+{
+	if (!h)
+		return RTLSDR_GPU_ERR_NULL;
+	CU(cudaSetDevice(h->cfg.device));
+	double total = 0;
+	uint64_t n = 0;
+	if (h->timing) {
+		CU(cudaStreamSynchronize(h->stream));
+		for (auto &p : h->timed) {
+			float t = 0;
+			if (cudaEventElapsedTime(&t, p.first, p.second) == cudaSuccess) {
+				total += t;
+				n++;
+			}
+			h->ev_pool.push_back(p.first);
+			h->ev_pool.push_back(p.second);
+		}
+		h->timed.clear();
+	}
+	h->timing = true; /* first call arms the timers */
+	if (ms)
+		*ms = total;
+	if (launches)
+		*launches = n;
+	return 0;
+}
+
+} /* extern "C" */

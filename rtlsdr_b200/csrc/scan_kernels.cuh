@@ -1,0 +1,718 @@
+/*
+ * scan_kernels.cuh -- sm_100a kernels for rtl_power's per-hop scan pipeline.
+ *
+ * Reference semantics reproduced bit-for-bit (file:line in /root/reference):
+ *   u8 -> int16 minus 127                      src/rtl_power.c:666-668
+ *   boxcar decimation                          src/rtl_power.c:671-681
+ *   fifth_order x downsample_passes            src/rtl_power.c:554-579, 628-634, 683-685
+ *   generic_fir (9-tap droop compensation)     src/rtl_power.c:598-626, 687-690
+ *   remove_dc over the whole read buffer       src/rtl_power.c:581-596, 692-693
+ *   window multiply (int16 truncation)         src/rtl_power.c:695-706
+ *   fix_fft: Q15 radix-2 DIT, FIX_MPY rounding,
+ *            halving on every stage             src/rtl_power.c:263-327
+ *   |X|^2 int64 accumulate / peak hold         src/rtl_power.c:636-640, 708-716
+ *   rms_power for 1-bin hops                   src/rtl_power.c:410-436
+ *   csv_dbm numeric half (DC nuke, half swap,
+ *            crop, dB)                          src/rtl_power.c:722-760
+ *
+ * Design (B200-first, no tensor cores: this is integer butterfly work):
+ *  - A complex int16 sample is ONE 32-bit register (re low, im high), the same
+ *    bytes as the reference's interleaved int16 buffer.
+ *  - Each thread keeps 16 samples in registers and runs 4 consecutive radix-2
+ *    stages on them ("register-blocked radix-16", with the reference's per-stage
+ *    rounding, halving and int16 wrap intact -- no algebraic radix-4).  A CTA of
+ *    256 threads therefore owns a 4096-sample working set; three passes with two
+ *    padded shared-memory transposes cover 12 stages.
+ *  - Input arrives with 16-byte cp.async (LDGSTS) copies into a double-buffered
+ *    shared staging area; the next read is in flight while the current one is
+ *    transformed.
+ *  - |X|^2 is accumulated in registers across all the reads a CTA owns and
+ *    flushed once with 64-bit atomics.
+ */
+#pragma once
+#include "scan_compat.cuh"
+
+namespace rscan {
+
+typedef uint32_t c16; /* packed complex int16: re = bits 0..15, im = bits 16..31 */
+
+constexpr int kThreads = 256;                 /* threads per CTA */
+constexpr int kPts     = 16;                  /* samples per thread */
+constexpr int kWS      = kThreads * kPts;     /* 4096-sample working set */
+constexpr int kStageBytes = 16384;            /* one staging slot */
+constexpr int kXchWords   = kWS + kWS / 16;   /* transpose buffer, 1 pad word per 16 */
+
+/* ---- packed helpers ---------------------------------------------------- */
+
+SCAN_DEV int c16_re(c16 v) { return (int)(int16_t)(uint16_t)(v & 0xFFFFu); }
+SCAN_DEV int c16_im(c16 v) { return ((int32_t)v) >> 16; }
+SCAN_DEV c16 c16_pack(int re, int im) { return ((uint32_t)re & 0xFFFFu) | ((uint32_t)im << 16); }
+
+/* FIX_MPY (rtl_power.c:263-269): ((a*b)>>14 ; (c>>1)+(c&1)) == (a*b + 2^14) >> 15 */
+SCAN_DEV int fix_mpy(int w, int x) { return (w * x + 16384) >> 15; }
+
+/*
+ * One radix-2 DIT butterfly of fix_fft (rtl_power.c:309-321) on packed values.
+ * (wr, wi) is the twiddle AFTER its halving (wr = Sinewave[j+N/4] >> 1,
+ * wi = (-Sinewave[j]) >> 1, rtl_power.c:305-308).  tr/ti cannot leave int16
+ * (|w| <= 16384); the four q +- t results wrap to int16 in c16_pack.
+ */
+SCAN_DEV void butterfly(c16 &a, c16 &b, int wr, int wi)
+{
+	const int br = c16_re(b), bi = c16_im(b);
+	const int tr = fix_mpy(wr, br) - fix_mpy(wi, bi);
+	const int ti = fix_mpy(wr, bi) + fix_mpy(wi, br);
+	const int qr = c16_re(a) >> 1, qi = c16_im(a) >> 1;
+	b = c16_pack(qr - tr, qi - ti);
+	a = c16_pack(qr + tr, qi + ti);
+}
+
+/* ---- working-set geometry ---------------------------------------------- */
+
+/* Position (0..4095) of register r of thread t while pass K is in registers:
+ * r supplies bits [4K, 4K+4) of the position, t supplies the rest. */
+template <int K>
+SCAN_DEV int pos(int t, int r)
+{
+	constexpr int sh = 4 * K;
+	return ((t >> sh) << (sh + 4)) | (r << sh) | (t & ((1 << sh) - 1));
+}
+
+SCAN_DEV int xch_idx(int p) { return p + (p >> 4); }
+
+SCAN_DEV constexpr int brev4(int r)
+{
+	return ((r & 1) << 3) | ((r & 2) << 1) | ((r & 4) >> 1) | ((r & 8) >> 3);
+}
+
+SCAN_DEV int brev_bits(unsigned v, int bits)
+{
+	return bits <= 0 ? 0 : (int)(__brev(v) >> (32 - bits));
+}
+
+/*
+ * Passes of the engine.  LE = number of radix-2 stages the engine runs on the
+ * low LE bits of the position (LE <= 12).  Pass K covers stages
+ * [4K, min(4K+4, LE)).  TW::get<K>(s, pa) returns the halved twiddle of stage s
+ * for the butterfly whose upper ("a") element sits at position pa.
+ */
+template <int K, int LE, class TW>
+SCAN_DEV void run_pass(c16 (&v)[kPts], int t, const TW &tw)
+{
+	constexpr int s0 = 4 * K;
+	constexpr int ns = (LE - s0) < 4 ? (LE - s0) : 4;
+#pragma unroll
+	for (int b = 0; b < ns; ++b) {
+#pragma unroll
+		for (int r = 0; r < kPts; ++r) {
+			if ((r & (1 << b)) == 0) {
+				const int2 w = tw.template get<K>(s0 + b, pos<K>(t, r));
+				butterfly(v[r], v[r | (1 << b)], w.x, w.y);
+			}
+		}
+	}
+}
+
+template <int KA, int KB>
+SCAN_DEV void exchange(c16 (&v)[kPts], c16 *xch, int t)
+{
+	__syncthreads(); /* every reader of the previous transpose is done */
+#pragma unroll
+	for (int r = 0; r < kPts; ++r)
+		xch[xch_idx(pos<KA>(t, r))] = v[r];
+	__syncthreads();
+#pragma unroll
+	for (int r = 0; r < kPts; ++r)
+		v[r] = xch[xch_idx(pos<KB>(t, r))];
+}
+
+/* Runs stages 0..LE-1; on return register r of thread t holds position
+ * pos<(LE-1)/4>(t, r). */
+template <int LE, class TW>
+SCAN_DEV void engine_fft(c16 (&v)[kPts], c16 *xch, int t, const TW &tw)
+{
+	run_pass<0, LE>(v, t, tw);
+	if constexpr (LE > 4) {
+		exchange<0, 1>(v, xch, t);
+		run_pass<1, LE>(v, t, tw);
+	}
+	if constexpr (LE > 8) {
+		exchange<1, 2>(v, xch, t);
+		run_pass<2, LE>(v, t, tw);
+	}
+}
+
+template <int LE>
+SCAN_DEV int last_pos(int t, int r)
+{
+	return pos<(LE - 1) / 4>(t, r);
+}
+
+/* ======================================================================== *
+ *  Path 1: N <= 4096.  One CTA owns whole read buffers of one hop.          *
+ * ======================================================================== */
+
+struct PassTw {
+	int2 w[15]; /* pass-0 twiddles: stage b, group g at w[(1<<b)-1+g] */
+};
+
+struct SmallParams {
+	const uint8_t *base;        /* u8 reads, or (IN16) decimated c16 images */
+	const long long *read_off;  /* byte offset of entry e from base; NULL = regular */
+	long long regular_stride;   /* read_off == NULL: entry e at (e - entry_base) * regular_stride */
+	int entry_base;             /* first entry of this launch (IN16 images / dc_sums are relative to it) */
+	const int4 *segs;           /* (hop, first entry, entry count, -) */
+	int n_segs;
+	long long *avg;             /* [tune_count << L] */
+	const int2 *tw;             /* [N/2] halved twiddles (wr, wi) */
+	const uint16_t *win;        /* [N] low 16 bits of window_coefs */
+	/* IN16 only */
+	const long long *dc_sums;   /* [entry - entry_base][2]: sums the reference's remove_dc sees */
+	int l_len;                  /* buf_len / downsample (interleaved int16 count) */
+	int n_blocks;               /* FFT blocks per read */
+	int units_per_read;         /* 4096-sample working sets per decimated image */
+	PassTw tw0;
+};
+
+template <int L>
+struct SmallSmem {
+	static constexpr int N = 1 << L;
+	static constexpr int off_stage = 0;
+	static constexpr int off_xch = 2 * kStageBytes;
+	static constexpr int off_tw = off_xch + kXchWords * 4;
+	static constexpr int off_win = off_tw + (N / 2 > 0 ? N / 2 : 1) * 8;
+	static constexpr int off_red = (off_win + N * 2 + 15) & ~15;
+	static constexpr int bytes = off_red + 128;
+};
+
+template <int L>
+struct TwSmall {
+	const int2 *tws;
+	const PassTw *tw0;
+	template <int K>
+	SCAN_DEV int2 get(int s, int pa) const
+	{
+		const int m = pa & ((1 << s) - 1);
+		if constexpr (K == 0)
+			return tw0->w[(1 << s) - 1 + m]; /* compile-time index: constant bank */
+		else
+			return tws[m << (L - 1 - s)];
+	}
+};
+
+SCAN_DEV long long entry_offset(const SmallParams &prm, int e)
+{
+	return prm.read_off ? prm.read_off[e] : (long long)(e - prm.entry_base) * prm.regular_stride;
+}
+
+/* rtl_power.c:581-596 divides by the INTERLEAVED length and truncates toward 0 */
+SCAN_DEV int dc_average(long long sum, int length)
+{
+	return (int)(int16_t)(sum / (long long)length);
+}
+
+template <int L, bool PEAK, bool IN16>
+__global__ void __launch_bounds__(kThreads, 2)
+scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
+{
+	SCAN_DYN_SMEM(smem);
+	typedef SmallSmem<L> SM;
+	constexpr int N = 1 << L;
+	constexpr int KL = (L - 1) / 4;
+	uint8_t *stage = smem + SM::off_stage;
+	c16 *xch = (c16 *)(smem + SM::off_xch);
+	int2 *tws = (int2 *)(smem + SM::off_tw);
+	uint16_t *wins = (uint16_t *)(smem + SM::off_win);
+	long long *red = (long long *)(smem + SM::off_red); /* [8 warps][2] then K_I, K_Q */
+	int *dck = (int *)(red + 16);
+
+	const int t = threadIdx.x;
+	for (int i = t; i < N / 2; i += kThreads)
+		tws[i] = prm.tw[i];
+	for (int i = t; i < N; i += kThreads)
+		wins[i] = prm.win[i];
+
+	TwSmall<L> tw;
+	tw.tws = tws;
+	tw.tw0 = &prm.tw0;
+
+	/* sample index (inside its FFT block) that feeds position (16t + r), minus
+	 * the r-dependent part: n = blkbase + (brev4(r) << (L-4)) + trev   (L >= 4) */
+	int trev = 0, blkbase = 0;
+	if constexpr (L >= 4) {
+		trev = brev_bits((unsigned)(t & ((1 << (L - 4)) - 1)), L - 4);
+		blkbase = (t >> (L - 4)) << L;
+	}
+
+	constexpr int kWsPerUnit = IN16 ? 1 : 2; /* a 16 KiB slot = 8192 u8 pairs or 4096 c16 */
+
+	for (int seg = blockIdx.x; seg < prm.n_segs; seg += gridDim.x) {
+		const int4 sg = prm.segs[seg];
+		const int hop = sg.x, first = sg.y;
+		const int units = IN16 ? sg.z * prm.units_per_read : sg.z;
+
+		unsigned long long acc[kPts];
+#pragma unroll
+		for (int r = 0; r < kPts; ++r)
+			acc[r] = 0ull;
+
+		/* prefetch unit 0 */
+		{
+			const uint8_t *src = prm.base + entry_offset(prm, first);
+#pragma unroll
+			for (int i = 0; i < kStageBytes / (kThreads * 16); ++i)
+				cp_async16(stage + (i * kThreads + t) * 16, src + (i * kThreads + t) * 16);
+			cp_async_commit();
+		}
+
+		for (int u = 0; u < units; ++u) {
+			cp_async_wait_all();
+			__syncthreads(); /* slot u&1 landed; slot (u+1)&1 no longer read */
+			if (u + 1 < units) {
+				int e = first + (IN16 ? (u + 1) / prm.units_per_read : (u + 1));
+				long long o = entry_offset(prm, e);
+				if (IN16)
+					o += (long long)((u + 1) % prm.units_per_read) * kStageBytes;
+				const uint8_t *src = prm.base + o;
+				uint8_t *dst = stage + ((u + 1) & 1) * kStageBytes;
+#pragma unroll
+				for (int i = 0; i < kStageBytes / (kThreads * 16); ++i)
+					cp_async16(dst + (i * kThreads + t) * 16, src + (i * kThreads + t) * 16);
+				cp_async_commit();
+			}
+			const uint8_t *st = stage + (u & 1) * kStageBytes;
+
+			/* ---- DC term of the whole read (rtl_power.c:692-693) ---- */
+			int limI = kWS, limQ = kWS, nvalid = kWS / N;
+			if constexpr (!IN16) {
+				unsigned sI = 0, sQ = 0;
+#pragma unroll
+				for (int i = 0; i < kStageBytes / (kThreads * 16); ++i) {
+					const uint4 q = *(const uint4 *)(st + (i * kThreads + t) * 16);
+					sI = __dp4a(q.x, 0x00010001u, sI);
+					sQ = __dp4a(q.x, 0x01000100u, sQ);
+					sI = __dp4a(q.y, 0x00010001u, sI);
+					sQ = __dp4a(q.y, 0x01000100u, sQ);
+					sI = __dp4a(q.z, 0x00010001u, sI);
+					sQ = __dp4a(q.z, 0x01000100u, sQ);
+					sI = __dp4a(q.w, 0x00010001u, sI);
+					sQ = __dp4a(q.w, 0x01000100u, sQ);
+				}
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) {
+					sI += __shfl_xor_sync(0xffffffffu, sI, o);
+					sQ += __shfl_xor_sync(0xffffffffu, sQ, o);
+				}
+				if ((t & 31) == 0) {
+					red[(t >> 5) * 2 + 0] = (long long)sI;
+					red[(t >> 5) * 2 + 1] = (long long)sQ;
+				}
+				__syncthreads();
+				if (t < 2) {
+					long long s = 0;
+#pragma unroll
+					for (int w = 0; w < kThreads / 32; ++w)
+						s += red[w * 2 + t];
+					s -= 127ll * (kStageBytes / 2); /* sum of (b - 127) */
+					dck[t] = 127 + dc_average(s, kStageBytes - t);
+				}
+				__syncthreads();
+			} else {
+				const int e = first + u / prm.units_per_read;
+				const int w = u % prm.units_per_read;
+				if (t < 2)
+					dck[t] = dc_average(prm.dc_sums[2 * (e - prm.entry_base) + t], prm.l_len - t);
+				limI = ((prm.l_len + 1) >> 1) - w * kWS;
+				limQ = (prm.l_len >> 1) - w * kWS;
+				nvalid = prm.n_blocks - w * (kWS / N);
+				__syncthreads();
+			}
+			const int kI = dck[0], kQ = dck[1];
+
+#pragma unroll 1
+			for (int ws = 0; ws < kWsPerUnit; ++ws) {
+				c16 v[kPts];
+				/* ---- convert, remove DC, window, bit-reversed placement ---- */
+#pragma unroll
+				for (int r = 0; r < kPts; ++r) {
+					int nblk, n; /* sample index inside its block / inside the working set */
+					if constexpr (L >= 4) {
+						nblk = (brev4(r) << (L - 4)) + trev;
+						n = blkbase + nblk;
+					} else {
+						nblk = brev_bits((unsigned)(r & (N - 1)), L);
+						n = (t << 4) + (r & ~(N - 1)) + nblk;
+					}
+					const int wv = wins[nblk];
+					int re, im;
+					if constexpr (!IN16) {
+						const unsigned raw = ((const uint16_t *)st)[ws * kWS + n];
+						re = ((int)(raw & 0xFFu) - kI) * wv;
+						im = ((int)(raw >> 8) - kQ) * wv;
+					} else {
+						const c16 raw = ((const c16 *)st)[n];
+						re = c16_re(raw);
+						im = c16_im(raw);
+						if (n < limI)
+							re -= kI;
+						if (n < limQ)
+							im -= kQ;
+						re *= wv;
+						im *= wv;
+					}
+					v[r] = c16_pack(re, im);
+				}
+
+				engine_fft<L>(v, xch, t, tw);
+
+				/* ---- |X|^2 (rtl_power.c:636-640, 708-716) ---- */
+#pragma unroll
+				for (int r = 0; r < kPts; ++r) {
+					const int re = c16_re(v[r]), im = c16_im(v[r]);
+					const unsigned pw = (unsigned)(re * re) + (unsigned)(im * im);
+					bool ok = true;
+					if constexpr (IN16)
+						ok = (last_pos<L>(t, r) >> L) < nvalid;
+					if (ok) {
+						if constexpr (PEAK)
+							acc[r] = acc[r] > pw ? acc[r] : (unsigned long long)pw;
+						else
+							acc[r] += pw;
+					}
+				}
+			}
+		}
+
+		/* ---- flush this segment's sums ---- */
+		long long *out = prm.avg + ((long long)hop << L);
+		if constexpr (L == 12) {
+#pragma unroll
+			for (int r = 0; r < kPts; ++r) {
+				const int bin = last_pos<L>(t, r) & (N - 1);
+				if constexpr (PEAK)
+					atomicMax(out + bin, (long long)acc[r]);
+				else
+					atomicAdd((unsigned long long *)(out + bin), acc[r]);
+			}
+		} else {
+			/* several registers of the CTA share a bin: combine in shared first */
+			unsigned long long *bins = (unsigned long long *)stage;
+			__syncthreads();
+			for (int i = t; i < N; i += kThreads)
+				bins[i] = 0ull;
+			__syncthreads();
+#pragma unroll
+			for (int r = 0; r < kPts; ++r) {
+				const int bin = last_pos<L>(t, r) & (N - 1);
+				if constexpr (PEAK)
+					atomicMax(bins + bin, acc[r]);
+				else
+					atomicAdd(bins + bin, acc[r]);
+			}
+			__syncthreads();
+			for (int i = t; i < N; i += kThreads) {
+				if constexpr (PEAK)
+					atomicMax(out + i, (long long)bins[i]);
+				else
+					atomicAdd((unsigned long long *)(out + i), bins[i]);
+			}
+			__syncthreads();
+		}
+	}
+}
+
+/* ======================================================================== *
+ *  Decimating front ends (narrow scans): u8 reads -> c16 images             *
+ * ======================================================================== */
+
+struct DecimParams {
+	const uint8_t *base;       /* u8 reads */
+	const long long *read_off; /* byte offset of entry e */
+	int n_reads;
+	int pairs;                 /* buf_len / 2 complex samples per read */
+	int ds;
+	c16 *out;                  /* entry e at out + e * out_stride */
+	long long out_stride;      /* in c16 units */
+	int out_count;             /* c16 slots to write per entry */
+};
+
+/* rtl_power.c:671-681 in closed form: slot k = wrap16(sum of inputs k*ds ..
+ * k*ds+ds-1 that exist); slots past ceil(pairs/ds) are zero. */
+__global__ void __launch_bounds__(256)
+boxcar_kernel(const SCAN_GRID_CONSTANT DecimParams prm)
+{
+	const int e = blockIdx.y;
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= prm.out_count)
+		return;
+	const uint16_t *src = (const uint16_t *)(prm.base + prm.read_off[e]);
+	const int outs = (prm.pairs + prm.ds - 1) / prm.ds;
+	int si = 0, sq = 0;
+	if (k < outs) {
+		const int lo = k * prm.ds;
+		const int hi = (lo + prm.ds < prm.pairs) ? lo + prm.ds : prm.pairs;
+		for (int i = lo; i < hi; ++i) {
+			const unsigned raw = __ldg(src + i);
+			si += (int)(raw & 0xFFu) - 127;
+			sq += (int)(raw >> 8) - 127;
+		}
+	}
+	prm.out[e * prm.out_stride + k] = c16_pack(si, sq);
+}
+
+struct HalfbandParams {
+	const void *in;            /* u8 pairs (first pass) or c16 */
+	const long long *read_off; /* first pass: byte offsets of the u8 reads */
+	long long in_stride;       /* c16 units, later passes */
+	c16 *out;
+	long long out_stride;      /* c16 units */
+	int n_out;                 /* outputs per entry = inputs / 2 */
+};
+
+template <bool FROM_U8>
+SCAN_DEV void hb_sample(const HalfbandParams &prm, int e, int n, int &re, int &im)
+{
+	if constexpr (FROM_U8) {
+		const uint16_t *src = (const uint16_t *)((const uint8_t *)prm.in + prm.read_off[e]);
+		const unsigned raw = __ldg(src + n);
+		re = (int)(raw & 0xFFu) - 127;
+		im = (int)(raw >> 8) - 127;
+	} else {
+		const c16 raw = __ldg((const c16 *)prm.in + e * prm.in_stride + n);
+		re = c16_re(raw);
+		im = c16_im(raw);
+	}
+}
+
+/*
+ * One fifth_order pass (rtl_power.c:554-579) on both halves, stateless per read.
+ * With s[n] the inputs of one half, output n is
+ *   n=0: ((s0+s1)*10 + (s2+s3)*5 + s3 + s5) >> 4
+ *   n=1: ((s1+s2)*10 + (s0+s3)*5 + s4 + s5) >> 4
+ *   n=2: (s0 + (s1+s4)*5 + (s2+s3)*10 + s5) >> 4
+ *   n>=3: (a + (b+e)*5 + (c+d)*10 + f) >> 4 with (a..f) =
+ *        n=3: s2 s3 s4 s5 s5 s6   n=4: s4 s5 s5 s6 s7 s8   (the reference's ease-in)
+ *        n>=5: s[2n-5] s[2n-4] s[2n-3] s[2n-2] s[2n-1] s[2n]
+ */
+template <bool FROM_U8>
+__global__ void __launch_bounds__(256)
+halfband_kernel(const SCAN_GRID_CONSTANT HalfbandParams prm)
+{
+	const int e = blockIdx.y;
+	const int n = blockIdx.x * blockDim.x + threadIdx.x;
+	if (n >= prm.n_out)
+		return;
+	int idx[6];
+	if (n >= 5) {
+		idx[0] = 2 * n - 5; idx[1] = 2 * n - 4; idx[2] = 2 * n - 3;
+		idx[3] = 2 * n - 2; idx[4] = 2 * n - 1; idx[5] = 2 * n;
+	} else if (n == 4) {
+		idx[0] = 4; idx[1] = 5; idx[2] = 5; idx[3] = 6; idx[4] = 7; idx[5] = 8;
+	} else if (n == 3) {
+		idx[0] = 2; idx[1] = 3; idx[2] = 4; idx[3] = 5; idx[4] = 5; idx[5] = 6;
+	} else {
+		idx[0] = 0; idx[1] = 1; idx[2] = 2; idx[3] = 3; idx[4] = 4; idx[5] = 5;
+	}
+	int xr[6], xi[6];
+#pragma unroll
+	for (int i = 0; i < 6; ++i)
+		hb_sample<FROM_U8>(prm, e, idx[i], xr[i], xi[i]);
+	int re, im;
+	if (n == 0) {
+		re = ((xr[0] + xr[1]) * 10 + (xr[2] + xr[3]) * 5 + xr[3] + xr[5]) >> 4;
+		im = ((xi[0] + xi[1]) * 10 + (xi[2] + xi[3]) * 5 + xi[3] + xi[5]) >> 4;
+	} else if (n == 1) {
+		re = ((xr[1] + xr[2]) * 10 + (xr[0] + xr[3]) * 5 + xr[4] + xr[5]) >> 4;
+		im = ((xi[1] + xi[2]) * 10 + (xi[0] + xi[3]) * 5 + xi[4] + xi[5]) >> 4;
+	} else if (n == 2) {
+		re = (xr[0] + (xr[1] + xr[4]) * 5 + (xr[2] + xr[3]) * 10 + xr[5]) >> 4;
+		im = (xi[0] + (xi[1] + xi[4]) * 5 + (xi[2] + xi[3]) * 10 + xi[5]) >> 4;
+	} else {
+		re = (xr[0] + (xr[1] + xr[4]) * 5 + (xr[2] + xr[3]) * 10 + xr[5]) >> 4;
+		im = (xi[0] + (xi[1] + xi[4]) * 5 + (xi[2] + xi[3]) * 10 + xi[5]) >> 4;
+	}
+	prm.out[e * prm.out_stride + n] = c16_pack(re, im);
+}
+
+struct FirParams {
+	const c16 *in;
+	long long in_stride;
+	c16 *out;
+	long long out_stride;
+	int count;     /* samples per entry */
+	int use_fir;   /* 0: plain copy */
+	int f1, f2, f3, f4, f5; /* cic_9_tables[ds_p][1..5], rtl_power.c:219-232 */
+};
+
+/* generic_fir (rtl_power.c:598-626): samples 0..8 pass through, sample k >= 9 is
+ * the 9-tap sum over inputs k-9..k-1, >> 15, int32 wrap-around arithmetic. */
+__global__ void __launch_bounds__(256)
+fir9_kernel(const SCAN_GRID_CONSTANT FirParams prm)
+{
+	const int e = blockIdx.y;
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= prm.count)
+		return;
+	const c16 *src = prm.in + e * prm.in_stride;
+	c16 o = __ldg(src + k);
+	if (prm.use_fir && k >= 9) {
+		int hr[9], hi[9];
+#pragma unroll
+		for (int i = 0; i < 9; ++i) {
+			const c16 x = __ldg(src + k - 9 + i);
+			hr[i] = c16_re(x);
+			hi[i] = c16_im(x);
+		}
+		unsigned sr = 0, si = 0;
+		sr += (unsigned)(hr[0] + hr[8]) * (unsigned)prm.f1;
+		sr += (unsigned)(hr[1] + hr[7]) * (unsigned)prm.f2;
+		sr += (unsigned)(hr[2] + hr[6]) * (unsigned)prm.f3;
+		sr += (unsigned)(hr[3] + hr[5]) * (unsigned)prm.f4;
+		sr += (unsigned)hr[4] * (unsigned)prm.f5;
+		si += (unsigned)(hi[0] + hi[8]) * (unsigned)prm.f1;
+		si += (unsigned)(hi[1] + hi[7]) * (unsigned)prm.f2;
+		si += (unsigned)(hi[2] + hi[6]) * (unsigned)prm.f3;
+		si += (unsigned)(hi[3] + hi[5]) * (unsigned)prm.f4;
+		si += (unsigned)hi[4] * (unsigned)prm.f5;
+		o = c16_pack((int)sr >> 15, (int)si >> 15);
+	}
+	prm.out[e * prm.out_stride + k] = o;
+}
+
+struct DcSumParams {
+	const c16 *img;
+	long long stride;  /* c16 units */
+	int l_len;         /* interleaved int16 length the reference's remove_dc sees */
+	long long *sums;   /* [entry][2], zeroed by the host before launch */
+};
+
+/* Sums for remove_dc (rtl_power.c:586-588): I over even indices < l_len,
+ * Q over odd indices < l_len. */
+__global__ void __launch_bounds__(256)
+dc_sums_c16_kernel(const SCAN_GRID_CONSTANT DcSumParams prm)
+{
+	const int e = blockIdx.y;
+	const c16 *src = prm.img + e * prm.stride;
+	const int nI = (prm.l_len + 1) >> 1, nQ = prm.l_len >> 1;
+	long long sI = 0, sQ = 0;
+	for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nI; k += gridDim.x * blockDim.x) {
+		const c16 x = __ldg(src + k);
+		sI += c16_re(x);
+		if (k < nQ)
+			sQ += c16_im(x);
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		sI += __shfl_xor_sync(0xffffffffu, sI, o);
+		sQ += __shfl_xor_sync(0xffffffffu, sQ, o);
+	}
+	if ((threadIdx.x & 31) == 0) {
+		atomicAdd((unsigned long long *)(prm.sums + 2 * e), (unsigned long long)sI);
+		atomicAdd((unsigned long long *)(prm.sums + 2 * e + 1), (unsigned long long)sQ);
+	}
+}
+
+/* ======================================================================== *
+ *  rms_power: 1-bin hops (rtl_power.c:410-436)                              *
+ * ======================================================================== */
+
+struct RmsParams {
+	const uint8_t *base;
+	const long long *read_off;
+	const int *hop_of;   /* hop of entry e */
+	int buf_len;
+	int peak;
+	long long *avg;      /* [tune_count] */
+};
+
+__global__ void __launch_bounds__(256)
+rms_kernel(const SCAN_GRID_CONSTANT RmsParams prm)
+{
+	__shared__ long long sh[2 * 8];
+	const int e = blockIdx.x;
+	const uint8_t *src = prm.base + prm.read_off[e];
+	long long tsum = 0, psum = 0;
+	for (int i = threadIdx.x * 16; i < prm.buf_len; i += blockDim.x * 16) {
+		const uint4 q = __ldg((const uint4 *)(src + i));
+		const unsigned w[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+#pragma unroll
+			for (int b = 0; b < 4; ++b) {
+				const int s = (int)((w[j] >> (8 * b)) & 0xFFu) - 127;
+				tsum += s;
+				psum += s * s;
+			}
+		}
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
+		psum += __shfl_xor_sync(0xffffffffu, psum, o);
+	}
+	if ((threadIdx.x & 31) == 0) {
+		sh[(threadIdx.x >> 5) * 2] = tsum;
+		sh[(threadIdx.x >> 5) * 2 + 1] = psum;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		long long t = 0, p = 0;
+		for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+			t += sh[2 * w];
+			p += sh[2 * w + 1];
+		}
+		/* same IEEE double operations, in the reference's order, no FMA contraction */
+		const double n = (double)prm.buf_len;
+		const double dc = __ddiv_rn((double)t, n);
+		const double err = __dsub_rn(__dmul_rn((double)(t * 2), dc), __dmul_rn(__dmul_rn(dc, dc), n));
+		p -= (long long)round(err);
+		long long *dst = prm.avg + prm.hop_of[e];
+		if (prm.peak)
+			atomicMax(dst, p);
+		else
+			atomicAdd((unsigned long long *)dst, (unsigned long long)p);
+	}
+}
+
+/* ======================================================================== *
+ *  Report epilogue: DC nuke, half swap, crop, dB (rtl_power.c:722-760)      *
+ * ======================================================================== */
+
+struct EpilogueParams {
+	const long long *avg; /* [hops << bin_e] natural order */
+	const int *samples;   /* [hops] */
+	double *db;           /* [hops][db_count] */
+	int bin_e;
+	int i1, i2;           /* first / last printed bin of the swapped spectrum */
+	int rate;
+	int hop0;             /* first hop to process */
+};
+
+__global__ void __launch_bounds__(256)
+epilogue_kernel(const SCAN_GRID_CONSTANT EpilogueParams prm)
+{
+	const int hop = prm.hop0 + blockIdx.y;
+	const int n = 1 << prm.bin_e;
+	const int count = prm.i2 - prm.i1 + 2;
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= count)
+		return;
+	const long long *a = prm.avg + ((long long)hop << prm.bin_e);
+	const int i = (k < count - 1) ? prm.i1 + k : prm.i2;
+	long long v;
+	if (prm.bin_e > 0) {
+		const int j = (i + n / 2) & (n - 1); /* undo the half swap */
+		v = a[j == 0 ? 1 : j];               /* avg[0] = avg[1] */
+	} else {
+		v = a[0];
+	}
+	const double rate = (double)prm.rate, smp = (double)prm.samples[hop];
+	double d;
+	if (k < count - 1)
+		d = __ddiv_rn(__ddiv_rn((double)v, rate), smp);
+	else
+		d = __ddiv_rn((double)v, __dmul_rn(rate, smp));
+	prm.db[(long long)hop * count + k] = 10 * log10(d);
+}
+
+} // namespace rscan

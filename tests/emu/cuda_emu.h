@@ -1,0 +1,146 @@
+/*
+ * cuda_emu.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * A tiny functional emulator of the CUDA execution model, just big enough to
+ * run rtlsdr_b200/csrc/scan_kernels.cuh on the GPU-less build box: one OS
+ * thread per CUDA thread, std::barrier for __syncthreads / warp shuffles,
+ * blocks executed one after another.  It checks index math and data flow, not
+ * performance and not data races.  Nothing in the shipped library includes it.
+ */
+#pragma once
+#include <atomic>
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+struct dim3 {
+	unsigned x, y, z;
+	dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+struct int2 { int x, y; };
+struct int4 { int x, y, z, w; };
+struct uint4 { unsigned x, y, z, w; };
+static inline int2 make_int2(int x, int y) { return int2{ x, y }; }
+static inline int4 make_int4(int x, int y, int z, int w) { return int4{ x, y, z, w }; }
+
+namespace cuda_emu {
+inline thread_local dim3 t_threadIdx, t_blockIdx;
+inline dim3 g_blockDim, g_gridDim;
+inline unsigned char *g_smem = nullptr;
+inline std::barrier<> *g_block_bar = nullptr;
+inline std::vector<std::unique_ptr<std::barrier<>>> g_warp_bar;
+inline std::vector<uint64_t> g_shfl;
+
+inline unsigned char *dyn_smem() { return g_smem; }
+inline void copy16(void *d, const void *s) { memcpy(d, s, 16); }
+inline unsigned linear_tid() { return t_threadIdx.x + g_blockDim.x * (t_threadIdx.y + g_blockDim.y * t_threadIdx.z); }
+
+template <class T>
+inline T shfl_idx(T v, unsigned src_lane)
+{
+	unsigned tid = linear_tid(), w = tid / 32, lane = tid % 32;
+	uint64_t raw = 0;
+	memcpy(&raw, &v, sizeof(T));
+	g_shfl[w * 32 + lane] = raw;
+	g_warp_bar[w]->arrive_and_wait();
+	raw = g_shfl[w * 32 + (src_lane & 31)];
+	g_warp_bar[w]->arrive_and_wait();
+	T out;
+	memcpy(&out, &raw, sizeof(T));
+	return out;
+}
+
+/* run `body` for every thread of every block; blocks are sequential */
+inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()> &body)
+{
+	const unsigned nthreads = block.x * block.y * block.z;
+	const unsigned nblocks = grid.x * grid.y * grid.z;
+	std::vector<unsigned char> smem(smem_bytes + 64);
+	g_smem = (unsigned char *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
+	g_blockDim = block;
+	g_gridDim = grid;
+	std::barrier<> bar((std::ptrdiff_t)nthreads);
+	g_block_bar = &bar;
+	const unsigned nwarps = (nthreads + 31) / 32;
+	g_warp_bar.clear();
+	for (unsigned w = 0; w < nwarps; w++) {
+		unsigned cnt = std::min(32u, nthreads - w * 32);
+		g_warp_bar.emplace_back(new std::barrier<>((std::ptrdiff_t)cnt));
+	}
+	g_shfl.assign((size_t)nwarps * 32, 0);
+	std::vector<std::thread> pool;
+	pool.reserve(nthreads);
+	for (unsigned tid = 0; tid < nthreads; tid++) {
+		pool.emplace_back([&, tid]() {
+			t_threadIdx = dim3(tid % block.x, (tid / block.x) % block.y, tid / (block.x * block.y));
+			for (unsigned b = 0; b < nblocks; b++) {
+				t_blockIdx = dim3(b % grid.x, (b / grid.x) % grid.y, b / (grid.x * grid.y));
+				body();
+				bar.arrive_and_wait(); /* next block reuses the shared memory */
+			}
+		});
+	}
+	for (auto &th : pool)
+		th.join();
+	g_block_bar = nullptr;
+}
+} // namespace cuda_emu
+
+#define threadIdx (::cuda_emu::t_threadIdx)
+#define blockIdx (::cuda_emu::t_blockIdx)
+#define blockDim (::cuda_emu::g_blockDim)
+#define gridDim (::cuda_emu::g_gridDim)
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __shared__ static
+#define __launch_bounds__(...)
+#define __align__(n) alignas(n)
+
+static inline void __syncthreads() { ::cuda_emu::g_block_bar->arrive_and_wait(); }
+template <class T>
+static inline T __shfl_xor_sync(unsigned, T v, int lane_mask)
+{
+	return ::cuda_emu::shfl_idx(v, (::cuda_emu::linear_tid() % 32) ^ (unsigned)lane_mask);
+}
+template <class T>
+static inline T __ldg(const T *p) { return *p; }
+static inline unsigned __brev(unsigned v)
+{
+	unsigned r = 0;
+	for (int i = 0; i < 32; i++) {
+		r = (r << 1) | (v & 1u);
+		v >>= 1;
+	}
+	return r;
+}
+static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c)
+{
+	for (int i = 0; i < 4; i++)
+		c += ((a >> (8 * i)) & 0xFFu) * ((b >> (8 * i)) & 0xFFu);
+	return c;
+}
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v)
+{
+	return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
+}
+template <class T>
+static inline T emu_atomic_max(T *p, T v)
+{
+	T old = __atomic_load_n(p, __ATOMIC_RELAXED);
+	while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+	}
+	return old;
+}
+static inline long long atomicMax(long long *p, long long v) { return emu_atomic_max(p, v); }
+static inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) { return emu_atomic_max(p, v); }

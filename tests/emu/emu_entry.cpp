@@ -1,0 +1,213 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- runs the real kernel source
+ * (rtlsdr_b200/csrc/scan_kernels.cuh, scan_large.cuh) on the CPU through
+ * cuda_emu.h so that index math / data flow can be parity-checked against the
+ * oracle on a box without a GPU.  Built by tests/test_emu_kernels.py with
+ *   g++ -std=c++20 -O2 -DSCAN_EMU -Itests/emu -Irtlsdr_b200/csrc -shared -fPIC
+ */
+#include "scan_kernels.cuh"
+#include "scan_large.cuh"
+
+#include <cstdio>
+#include <vector>
+
+using namespace rscan;
+
+namespace {
+
+template <int L, bool PEAK, bool IN16>
+void run_small_t(const SmallParams &prm)
+{
+	cuda_emu::launch(dim3(prm.n_segs), dim3(kThreads), SmallSmem<L>::bytes,
+			 [&]() { scan_small_kernel<L, PEAK, IN16>(prm); });
+}
+
+template <int L>
+void run_small_l(const SmallParams &prm, int peak, int in16)
+{
+	if (peak)
+		in16 ? run_small_t<L, true, true>(prm) : run_small_t<L, true, false>(prm);
+	else
+		in16 ? run_small_t<L, false, true>(prm) : run_small_t<L, false, false>(prm);
+}
+
+void run_small(int L, const SmallParams &prm, int peak, int in16)
+{
+	switch (L) {
+	case 1: run_small_l<1>(prm, peak, in16); break;
+	case 2: run_small_l<2>(prm, peak, in16); break;
+	case 3: run_small_l<3>(prm, peak, in16); break;
+	case 4: run_small_l<4>(prm, peak, in16); break;
+	case 5: run_small_l<5>(prm, peak, in16); break;
+	case 6: run_small_l<6>(prm, peak, in16); break;
+	case 7: run_small_l<7>(prm, peak, in16); break;
+	case 8: run_small_l<8>(prm, peak, in16); break;
+	case 9: run_small_l<9>(prm, peak, in16); break;
+	case 10: run_small_l<10>(prm, peak, in16); break;
+	case 11: run_small_l<11>(prm, peak, in16); break;
+	case 12: run_small_l<12>(prm, peak, in16); break;
+	default: break;
+	}
+}
+
+void fill_tw0(PassTw &tw0, const int2 *tw, int L)
+{
+	memset(&tw0, 0, sizeof(tw0));
+	for (int b = 0; b < 4 && b < L; b++)
+		for (int g = 0; g < (1 << b); g++)
+			tw0.w[(1 << b) - 1 + g] = tw[(size_t)g << (L - 1 - b)];
+}
+
+} // namespace
+
+extern "C" {
+
+/* u8 path: reads [n_reads][16384], segs [n_segs][4] = (hop, first, count, 0) */
+void emu_small_u8(int L, int peak, const uint8_t *reads, int n_reads, const int *segs, int n_segs,
+		  const int *tw /* [N/2][2] */, const uint16_t *win, long long *avg)
+{
+	std::vector<long long> offs(n_reads);
+	for (int i = 0; i < n_reads; i++)
+		offs[i] = (long long)i * kStageBytes;
+	SmallParams p;
+	memset(&p, 0, sizeof(p));
+	p.base = reads;
+	p.read_off = offs.data();
+	p.segs = (const int4 *)segs;
+	p.n_segs = n_segs;
+	p.avg = avg;
+	p.tw = (const int2 *)tw;
+	p.win = win;
+	p.units_per_read = 1;
+	fill_tw0(p.tw0, p.tw, L);
+	run_small(L, p, peak, 0);
+}
+
+/*
+ * decimating path: u8 reads [n_reads][buf_len] -> images -> spectra.
+ * mode 0 = boxcar(ds), mode 1 = fifth_order x ds_p (+ 9-tap FIR if fir5 != NULL)
+ */
+void emu_small_decim(int L, int peak, const uint8_t *reads, int n_reads, int buf_len, int ds, int ds_p,
+		     int mode, const int *fir5, const int *segs, int n_segs, const int *tw,
+		     const uint16_t *win, long long *avg, uint32_t *image_out, long long *sums_out)
+{
+	const int N = 1 << L, pairs = buf_len / 2;
+	const int l_len = buf_len / ds;
+	const int n_blocks = (l_len + 2 * N - 1) / (2 * N);
+	const int units = (int)(((long long)n_blocks * N + kWS - 1) / kWS);
+	const long long stride = (long long)units * kWS;
+	std::vector<long long> offs(n_reads);
+	for (int i = 0; i < n_reads; i++)
+		offs[i] = (long long)i * buf_len;
+	std::vector<c16> img((size_t)n_reads * stride, 0xDEADBEEFu); /* padding must not matter */
+	std::vector<long long> sums((size_t)n_reads * 2, 0);
+
+	if (mode == 0) {
+		DecimParams d;
+		d.base = reads;
+		d.read_off = offs.data();
+		d.n_reads = n_reads;
+		d.pairs = pairs;
+		d.ds = ds;
+		d.out = img.data();
+		d.out_stride = stride;
+		d.out_count = (int)stride;
+		cuda_emu::launch(dim3((unsigned)((stride + 255) / 256), n_reads), dim3(256), 0, [&]() { boxcar_kernel(d); });
+	} else {
+		std::vector<c16> a((size_t)n_reads * (pairs / 2)), b((size_t)n_reads * (pairs / 4 + 4));
+		const c16 *cur = nullptr;
+		long long cur_stride = 0;
+		int count = pairs;
+		for (int j = 0; j < ds_p; j++) {
+			HalfbandParams hp;
+			c16 *dst = (j & 1) ? b.data() : a.data();
+			long long dst_stride = (j & 1) ? (pairs / 4 + 4) : (pairs / 2);
+			hp.in = j == 0 ? (const void *)reads : (const void *)cur;
+			hp.read_off = offs.data();
+			hp.in_stride = cur_stride;
+			hp.out = dst;
+			hp.out_stride = dst_stride;
+			hp.n_out = count / 2;
+			dim3 grid((hp.n_out + 255) / 256, n_reads);
+			if (j == 0)
+				cuda_emu::launch(grid, dim3(256), 0, [&]() { halfband_kernel<true>(hp); });
+			else
+				cuda_emu::launch(grid, dim3(256), 0, [&]() { halfband_kernel<false>(hp); });
+			cur = dst;
+			cur_stride = dst_stride;
+			count /= 2;
+		}
+		FirParams f;
+		f.in = cur;
+		f.in_stride = cur_stride;
+		f.out = img.data();
+		f.out_stride = stride;
+		f.count = count;
+		f.use_fir = fir5 ? 1 : 0;
+		f.f1 = fir5 ? fir5[0] : 0; f.f2 = fir5 ? fir5[1] : 0; f.f3 = fir5 ? fir5[2] : 0;
+		f.f4 = fir5 ? fir5[3] : 0; f.f5 = fir5 ? fir5[4] : 0;
+		cuda_emu::launch(dim3((count + 255) / 256, n_reads), dim3(256), 0, [&]() { fir9_kernel(f); });
+	}
+	DcSumParams dc;
+	dc.img = img.data();
+	dc.stride = stride;
+	dc.l_len = l_len;
+	dc.sums = sums.data();
+	cuda_emu::launch(dim3(3, n_reads), dim3(256), 0, [&]() { dc_sums_c16_kernel(dc); });
+	if (image_out)
+		memcpy(image_out, img.data(), img.size() * 4);
+	if (sums_out)
+		memcpy(sums_out, sums.data(), sums.size() * 8);
+
+	SmallParams p;
+	memset(&p, 0, sizeof(p));
+	p.base = (const uint8_t *)img.data();
+	p.read_off = nullptr;
+	p.regular_stride = stride * 4;
+	p.entry_base = 0;
+	p.segs = (const int4 *)segs;
+	p.n_segs = n_segs;
+	p.avg = avg;
+	p.tw = (const int2 *)tw;
+	p.win = win;
+	p.dc_sums = sums.data();
+	p.l_len = l_len;
+	p.n_blocks = n_blocks;
+	p.units_per_read = units;
+	fill_tw0(p.tw0, p.tw, L);
+	run_small(L, p, peak, 1);
+}
+
+void emu_rms(const uint8_t *reads, int n_reads, int buf_len, const int *hop_of, int peak, long long *avg)
+{
+	std::vector<long long> offs(n_reads);
+	for (int i = 0; i < n_reads; i++)
+		offs[i] = (long long)i * buf_len;
+	RmsParams p;
+	p.base = reads;
+	p.read_off = offs.data();
+	p.hop_of = hop_of;
+	p.buf_len = buf_len;
+	p.peak = peak;
+	p.avg = avg;
+	cuda_emu::launch(dim3(n_reads), dim3(256), 0, [&]() { rms_kernel(p); });
+}
+
+void emu_epilogue(const long long *avg, const int *samples, double *db, int bin_e, int i1, int i2, int rate, int hops)
+{
+	EpilogueParams p;
+	p.avg = avg;
+	p.samples = samples;
+	p.db = db;
+	p.bin_e = bin_e;
+	p.i1 = i1;
+	p.i2 = i2;
+	p.rate = rate;
+	p.hop0 = 0;
+	int count = i2 - i1 + 2;
+	cuda_emu::launch(dim3((count + 255) / 256, hops), dim3(256), 0, [&]() { epilogue_kernel(p); });
+}
+
+#include "emu_large.inl"
+
+} /* extern "C" */
