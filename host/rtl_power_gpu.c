@@ -1,0 +1,335 @@
+/*
+ * rtl_power_gpu -- rtl_power's command line and CSV output with the scan
+ * arithmetic done on a B200 through include/rtlsdr_gpu_scan.h.
+ *
+ * What is kept from the reference tool (src/rtl_power.c):
+ *   - the option letters and their meaning            (:798-882)
+ *   - the hop plan                                     (:438-540, rtl_power_plan.c)
+ *   - the sweep order: for every hop, retune if the centre frequency differs
+ *     (5 ms settle + a 4096-byte dump read), then ONE rtlsdr_read_sync of
+ *     buf_len bytes                                    (:642-659, :542-552)
+ *   - reporting once per interval, rows "date, time, low, high, step, samples,
+ *     dB..." in hop order                              (:989-1003, :722-760)
+ *   - SIGINT: first = finish the pass and exit, second = abort (:182-211, :651)
+ * What is replaced: the DSP between the read and the row (:660-718, :730-764)
+ * is rtlsdr_gpu_scan_submit() / rtlsdr_gpu_scan_collect().
+ *
+ * The sample source is host/synth_source.c (no dongle on the GPU box); it is
+ * configured through environment variables so that the command line stays the
+ * reference's:
+ *   RTLSDR_SYNTH_MODE   xorshift | counter | const | biased | tone | replay
+ *   RTLSDR_SYNTH_SEED   integer      RTLSDR_SYNTH_PARAM  integer
+ *   RTLSDR_SYNTH_REPLAY path of a raw interleaved u8 IQ file (rtl_sdr format)
+ *   RTL_POWER_PASSES    report after this many sweeps instead of by wall clock
+ *   RTL_POWER_TIMESTAMP fixed "date, time" prefix (byte-reproducible output)
+ *   RTLSDR_GPU_DEVICE   CUDA device ordinal
+ */
+#include <math.h>
+#include <signal.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+
+#include "rtl_power_plan.h"
+#include "rtlsdr_gpu_scan.h"
+#include "synth_source.h"
+
+#define SETTLE_DUMP_BYTES 4096 /* BUFFER_DUMP, rtl_power.c:76 */
+
+static volatile sig_atomic_t stop_requests = 0;
+
+static void on_signal(int signum)
+{
+	(void)signum;
+	stop_requests++;
+}
+
+static void print_usage(void)
+{
+	fprintf(stderr,
+		"rtl_power_gpu, rtl_power's FFT logger with the scan on a B200 GPU\n\n"
+		"Use:\trtl_power_gpu -f freq_range [-options] [filename]\n"
+		"\t-f lower:upper:bin_size [Hz]\n"
+		"\t[-i integration_interval (default: 10 seconds)]\n"
+		"\t[-1 enables single-shot mode (default: off)]\n"
+		"\t[-e exit_timer (default: off/0)]\n"
+		"\t[-d device_index] [-g tuner_gain] [-p ppm_error] [-T] [-O] [-D mode]\n"
+		"\t\t(accepted for compatibility; the synthetic source ignores them)\n"
+		"\t[-w window (default: rectangle)]\n"
+		"\t\t(hamming, blackman, blackman-harris, hann-poisson, bartlett, youssef)\n"
+		"\t[-c crop_percent (default: 0%%)]\n"
+		"\t[-F fir_size (default: disabled)] (0 or 9; switches boxcar off)\n"
+		"\t[-P enables peak hold (default: off)]\n"
+		"\t[-s avg|iir] [-t threads] (parsed and ignored, like the reference)\n"
+		"\tfilename (a '-' dumps samples to stdout, the default)\n");
+	exit(1);
+}
+
+static int env_int(const char *name, int dflt)
+{
+	const char *v = getenv(name);
+	return (v && *v) ? atoi(v) : dflt;
+}
+
+static int synth_mode_from_env(void)
+{
+	const char *v = getenv("RTLSDR_SYNTH_MODE");
+	if (!v) return SYNTH_XORSHIFT;
+	if (!strcmp(v, "counter")) return SYNTH_COUNTER;
+	if (!strcmp(v, "const")) return SYNTH_CONST;
+	if (!strcmp(v, "biased")) return SYNTH_BIASED;
+	if (!strcmp(v, "tone")) return SYNTH_TONE;
+	if (!strcmp(v, "replay")) return SYNTH_REPLAY;
+	return SYNTH_XORSHIFT;
+}
+
+static uint8_t *load_replay(const char *path, size_t read_len, size_t *n_reads)
+{
+	FILE *f = fopen(path, "rb");
+	uint8_t *buf;
+	long size;
+	if (!f)
+		return NULL;
+	fseek(f, 0, SEEK_END);
+	size = ftell(f);
+	fseek(f, 0, SEEK_SET);
+	*n_reads = (size_t)size / read_len;
+	if (*n_reads == 0) {
+		fclose(f);
+		return NULL;
+	}
+	buf = (uint8_t *)malloc(*n_reads * read_len);
+	if (buf && fread(buf, read_len, *n_reads, f) != *n_reads) {
+		free(buf);
+		buf = NULL;
+	}
+	fclose(f);
+	return buf;
+}
+
+/* retune(): rtl_power.c:542-552 */
+static void settle_on(rtlsdr_dev_t *dev, int freq)
+{
+	uint8_t dump[SETTLE_DUMP_BYTES];
+	int got = 0;
+	rtlsdr_set_center_freq(dev, (uint32_t)freq);
+	if (!getenv("RTL_POWER_PASSES"))
+		usleep(5000);
+	rtlsdr_read_sync(dev, dump, SETTLE_DUMP_BYTES, &got);
+	if (got != SETTLE_DUMP_BYTES)
+		fprintf(stderr, "Error: bad retune.\n");
+}
+
+/* one sweep over all hops: the control flow of scanner(), rtl_power.c:642-659 */
+static int sweep(rtlsdr_dev_t *dev, rtlsdr_gpu_scan_t *gpu, const rp_plan_t *plan, uint8_t *buf8)
+{
+	int hop, got, rc;
+	for (hop = 0; hop < plan->tune_count; hop++) {
+		if (stop_requests >= 2)
+			return 0;
+		if ((int)rtlsdr_get_center_freq(dev) != plan->freq[hop])
+			settle_on(dev, plan->freq[hop]);
+		got = 0;
+		rtlsdr_read_sync(dev, buf8, plan->buf_len, &got);
+		if (got != plan->buf_len)
+			fprintf(stderr, "Error: dropped samples.\n");
+		/* like the reference, the whole buffer is processed even after a short read */
+		rc = rtlsdr_gpu_scan_submit(gpu, hop, buf8, (uint32_t)plan->buf_len);
+		if (rc) {
+			fprintf(stderr, "rtlsdr_gpu_scan_submit: %s (%s)\n", rtlsdr_gpu_scan_strerror(rc),
+				rtlsdr_gpu_scan_last_cuda_error(gpu));
+			return rc;
+		}
+	}
+	return 0;
+}
+
+int main(int argc, char **argv)
+{
+	const char *range = NULL, *window = "rectangle", *filename = "-";
+	const char *fixed_stamp = getenv("RTL_POWER_TIMESTAMP");
+	int opt, interval = 10, single = 0, peak_hold = 0, boxcar = 1, comp_fir_size = 0;
+	int passes_per_report = env_int("RTL_POWER_PASSES", 0), passes = 0, rc = 0, hop;
+	long exit_after = 0;
+	double crop = 0.0;
+	time_t next_tick, exit_time = 0, now;
+	rp_plan_t *plan;
+	rtlsdr_dev_t *dev = NULL;
+	rtlsdr_gpu_scan_t *gpu = NULL;
+	rtlsdr_gpu_scan_cfg_t cfg;
+	int32_t *window_coefs = NULL;
+	uint8_t *buf8, *replay = NULL;
+	double *db;
+	char *row, stamp[64];
+	size_t row_cap;
+	FILE *out;
+	struct sigaction sa;
+
+	while ((opt = getopt(argc, argv, "f:i:s:t:d:g:p:e:w:c:F:1POhTD:")) != -1) {
+		switch (opt) {
+		case 'f': range = optarg; break;
+		case 'i': interval = (int)round(rp_atoft(optarg)); break;
+		case 'e': exit_after = (long)round(rp_atoft(optarg)); break;
+		case 'w': window = optarg; break;
+		case 'c': crop = rp_atofp(optarg); break;
+		case 'F': boxcar = 0; comp_fir_size = atoi(optarg); break;
+		case '1': single = 1; break;
+		case 'P': peak_hold = 1; break;
+		case 's': case 't': case 'd': case 'g': case 'p': case 'O': case 'T': case 'D':
+			break; /* device housekeeping or options the reference parses and ignores */
+		case 'h':
+		default:
+			print_usage();
+		}
+	}
+	if (!range) {
+		fprintf(stderr, "No frequency range provided.\n");
+		return 1;
+	}
+	if (crop < 0.0 || crop > 1.0) {
+		fprintf(stderr, "Crop value outside of 0 to 1.\n");
+		return 1;
+	}
+	plan = (rp_plan_t *)calloc(1, sizeof(*plan));
+	rc = rp_plan_range(range, crop, boxcar, plan);
+	if (rc == -2) {
+		fprintf(stderr, "Error: bandwidth too wide.\n");
+		return 1;
+	}
+	if (rc || plan->tune_count == 0)
+		print_usage();
+	rp_plan_report(plan, stderr);
+	if (optind < argc)
+		filename = argv[optind];
+	if (interval < 1)
+		interval = 1;
+	fprintf(stderr, "Reporting every %i seconds\n", interval);
+
+	if (rtlsdr_open(&dev, 0) < 0) {
+		fprintf(stderr, "Failed to open rtlsdr device #0.\n");
+		return 1;
+	}
+	synth_configure(dev, synth_mode_from_env(), (uint64_t)env_int("RTLSDR_SYNTH_SEED", 0),
+			env_int("RTLSDR_SYNTH_PARAM", 0));
+	synth_set_hops(dev, plan->freq, plan->tune_count);
+	synth_set_block_len(dev, (size_t)plan->buf_len);
+	if (synth_mode_from_env() == SYNTH_REPLAY) {
+		size_t n_reads = 0;
+		const char *path = getenv("RTLSDR_SYNTH_REPLAY");
+		replay = path ? load_replay(path, (size_t)plan->buf_len, &n_reads) : NULL;
+		if (!replay) {
+			fprintf(stderr, "Failed to load replay file.\n");
+			return 1;
+		}
+		synth_set_replay(dev, replay, (size_t)plan->buf_len, n_reads);
+	}
+
+	memset(&sa, 0, sizeof(sa));
+	sa.sa_handler = on_signal;
+	sigemptyset(&sa.sa_mask);
+	sigaction(SIGINT, &sa, NULL);
+	sigaction(SIGTERM, &sa, NULL);
+	sigaction(SIGQUIT, &sa, NULL);
+	sigaction(SIGPIPE, &sa, NULL);
+
+	if (strcmp(filename, "-") == 0) {
+		out = stdout;
+	} else {
+		out = fopen(filename, "wb");
+		if (!out) {
+			fprintf(stderr, "Failed to open %s\n", filename);
+			return 1;
+		}
+	}
+
+	rtlsdr_reset_buffer(dev);
+	rtlsdr_set_sample_rate(dev, (uint32_t)plan->rate);
+
+	/* host-built window table, rtl_power.c:985-988 */
+	window_coefs = (int32_t *)malloc(sizeof(int32_t) << plan->bin_e);
+	rtlsdr_gpu_scan_window(window, 1 << plan->bin_e, window_coefs);
+
+	memset(&cfg, 0, sizeof(cfg));
+	cfg.struct_size = sizeof(cfg);
+	cfg.device = env_int("RTLSDR_GPU_DEVICE", 0);
+	cfg.tune_count = plan->tune_count;
+	cfg.bin_e = plan->bin_e;
+	cfg.buf_len = plan->buf_len;
+	cfg.downsample = plan->downsample;
+	cfg.downsample_passes = plan->downsample_passes;
+	cfg.boxcar = boxcar;
+	cfg.comp_fir_size = comp_fir_size;
+	cfg.peak_hold = peak_hold;
+	cfg.rate = plan->rate;
+	cfg.crop = plan->crop;
+	cfg.window_coefs = window_coefs;
+	rc = rtlsdr_gpu_scan_init(&cfg, &gpu);
+	if (rc) {
+		fprintf(stderr, "rtlsdr_gpu_scan_init: %s\n", rtlsdr_gpu_scan_strerror(rc));
+		return 1;
+	}
+
+	buf8 = (uint8_t *)malloc((size_t)plan->buf_len);
+	db = (double *)malloc(sizeof(double) * (size_t)rtlsdr_gpu_scan_db_count(gpu));
+	row_cap = (size_t)rtlsdr_gpu_scan_db_count(gpu) * 16 + 256;
+	row = (char *)malloc(row_cap);
+	next_tick = time(NULL) + interval;
+	if (exit_after)
+		exit_time = time(NULL) + exit_after;
+
+	while (!stop_requests) {
+		rc = sweep(dev, gpu, plan, buf8);
+		if (rc)
+			break;
+		passes++;
+		now = time(NULL);
+		if (passes_per_report ? (passes % passes_per_report) != 0 : now < next_tick)
+			continue;
+		if (fixed_stamp) {
+			snprintf(stamp, sizeof(stamp), "%s", fixed_stamp);
+		} else {
+			struct tm *cal = localtime(&now);
+			strftime(stamp, sizeof(stamp), "%Y-%m-%d, %H:%M:%S", cal);
+		}
+		for (hop = 0; hop < plan->tune_count; hop++) {
+			int samples = 0;
+			rc = rtlsdr_gpu_scan_collect(gpu, hop, NULL, &samples, db);
+			if (rc) {
+				fprintf(stderr, "rtlsdr_gpu_scan_collect: %s (%s)\n", rtlsdr_gpu_scan_strerror(rc),
+					rtlsdr_gpu_scan_last_cuda_error(gpu));
+				break;
+			}
+			if (rp_csv_row(row, row_cap, plan, hop, samples, db, rtlsdr_gpu_scan_db_count(gpu)) < 0)
+				break;
+			fprintf(out, "%s, %s", stamp, row);
+		}
+		fflush(out);
+		if (rc)
+			break;
+		while (time(NULL) >= next_tick)
+			next_tick += interval;
+		if (single)
+			break;
+		if (exit_time && time(NULL) >= exit_time)
+			break;
+	}
+
+	if (stop_requests)
+		fprintf(stderr, "\nUser cancel, exiting...\n");
+	else if (rc)
+		fprintf(stderr, "\nLibrary error %d, exiting...\n", rc);
+	if (out != stdout)
+		fclose(out);
+	rtlsdr_gpu_scan_close(gpu);
+	rtlsdr_close(dev);
+	free(buf8);
+	free(db);
+	free(row);
+	free(window_coefs);
+	free(replay);
+	free(plan);
+	return rc ? 1 : 0;
+}

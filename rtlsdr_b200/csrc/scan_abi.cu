@@ -385,12 +385,11 @@ struct DecimScratch {
 	static size_t per_entry(const rtlsdr_gpu_scan *h)
 	{
 		size_t pairs = (size_t)h->cfg.buf_len / 2;
-		return (size_t)h->image_stride * 4 + (pairs / 2) * 4 + (pairs / 4 + 4) * 4 + 16;
+		return (size_t)h->image_stride * 4 + (pairs / 2) * 4 + (pairs / 4 + 4) * 4 + 32;
 	}
-	DecimScratch(const rtlsdr_gpu_scan *h, int n)
+	DecimScratch(const rtlsdr_gpu_scan *h, int n, uint8_t *p)
 	{
 		size_t pairs = (size_t)h->cfg.buf_len / 2;
-		uint8_t *p = h->d_scratch;
 		img = (c16 *)p;
 		p += (size_t)n * h->image_stride * 4;
 		a = (c16 *)p;
@@ -532,7 +531,7 @@ int launch_batch(rtlsdr_gpu_scan *h, const uint8_t *base, const uint8_t *d_desc,
 			}
 			if ((rc = ensure_scratch(h, per * (size_t)cnt + 256)))
 				return rc;
-			DecimScratch sc(h, cnt);
+			DecimScratch sc(h, cnt, h->d_scratch);
 			TimedScope ts(h);
 			if ((rc = run_decimators(h, base, d_offs + e0, cnt, sc)))
 				return rc;

@@ -182,7 +182,8 @@ struct SmallSmem {
 	static constexpr int off_tw = off_xch + kXchWords * 4;
 	static constexpr int off_win = off_tw + (N / 2 > 0 ? N / 2 : 1) * 8;
 	static constexpr int off_red = (off_win + N * 2 + 15) & ~15;
-	static constexpr int bytes = off_red + 128;
+	static constexpr int off_dck = off_red + 16 * 8; /* after red[8 warps][2] */
+	static constexpr int bytes = off_dck + 16;
 };
 
 template <int L>
@@ -218,13 +219,12 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 	SCAN_DYN_SMEM(smem);
 	typedef SmallSmem<L> SM;
 	constexpr int N = 1 << L;
-	constexpr int KL = (L - 1) / 4;
 	uint8_t *stage = smem + SM::off_stage;
 	c16 *xch = (c16 *)(smem + SM::off_xch);
 	int2 *tws = (int2 *)(smem + SM::off_tw);
 	uint16_t *wins = (uint16_t *)(smem + SM::off_win);
 	long long *red = (long long *)(smem + SM::off_red); /* [8 warps][2] then K_I, K_Q */
-	int *dck = (int *)(red + 16);
+	int *dck = (int *)(smem + SM::off_dck);
 
 	const int t = threadIdx.x;
 	for (int i = t; i < N / 2; i += kThreads)

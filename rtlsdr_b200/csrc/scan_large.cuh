@@ -1,2 +1,304 @@
+/*
+ * scan_large.cuh -- N >= 8192 bins (bin_e 13..21): one FFT block per read, too
+ * big for one CTA's shared memory (4N bytes = 32 KiB .. 8 MiB).
+ *
+ * fix_fft (reference src/rtl_power.c:271-327) is a radix-2 DIT on bit-reversed
+ * data: stage s pairs positions that differ in bit s.  The stages are run in
+ * up to three rounds, each a kernel over 4096-sample tiles that reuses the
+ * register-blocked engine of scan_kernels.cuh; between rounds the packed int16
+ * data lives in a global scratch (L2 resident: 512 KiB per read at N = 2^17):
+ *
+ *   round A  stages 0..7     reads the u8 buffer (or a decimated c16 image),
+ *                            removes DC, applies the window, and performs the
+ *                            bit-reversal as a tile transpose: a tile is 16
+ *                            consecutive input samples x 256 strided rows, so
+ *                            both the gather and the scatter move >= 32-byte runs
+ *   round B  stages 8..15    in place on the scratch, tile = consecutive
+ *                            positions x 2^LB strided rows
+ *   round C  stages 16..L-1  (N > 65536) register-only, 2^(L-16) strided points
+ *                            per thread, then |X|^2 accumulation in natural bin
+ *                            order (coalesced 64-bit atomics)
+ * The last round accumulates |X|^2 / peak hold (rtl_power.c:708-716).
+ * Rounding, halving, twiddles and int16 wrap are those of butterfly().
+ */
 #pragma once
 #include "scan_kernels.cuh"
+
+namespace rscan {
+
+struct LargeParams {
+	const uint8_t *base;        /* u8 reads or decimated c16 images */
+	const long long *read_off;  /* byte offset per entry, NULL = regular */
+	long long regular_stride;
+	int entry_base;             /* first entry of this chunk */
+	const int *hop_of;          /* hop per entry (absolute entry index) */
+	c16 *scratch;               /* [chunk][N] */
+	const long long *dc_sums;   /* [chunk][2] */
+	long long *avg;
+	const int2 *tw;             /* [N/2] */
+	const uint16_t *win;        /* [N] */
+	int L;
+	PassTw tw0;
+};
+
+SCAN_DEV long long large_entry_offset(const LargeParams &prm, int e)
+{
+	return prm.read_off ? prm.read_off[e] : (long long)(e - prm.entry_base) * prm.regular_stride;
+}
+
+/* per-read byte sums of I and Q for the u8 input (remove_dc, rtl_power.c:586-588) */
+struct DcSumU8Params {
+	const uint8_t *base;
+	const long long *read_off;
+	int entry_base;
+	int buf_len;
+	long long *sums; /* [chunk][2], zeroed by the host */
+};
+
+__global__ void __launch_bounds__(256)
+dc_sums_u8_kernel(const SCAN_GRID_CONSTANT DcSumU8Params prm)
+{
+	const int rel = blockIdx.y;
+	const uint8_t *src = prm.base + prm.read_off[prm.entry_base + rel];
+	unsigned sI = 0, sQ = 0; /* <= 2^21 bytes of 255 per component: fits */
+	for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 16; i < prm.buf_len; i += gridDim.x * blockDim.x * 16) {
+		const uint4 q = __ldg((const uint4 *)(src + i));
+		sI = __dp4a(q.x, 0x00010001u, sI);
+		sQ = __dp4a(q.x, 0x01000100u, sQ);
+		sI = __dp4a(q.y, 0x00010001u, sI);
+		sQ = __dp4a(q.y, 0x01000100u, sQ);
+		sI = __dp4a(q.z, 0x00010001u, sI);
+		sQ = __dp4a(q.z, 0x01000100u, sQ);
+		sI = __dp4a(q.w, 0x00010001u, sI);
+		sQ = __dp4a(q.w, 0x01000100u, sQ);
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		sI += __shfl_xor_sync(0xffffffffu, sI, o);
+		sQ += __shfl_xor_sync(0xffffffffu, sQ, o);
+	}
+	if ((threadIdx.x & 31) == 0) {
+		atomicAdd((unsigned long long *)(prm.sums + 2 * rel), (unsigned long long)sI);
+		atomicAdd((unsigned long long *)(prm.sums + 2 * rel + 1), (unsigned long long)sQ);
+	}
+}
+
+/* ---- round A ----------------------------------------------------------- */
+
+struct TwLargeA {
+	const int2 *twc;     /* compact: stage s (4..7), group m at twc[(1<<s)-16+m] */
+	const PassTw *tw0;
+	template <int K>
+	SCAN_DEV int2 get(int s, int pa) const
+	{
+		const int m = pa & ((1 << s) - 1);
+		if constexpr (K == 0)
+			return tw0->w[(1 << s) - 1 + m];
+		else
+			return twc[(1 << s) - 16 + m];
+	}
+};
+
+constexpr int kLargeSmemA = kXchWords * 4 + 240 * 8 + 16;
+
+template <bool IN16>
+__global__ void __launch_bounds__(kThreads, 2)
+large_round_a_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
+{
+	SCAN_DYN_SMEM(smem);
+	c16 *stage = (c16 *)smem;
+	int2 *twc = (int2 *)(smem + kXchWords * 4);
+	int *dck = (int *)(smem + kXchWords * 4 + 240 * 8);
+	const int t = threadIdx.x, L = prm.L;
+	const int tile = blockIdx.x, rel = blockIdx.y, e = prm.entry_base + rel;
+	const long long N = 1ll << L;
+	const uint8_t *src = prm.base + large_entry_offset(prm, e);
+
+	if (t < 240) {
+		/* entry t of the compact table: stage s = 4 + floor(log2(t/16 + 1)) */
+		int s = 4, off = 0;
+		while (t >= off + (1 << s)) {
+			off += 1 << s;
+			s++;
+		}
+		twc[t] = prm.tw[(size_t)(t - off) << (L - 1 - s)];
+	}
+	if (t < 2) {
+		long long s = prm.dc_sums[2 * rel + t];
+		if constexpr (!IN16)
+			dck[t] = 127 + dc_average(s - 127ll * N, (int)(2 * N) - t);
+		else
+			dck[t] = dc_average(s, (int)(2 * N) - t);
+	}
+
+	/* gather: thread t owns row i = t, 16 consecutive input samples */
+	{
+		const long long n0 = ((long long)t << (L - 8)) + 16 * tile;
+		if constexpr (!IN16) {
+			const uint4 a = __ldg((const uint4 *)(src + 2 * n0));
+			const uint4 b = __ldg((const uint4 *)(src + 2 * n0 + 16));
+			const unsigned w[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+#pragma unroll
+			for (int c = 0; c < 16; ++c)
+				stage[xch_idx(c * 256 + t)] = (w[c >> 1] >> (16 * (c & 1))) & 0xFFFFu;
+		} else {
+#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				const uint4 a = __ldg((const uint4 *)(src + 4 * n0 + 16 * k));
+				stage[xch_idx((4 * k + 0) * 256 + t)] = a.x;
+				stage[xch_idx((4 * k + 1) * 256 + t)] = a.y;
+				stage[xch_idx((4 * k + 2) * 256 + t)] = a.z;
+				stage[xch_idx((4 * k + 3) * 256 + t)] = a.w;
+			}
+		}
+	}
+	__syncthreads();
+	const int kI = dck[0], kQ = dck[1];
+
+	/* convert + window; position 16t + r is column c = t >> 4, row bitrev8(q) */
+	c16 v[kPts];
+	const int c = t >> 4;
+	const int n_low = 16 * tile + c;
+#pragma unroll
+	for (int r = 0; r < kPts; ++r) {
+		const int i = (brev4(r) << 4) | brev_bits((unsigned)(t & 15), 4);
+		const unsigned raw = stage[xch_idx(c * 256 + i)];
+		const long long n = ((long long)i << (L - 8)) | n_low;
+		const int wv = __ldg(prm.win + n);
+		int re, im;
+		if constexpr (!IN16) {
+			re = ((int)(raw & 0xFFu) - kI) * wv;
+			im = ((int)(raw >> 8) - kQ) * wv;
+		} else {
+			re = (c16_re(raw) - kI) * wv;
+			im = (c16_im(raw) - kQ) * wv;
+		}
+		v[r] = c16_pack(re, im);
+	}
+
+	TwLargeA tw;
+	tw.twc = twc;
+	tw.tw0 = &prm.tw0;
+	engine_fft<8>(v, stage, t, tw);
+
+	/* scatter: column n_low lands on positions (bitrev(n_low) << 8) | q */
+	c16 *dst = prm.scratch + (long long)rel * N;
+#pragma unroll
+	for (int r = 0; r < kPts; ++r) {
+		const int p = last_pos<8>(t, r);
+		const int cc = p >> 8, q = p & 255;
+		const long long P = ((long long)brev_bits((unsigned)(16 * tile + cc), L - 8) << 8) | q;
+		dst[P] = v[r];
+	}
+}
+
+/* ---- round B ----------------------------------------------------------- */
+
+template <int LB>
+struct TwLargeB {
+	const int2 *tw;
+	int plow0, L;
+	template <int K>
+	SCAN_DEV int2 get(int se, int pa) const
+	{
+		const int col = pa >> LB, i = pa & ((1 << LB) - 1);
+		const long long m = ((long long)(i & ((1 << se) - 1)) << 8) | (plow0 + col);
+		return __ldg(tw + (m << (L - 9 - se)));
+	}
+};
+
+SCAN_DEV void accumulate_bin(long long *dst, c16 x, bool peak)
+{
+	const int re = c16_re(x), im = c16_im(x);
+	const unsigned pw = (unsigned)(re * re) + (unsigned)(im * im);
+	if (peak)
+		atomicMax(dst, (long long)pw);
+	else
+		atomicAdd((unsigned long long *)dst, (unsigned long long)pw);
+}
+
+template <int LB, bool LAST, bool PEAK>
+__global__ void __launch_bounds__(kThreads, 2)
+large_round_b_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
+{
+	SCAN_DYN_SMEM(smem);
+	c16 *stage = (c16 *)smem;
+	constexpr int ncols = kWS >> LB;
+	constexpr int tiles_per_u = 256 / ncols;
+	const int t = threadIdx.x, L = prm.L;
+	const int rel = blockIdx.y;
+	const long long N = 1ll << L;
+	const int U = blockIdx.x / tiles_per_u, plow0 = (blockIdx.x % tiles_per_u) * ncols;
+	c16 *data = prm.scratch + (long long)rel * N + ((long long)U << (8 + LB)) + plow0;
+
+#pragma unroll
+	for (int k = 0; k < kPts; ++k) {
+		const int eidx = t + kThreads * k;
+		const int col = eidx % ncols, i = eidx / ncols;
+		stage[xch_idx((col << LB) | i)] = data[((long long)i << 8) + col];
+	}
+	__syncthreads();
+	c16 v[kPts];
+#pragma unroll
+	for (int r = 0; r < kPts; ++r)
+		v[r] = stage[xch_idx(pos<0>(t, r))];
+
+	TwLargeB<LB> tw;
+	tw.tw = prm.tw;
+	tw.plow0 = plow0;
+	tw.L = L;
+	engine_fft<LB>(v, stage, t, tw);
+
+	__syncthreads();
+#pragma unroll
+	for (int r = 0; r < kPts; ++r)
+		stage[xch_idx(last_pos<LB>(t, r))] = v[r];
+	__syncthreads();
+	long long *out = nullptr;
+	if constexpr (LAST)
+		out = prm.avg + ((long long)prm.hop_of[prm.entry_base + rel] << L) + plow0;
+#pragma unroll
+	for (int k = 0; k < kPts; ++k) {
+		const int eidx = t + kThreads * k;
+		const int col = eidx % ncols, i = eidx / ncols;
+		const c16 x = stage[xch_idx((col << LB) | i)];
+		if constexpr (LAST)
+			accumulate_bin(out + ((long long)i << 8) + col, x, PEAK);
+		else
+			data[((long long)i << 8) + col] = x;
+	}
+}
+
+/* ---- round C ----------------------------------------------------------- */
+
+template <int LC, bool PEAK>
+__global__ void __launch_bounds__(kThreads)
+large_round_c_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
+{
+	constexpr int R = 1 << LC;
+	const int L = prm.L, rel = blockIdx.y;
+	const int plow = blockIdx.x * kThreads + threadIdx.x; /* 0 .. 65535 */
+	const long long N = 1ll << L;
+	const c16 *data = prm.scratch + (long long)rel * N + plow;
+	c16 v[R];
+#pragma unroll
+	for (int r = 0; r < R; ++r)
+		v[r] = data[(long long)r << 16];
+#pragma unroll
+	for (int se = 0; se < LC; ++se) {
+#pragma unroll
+		for (int r = 0; r < R; ++r) {
+			if ((r & (1 << se)) == 0) {
+				const long long m = ((long long)(r & ((1 << se) - 1)) << 16) | plow;
+				const int2 w = __ldg(prm.tw + (m << (L - 17 - se)));
+				butterfly(v[r], v[r | (1 << se)], w.x, w.y);
+			}
+		}
+	}
+	long long *out = prm.avg + ((long long)prm.hop_of[prm.entry_base + rel] << L) + plow;
+#pragma unroll
+	for (int r = 0; r < R; ++r)
+		accumulate_bin(out + ((long long)r << 16), v[r], PEAK);
+}
+
+} // namespace rscan

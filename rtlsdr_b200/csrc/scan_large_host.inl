@@ -1,7 +1,136 @@
+/* Host side of the N >= 8192 path (see scan_large.cuh).  Included by scan_abi.cu
+ * after the handle definition. */
 namespace {
-int large_process(rtlsdr_gpu_scan *h, const uint8_t *, const long long *, const int *, int)
+
+template <int LB, bool LAST>
+int launch_round_b_t(rtlsdr_gpu_scan *h, const LargeParams &p, dim3 grid)
 {
-	h->last_error = "large FFT path not built";
-	return RTLSDR_GPU_ERR_CONFIG;
+	const int smem = kXchWords * 4;
+	if (h->cfg.peak_hold) {
+		auto k = large_round_b_kernel<LB, LAST, true>;
+		CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		k<<<grid, kThreads, smem, h->stream>>>(p);
+	} else {
+		auto k = large_round_b_kernel<LB, LAST, false>;
+		CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		k<<<grid, kThreads, smem, h->stream>>>(p);
+	}
+	return check_launch(h, "large_round_b_kernel");
 }
+
+int launch_round_b(rtlsdr_gpu_scan *h, const LargeParams &p, dim3 grid, int lb, bool last)
+{
+	switch (lb) {
+	case 5: return last ? launch_round_b_t<5, true>(h, p, grid) : RTLSDR_GPU_ERR_CONFIG;
+	case 6: return last ? launch_round_b_t<6, true>(h, p, grid) : RTLSDR_GPU_ERR_CONFIG;
+	case 7: return last ? launch_round_b_t<7, true>(h, p, grid) : RTLSDR_GPU_ERR_CONFIG;
+	case 8: return last ? launch_round_b_t<8, true>(h, p, grid) : launch_round_b_t<8, false>(h, p, grid);
+	default: return RTLSDR_GPU_ERR_CONFIG;
+	}
+}
+
+template <int LC>
+int launch_round_c_t(rtlsdr_gpu_scan *h, const LargeParams &p, dim3 grid)
+{
+	if (h->cfg.peak_hold)
+		large_round_c_kernel<LC, true><<<grid, kThreads, 0, h->stream>>>(p);
+	else
+		large_round_c_kernel<LC, false><<<grid, kThreads, 0, h->stream>>>(p);
+	return check_launch(h, "large_round_c_kernel");
+}
+
+int launch_round_c(rtlsdr_gpu_scan *h, const LargeParams &p, dim3 grid, int lc)
+{
+	switch (lc) {
+	case 1: return launch_round_c_t<1>(h, p, grid);
+	case 2: return launch_round_c_t<2>(h, p, grid);
+	case 3: return launch_round_c_t<3>(h, p, grid);
+	case 4: return launch_round_c_t<4>(h, p, grid);
+	case 5: return launch_round_c_t<5>(h, p, grid);
+	default: return RTLSDR_GPU_ERR_CONFIG;
+	}
+}
+
+/*
+ * Entries [0, n_reads) of the (hop-sorted) batch, `chunk` at a time.
+ * Scratch per chunk: [data chunk x N c16][sums chunk x 2 int64][decimation scratch].
+ */
+int large_process(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_offs, const int *d_hops, int n_reads)
+{
+	const int L = h->cfg.bin_e;
+	const size_t N = (size_t)1 << L;
+	const bool decim = (h->cfg.boxcar && h->cfg.downsample > 1) || h->cfg.downsample_passes > 0;
+	const size_t per = N * 4 + 16 + (decim ? DecimScratch::per_entry(h) : 0);
+	const int chunk_max = (int)std::max<size_t>(1, kScratchBudget / per);
+	int rc;
+	for (int e0 = 0; e0 < n_reads; e0 += chunk_max) {
+		const int cnt = std::min(chunk_max, n_reads - e0);
+		if ((rc = ensure_scratch(h, per * (size_t)cnt + 512)))
+			return rc;
+		uint8_t *sp = h->d_scratch;
+		c16 *data = (c16 *)sp;
+		sp += (size_t)cnt * N * 4;
+		long long *sums = (long long *)sp;
+		sp += (size_t)cnt * 16;
+
+		LargeParams p;
+		memset(&p, 0, sizeof(p));
+		p.entry_base = e0;
+		p.hop_of = d_hops;
+		p.scratch = data;
+		p.dc_sums = sums;
+		p.avg = h->d_avg;
+		p.tw = h->d_tw;
+		p.win = h->d_win;
+		p.L = L;
+		p.tw0 = h->tw0;
+
+		const int smem_a = kLargeSmemA;
+		dim3 grid_tiles((unsigned)(N / kWS), (unsigned)cnt);
+		if (!decim) {
+			CU(cudaMemsetAsync(sums, 0, (size_t)cnt * 16, h->stream));
+			DcSumU8Params d;
+			d.base = base;
+			d.read_off = d_offs;
+			d.entry_base = e0;
+			d.buf_len = h->cfg.buf_len;
+			d.sums = sums;
+			dim3 g((unsigned)std::max<size_t>(1, std::min<size_t>(32, (size_t)h->cfg.buf_len / (256 * 16 * 4))), (unsigned)cnt);
+			dc_sums_u8_kernel<<<g, 256, 0, h->stream>>>(d);
+			if ((rc = check_launch(h, "dc_sums_u8_kernel")))
+				return rc;
+			p.base = base;
+			p.read_off = d_offs;
+			auto k = large_round_a_kernel<false>;
+			CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a));
+			k<<<grid_tiles, kThreads, smem_a, h->stream>>>(p);
+			if ((rc = check_launch(h, "large_round_a_kernel")))
+				return rc;
+		} else {
+			/* decimate into c16 images placed after the sums, then transform from them */
+			DecimScratch sc(h, cnt, (uint8_t *)(((uintptr_t)sp + 255) & ~(uintptr_t)255));
+			if ((rc = run_decimators(h, base, d_offs + e0, cnt, sc)))
+				return rc;
+			CU(cudaMemcpyAsync(sums, sc.sums, (size_t)cnt * 16, cudaMemcpyDeviceToDevice, h->stream));
+			p.base = (const uint8_t *)sc.img;
+			p.read_off = nullptr;
+			p.regular_stride = h->image_stride * 4;
+			auto k = large_round_a_kernel<true>;
+			CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a));
+			k<<<grid_tiles, kThreads, smem_a, h->stream>>>(p);
+			if ((rc = check_launch(h, "large_round_a_kernel")))
+				return rc;
+		}
+		const int lb = std::min(8, L - 8);
+		if ((rc = launch_round_b(h, p, grid_tiles, lb, 8 + lb == L)))
+			return rc;
+		if (L > 16) {
+			dim3 g(65536 / kThreads, (unsigned)cnt);
+			if ((rc = launch_round_c(h, p, g, L - 16)))
+				return rc;
+		}
+	}
+	return 0;
+}
+
 } // namespace

@@ -1,0 +1,72 @@
+/* large path (bin_e 13..21) through the emulator: u8 reads [n_reads][2N] -> spectra.
+ * in16 != 0: `reads` are decimated c16 images [n_reads][N] and `sums_in` their DC sums. */
+void emu_large(int L, int peak, int in16, const uint8_t *reads, int n_reads, const int *hop_of,
+	       const int *tw, const uint16_t *win, const long long *sums_in, long long *avg)
+{
+	const size_t N = (size_t)1 << L;
+	std::vector<long long> offs(n_reads);
+	for (int i = 0; i < n_reads; i++)
+		offs[i] = (long long)i * (long long)(in16 ? 4 * N : 2 * N);
+	std::vector<c16> scratch((size_t)n_reads * N, 0xDEADBEEFu);
+	std::vector<long long> sums((size_t)n_reads * 2, 0);
+	LargeParams p;
+	memset(&p, 0, sizeof(p));
+	p.base = reads;
+	p.read_off = offs.data();
+	p.entry_base = 0;
+	p.hop_of = hop_of;
+	p.scratch = scratch.data();
+	p.dc_sums = sums.data();
+	p.avg = avg;
+	p.tw = (const int2 *)tw;
+	p.win = win;
+	p.L = L;
+	fill_tw0(p.tw0, p.tw, L);
+	dim3 tiles((unsigned)(N / kWS), n_reads);
+	if (!in16) {
+		DcSumU8Params d;
+		d.base = reads;
+		d.read_off = offs.data();
+		d.entry_base = 0;
+		d.buf_len = (int)(2 * N);
+		d.sums = sums.data();
+		cuda_emu::launch(dim3(3, n_reads), dim3(256), 0, [&]() { dc_sums_u8_kernel(d); });
+		cuda_emu::launch(tiles, dim3(kThreads), kLargeSmemA, [&]() { large_round_a_kernel<false>(p); });
+	} else {
+		memcpy(sums.data(), sums_in, sums.size() * 8);
+		cuda_emu::launch(tiles, dim3(kThreads), kLargeSmemA, [&]() { large_round_a_kernel<true>(p); });
+	}
+	const int lb = L - 8 < 8 ? L - 8 : 8;
+	const bool last = 8 + lb == L;
+#define RB(LBV, LASTV)                                                                                  \
+	do {                                                                                            \
+		if (peak)                                                                               \
+			cuda_emu::launch(tiles, dim3(kThreads), kXchWords * 4, [&]() { large_round_b_kernel<LBV, LASTV, true>(p); }); \
+		else                                                                                    \
+			cuda_emu::launch(tiles, dim3(kThreads), kXchWords * 4, [&]() { large_round_b_kernel<LBV, LASTV, false>(p); }); \
+	} while (0)
+	if (lb == 5) RB(5, true);
+	else if (lb == 6) RB(6, true);
+	else if (lb == 7) RB(7, true);
+	else if (last) RB(8, true);
+	else RB(8, false);
+#undef RB
+	if (L > 16) {
+		dim3 g(65536 / kThreads, n_reads);
+#define RC(LCV)                                                                                         \
+	do {                                                                                            \
+		if (peak)                                                                               \
+			cuda_emu::launch(g, dim3(kThreads), 0, [&]() { large_round_c_kernel<LCV, true>(p); }); \
+		else                                                                                    \
+			cuda_emu::launch(g, dim3(kThreads), 0, [&]() { large_round_c_kernel<LCV, false>(p); }); \
+	} while (0)
+		switch (L - 16) {
+		case 1: RC(1); break;
+		case 2: RC(2); break;
+		case 3: RC(3); break;
+		case 4: RC(4); break;
+		case 5: RC(5); break;
+		}
+#undef RC
+	}
+}

@@ -1,0 +1,203 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI
+(include/rtlsdr_gpu_scan.h), against the oracles on identical synthetic bytes.
+Bit-exact for int64 bins and sample counts; dB within 1e-6 relative."""
+import numpy as np
+import pytest
+
+from oracles import (SYNTH_BIASED, SYNTH_CONST, SYNTH_COUNTER, SYNTH_TONE, SYNTH_XORSHIFT, WINDOWS,
+                     fnv1a_int64)
+from scan_cases import KAT_ROWS, db_close, expected, make_reads, plan_dict
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def scan_mod():
+    import rtlsdr_b200.scan as s
+    s.load_library()  # must exist on a GPU box: no fallback
+    return s
+
+
+def run_gpu(scan_mod, plan, window, reads, hops, how="submit"):
+    g = scan_mod.GpuScan.from_plan(plan, window_coefs=window)
+    try:
+        if how == "submit":
+            for r, h in zip(reads, hops):
+                g.submit(int(h), r)
+        else:
+            import torch
+            tc = plan["tune_count"]
+            passes = len(reads) // tc
+            dev = torch.from_numpy(np.ascontiguousarray(reads)).cuda()
+            torch.cuda.synchronize()
+            b = plan["buf_len"]
+            g.submit_device(0, tc, passes, dev.data_ptr(), tc * b, b)
+            g.sync()
+        avg, smp, db = g.collect_all()
+        # accumulators are zero after a collect (rtl_power.c:761-764)
+        avg2, smp2, _ = g.collect_all(want_db=False)
+        assert not avg2.any() and not smp2.any()
+        return avg, smp, db
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("bin_e", list(range(1, 13)))
+@pytest.mark.parametrize("peak", [0, 1])
+def test_u8_path_all_sizes(scan_mod, port_oracle, bin_e, peak):
+    n = 1 << bin_e
+    rng = np.random.default_rng(bin_e * 2 + peak)
+    plan = plan_dict(bin_e, peak_hold=peak, tune_count=3, crop=0.1 if bin_e > 3 else 0.0)
+    window = port_oracle.window_coefs(WINDOWS[bin_e % len(WINDOWS)], n)
+    if bin_e % 5 == 0:
+        window = rng.integers(-70000, 70000, n).astype(np.int32)  # only the low 16 bits can matter
+    reads, hops = make_reads(port_oracle.lib, plan, 4, SYNTH_BIASED, seed=bin_e, param=11)
+    reads[1, :] = 255
+    reads[2, :] = 0
+    reads[5, 0::2] = 255
+    want = expected(port_oracle, plan, window, reads, hops)
+    got = run_gpu(scan_mod, plan, window, reads, hops)
+    assert np.array_equal(got[0], want[0])
+    assert np.array_equal(got[1], want[1])
+    assert db_close(got[2], want[2])
+
+
+@pytest.mark.parametrize("window", WINDOWS)
+@pytest.mark.parametrize("mode,param", [(SYNTH_XORSHIFT, 0), (SYNTH_COUNTER, 0), (SYNTH_CONST, 127),
+                                        (SYNTH_CONST, 255), (SYNTH_TONE, 126)])
+def test_windows_and_input_classes(scan_mod, port_oracle, window, mode, param):
+    plan = plan_dict(10, tune_count=2, rate=2400000)
+    w = port_oracle.window_coefs(window, 1024)
+    reads, hops = make_reads(port_oracle.lib, plan, 3, mode, seed=5, param=param)
+    want = expected(port_oracle, plan, w, reads, hops)
+    got = run_gpu(scan_mod, plan, w, reads, hops, how="device")
+    assert np.array_equal(got[0], want[0])
+    assert np.array_equal(got[1], want[1])
+    assert db_close(got[2], want[2])
+
+
+@pytest.mark.parametrize("row", KAT_ROWS, ids=[f"{r[0]}-{r[2]}-F{r[3]}-P{r[4]}" for r in KAT_ROWS])
+def test_survey_known_answers(scan_mod, port_oracle, row):
+    """FNV-1a of the reference's int64 bins, generated from the
+    unmodified reference; the GPU path must reproduce every hash."""
+    from rtlsdr_b200.planner import plan_scan
+    freq, crop, window, fir, peak, passes, mode, fnv = row
+    plan = plan_scan(freq, crop, None if fir < 0 else fir).as_dict()
+    plan["peak_hold"] = peak
+    w = port_oracle.window_coefs(window, 1 << plan["bin_e"])
+    reads, hops = make_reads(port_oracle.lib, plan, passes, mode, seed=0, param=0)
+    how = "device" if plan["tune_count"] > 100 else "submit"
+    avg, smp, db = run_gpu(scan_mod, plan, w, reads, hops, how=how)
+    assert fnv1a_int64(avg) == fnv
+
+
+@pytest.mark.parametrize("freq,window,fir,peak", [
+    ("100M:100.1M:100", "rectangle", -1, 0),   # boxcar ds=28, B=57344
+    ("100M:100.1M:100", "blackman", 9, 0),     # 4 x fifth_order + 9-tap FIR
+    ("100M:100.1M:100", "youssef", 0, 1),      # 4 x fifth_order, no FIR, peak hold
+    ("100M:100.5M:10k", "bartlett", -1, 0),    # ds=5, clamped buffer, partial tail block
+    ("100M:100.3M:3k", "hamming", -1, 1),      # ds=9
+    ("100M:100.9M:30k", "hamming", -1, 0),     # ds=3, odd l_len
+    ("100M:100.01M:50", "hamming", 9, 0),      # 8 passes, B=131072
+])
+@pytest.mark.parametrize("mode,param", [(SYNTH_XORSHIFT, 0), (SYNTH_BIASED, 40), (SYNTH_CONST, 255)])
+def test_decimating_paths(scan_mod, port_oracle, freq, window, fir, peak, mode, param):
+    from rtlsdr_b200.planner import plan_scan
+    plan = plan_scan(freq, 0.0, None if fir < 0 else fir).as_dict()
+    plan["peak_hold"] = peak
+    w = port_oracle.window_coefs(window, 1 << plan["bin_e"])
+    reads, hops = make_reads(port_oracle.lib, plan, 3, mode, seed=9, param=param)
+    want = expected(port_oracle, plan, w, reads, hops)
+    got = run_gpu(scan_mod, plan, w, reads, hops)
+    assert np.array_equal(got[0], want[0])
+    assert np.array_equal(got[1], want[1])
+    assert db_close(got[2], want[2])
+
+
+@pytest.mark.parametrize("peak", [0, 1])
+def test_rms_path(scan_mod, port_oracle, peak):
+    plan = plan_dict(0, tune_count=5, peak_hold=peak, rate=1000000)
+    reads, hops = make_reads(port_oracle.lib, plan, 4, SYNTH_BIASED, seed=2, param=25)
+    want = expected(port_oracle, plan, np.zeros(1, np.int32), reads, hops)
+    got = run_gpu(scan_mod, plan, None, reads, hops)
+    assert np.array_equal(got[0], want[0])
+    assert np.array_equal(got[1], want[1])
+    assert db_close(got[2], want[2])
+
+
+def test_per_hop_collect_and_reaccumulate(scan_mod, port_oracle):
+    """collect(hop) zeroes only that hop; later submits accumulate from zero."""
+    plan = plan_dict(9, tune_count=3)
+    w = port_oracle.window_coefs("hamming", 512)
+    reads, hops = make_reads(port_oracle.lib, plan, 2, SYNTH_XORSHIFT, seed=1)
+    want = expected(port_oracle, plan, w, reads, hops)
+    g = scan_mod.GpuScan.from_plan(plan, window_coefs=w)
+    try:
+        for r, h in zip(reads, hops):
+            g.submit(int(h), r)
+        a1, s1, d1 = g.collect(1)
+        assert np.array_equal(a1, want[0][1]) and s1 == want[1][1] and db_close(d1, want[2][1])
+        for r, h in zip(reads, hops):
+            g.submit(int(h), r)
+        a1b, s1b, _ = g.collect(1)
+        assert np.array_equal(a1b, want[0][1]) and s1b == want[1][1]
+        a0, s0, _ = g.collect(0)
+        assert np.array_equal(a0, 2 * want[0][0]) and s0 == 2 * want[1][0]
+    finally:
+        g.close()
+
+
+def test_error_codes(scan_mod):
+    g = scan_mod.GpuScan(2, 10, 16384)
+    try:
+        with pytest.raises(scan_mod.ScanError) as e:
+            g.submit(2, np.zeros(16384, np.uint8))
+        assert e.value.code == -3
+        with pytest.raises(scan_mod.ScanError) as e:
+            g.submit(0, np.zeros(100, np.uint8))
+        assert e.value.code == -4
+    finally:
+        g.close()
+    with pytest.raises(scan_mod.ScanError) as e:
+        scan_mod.GpuScan(0, 10, 16384)
+    assert e.value.code == -2
+
+
+@pytest.mark.parametrize("bin_e,peak,window", [(13, 0, "hamming"), (14, 1, "blackman"), (15, 0, "rectangle"),
+                                               (16, 0, "youssef"), (17, 1, "blackman-harris"),
+                                               (18, 0, "bartlett"), (20, 0, "hann-poisson"), (21, 1, "hamming")])
+def test_large_fft_path(scan_mod, port_oracle, bin_e, peak, window):
+    """N >= 8192: one FFT block per read, three-round transform through global scratch."""
+    n = 1 << bin_e
+    plan = plan_dict(bin_e, buf_len=2 * n, peak_hold=peak, tune_count=2, crop=0.25)
+    w = port_oracle.window_coefs(window, n)
+    reads, hops = make_reads(port_oracle.lib, plan, 2, SYNTH_BIASED, seed=bin_e, param=-17)
+    reads[1, : n // 2] = 255
+    want = expected(port_oracle, plan, w, reads, hops)
+    got = run_gpu(scan_mod, plan, w, reads, hops)
+    assert np.array_equal(got[0], want[0])
+    assert np.array_equal(got[1], want[1])
+    assert db_close(got[2], want[2])
+
+
+def test_large_fft_with_decimation(scan_mod, port_oracle):
+    """narrow scan with many bins: boxcar ds=3 feeding a 2^13-point transform."""
+    from rtlsdr_b200.planner import plan_scan
+    plan = plan_scan("100M:100.9M:120", 0.0).as_dict()
+    assert plan["bin_e"] == 13 and plan["downsample"] == 3
+    plan["peak_hold"] = 0
+    w = port_oracle.window_coefs("hamming", 1 << plan["bin_e"])
+    reads, hops = make_reads(port_oracle.lib, plan, 3, SYNTH_BIASED, seed=4, param=21)
+    want = expected(port_oracle, plan, w, reads, hops)
+    got = run_gpu(scan_mod, plan, w, reads, hops)
+    assert np.array_equal(got[0], want[0])
+    assert np.array_equal(got[1], want[1])
+    assert db_close(got[2], want[2])
+    plan = plan_scan("100M:100.9M:120", 0.0, 9).as_dict()  # -F 9: 1 fifth_order pass + FIR
+    plan["peak_hold"] = 1
+    w = port_oracle.window_coefs("blackman", 1 << plan["bin_e"])
+    reads, hops = make_reads(port_oracle.lib, plan, 2, SYNTH_TONE, seed=4, param=100)
+    want = expected(port_oracle, plan, w, reads, hops)
+    got = run_gpu(scan_mod, plan, w, reads, hops)
+    assert np.array_equal(got[0], want[0])
+    assert np.array_equal(got[1], want[1])
