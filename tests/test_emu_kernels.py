@@ -1,0 +1,147 @@
+"""The CUDA kernel SOURCE (rtlsdr_b200/csrc/*.cuh) compiled with g++ against the
+test-only emulator tests/emu/cuda_emu.h and compared with the oracle.  This is
+how kernel index math is checked on the GPU-less build box; the -m gpu suite
+repeats the same cases on real hardware through the C ABI."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracles import SYNTH_BIASED, SYNTH_CONST, SYNTH_TONE, SYNTH_XORSHIFT
+from scan_cases import expected, make_reads, plan_dict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+CSRC = os.path.join(ROOT, "rtlsdr_b200", "csrc")
+EMU_SO = os.path.join(EMU_DIR, "libscan_emu.so")
+
+
+def vp(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+@pytest.fixture(scope="module")
+def emu():
+    srcs = [os.path.join(EMU_DIR, f) for f in ("emu_entry.cpp", "emu_large.inl", "cuda_emu.h")]
+    srcs += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    if not os.path.exists(EMU_SO) or any(os.path.getmtime(s) > os.path.getmtime(EMU_SO) for s in srcs):
+        subprocess.run(["g++", "-std=c++20", "-O2", "-DSCAN_EMU", "-I" + EMU_DIR, "-I" + CSRC, "-shared",
+                        "-fPIC", "-pthread", "-o", EMU_SO, os.path.join(EMU_DIR, "emu_entry.cpp")], check=True)
+    return ctypes.CDLL(EMU_SO)
+
+
+def twiddles(sine, bin_e):
+    """wr = Sinewave[j + N/4] >> 1, wi = (-Sinewave[j]) >> 1 (rtl_power.c:305-308)"""
+    n = 1 << bin_e
+    s = np.concatenate([sine.astype(np.int16), np.zeros(4, np.int16)])
+    j = np.arange(max(n // 2, 1))
+    wr = (s[j + n // 4] >> 1).astype(np.int32)
+    wi = ((-s[j]).astype(np.int16) >> 1).astype(np.int32)
+    return np.ascontiguousarray(np.stack([wr, wi], 1))
+
+
+def sort_by_hop(reads, hops, tune_count, split=2):
+    order = np.argsort(hops, kind="stable")
+    reads, hops = np.ascontiguousarray(reads[order]), hops[order]
+    segs = []
+    for h in range(tune_count):
+        idx = np.nonzero(hops == h)[0]
+        if len(idx) == 0:
+            continue
+        cuts = np.linspace(0, len(idx), min(split, len(idx)) + 1).astype(int)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            if b > a:
+                segs.append((h, idx[0] + a, b - a, 0))
+    return reads, hops, np.array(segs, dtype=np.int32)
+
+
+@pytest.mark.parametrize("bin_e", list(range(1, 13)))
+def test_small_u8_kernel(emu, port_oracle, bin_e):
+    n = 1 << bin_e
+    rng = np.random.default_rng(bin_e)
+    for peak in (0, 1):
+        plan = plan_dict(bin_e, peak_hold=peak, tune_count=2)
+        win = rng.integers(-70000, 70000, n).astype(np.int32) if bin_e % 2 else port_oracle.window_coefs("hamming", n)
+        reads, hops = make_reads(port_oracle.lib, plan, 3, SYNTH_BIASED, seed=bin_e, param=10)
+        reads[1, :] = 255
+        reads[2, :] = 0
+        want, _, _ = expected(port_oracle, plan, win, reads, hops)
+        sreads, _, segs = sort_by_hop(reads, hops, 2)
+        tw = twiddles(port_oracle.sine_table(bin_e), bin_e)
+        w16 = (win & 0xFFFF).astype(np.uint16)
+        avg = np.zeros((2, n), dtype=np.int64)
+        emu.emu_small_u8(bin_e, peak, vp(sreads), len(sreads), vp(segs), len(segs), vp(tw), vp(w16), vp(avg))
+        assert np.array_equal(avg, want), (bin_e, peak)
+
+
+@pytest.mark.parametrize("freq,window,fir,peak", [
+    ("100M:100.1M:100", "rectangle", -1, 0), ("100M:100.1M:100", "blackman", 9, 0),
+    ("100M:100.1M:100", "youssef", 0, 1), ("100M:100.5M:10k", "bartlett", -1, 0),
+    ("100M:100.3M:3k", "hamming", -1, 1), ("100M:100.9M:30k", "hamming", -1, 0),
+    ("100M:100.01M:50", "hamming", 9, 0)])
+def test_decimating_kernels(emu, port_oracle, freq, window, fir, peak):
+    from rtlsdr_b200.planner import plan_scan
+    plan = plan_scan(freq, 0.0, None if fir < 0 else fir).as_dict()
+    plan["peak_hold"] = peak
+    bin_e, n = plan["bin_e"], 1 << plan["bin_e"]
+    win = port_oracle.window_coefs(window, n)
+    for mode, param in ((SYNTH_XORSHIFT, 0), (SYNTH_BIASED, 40), (SYNTH_CONST, 255), (SYNTH_TONE, 127)):
+        reads, hops = make_reads(port_oracle.lib, plan, 2, mode, seed=3, param=param)
+        want, _, _ = expected(port_oracle, plan, win, reads, hops)
+        segs = np.array([(0, 0, len(reads), 0)], dtype=np.int32)
+        tw = twiddles(port_oracle.sine_table(bin_e), bin_e)
+        w16 = (win & 0xFFFF).astype(np.uint16)
+        avg = np.zeros((1, n), dtype=np.int64)
+        box = plan["boxcar"] and plan["downsample"] > 1
+        fir5 = None
+        if not box and plan["comp_fir_size"] == 9 and plan["downsample_passes"] <= 10:
+            fir5 = np.array(list(port_oracle.lib.oracle_cic9(plan["downsample_passes"]).contents)[1:6], dtype=np.int32)
+        emu.emu_small_decim(bin_e, peak, vp(reads), len(reads), plan["buf_len"], plan["downsample"],
+                            plan["downsample_passes"], 0 if box else 1, vp(fir5), vp(segs), 1, vp(tw), vp(w16),
+                            vp(avg), None, None)
+        assert np.array_equal(avg, want), (freq, mode)
+
+
+@pytest.mark.parametrize("bin_e,peak", [(13, 0), (13, 1), (14, 0), (15, 0), (16, 1), (17, 0), (18, 1)])
+def test_large_kernels(emu, port_oracle, bin_e, peak):
+    n = 1 << bin_e
+    plan = plan_dict(bin_e, buf_len=2 * n, peak_hold=peak, tune_count=2)
+    win = port_oracle.window_coefs("blackman-harris" if bin_e % 2 else "hamming", n)
+    reads, hops = make_reads(port_oracle.lib, plan, 2, SYNTH_BIASED, seed=bin_e, param=35)
+    reads, hops = reads[:3], hops[:3]
+    want, _, _ = expected(port_oracle, plan, win, reads, hops)
+    sreads, shops, _ = sort_by_hop(reads, hops, 2)
+    tw = twiddles(port_oracle.sine_table(bin_e), bin_e)
+    w16 = (win & 0xFFFF).astype(np.uint16)
+    avg = np.zeros((2, n), dtype=np.int64)
+    emu.emu_large(bin_e, peak, 0, vp(sreads), len(sreads), vp(shops.astype(np.int32)), vp(tw), vp(w16), None, vp(avg))
+    assert np.array_equal(avg, want)
+
+
+def test_rms_and_epilogue_kernels(emu, port_oracle):
+    rng = np.random.default_rng(3)
+    for peak in (0, 1):
+        plan = plan_dict(0, tune_count=3, peak_hold=peak, rate=1000000)
+        reads, hops = make_reads(port_oracle.lib, plan, 3, SYNTH_BIASED, seed=1, param=50)
+        want, smp, db = expected(port_oracle, plan, np.zeros(1, np.int32), reads, hops)
+        avg = np.zeros(3, dtype=np.int64)
+        emu.emu_rms(vp(reads), len(reads), 16384, vp(hops.astype(np.int32)), peak, vp(avg))
+        assert np.array_equal(avg, want[:, 0])
+        out = np.zeros((3, 2), dtype=np.float64)
+        emu.emu_epilogue(vp(avg), vp(smp.astype(np.int32)), vp(out), 0, 0, 0, 1000000, 3)
+        assert np.allclose(out, db, rtol=1e-12)
+    # dB epilogue with crop on a 256-bin spectrum, incl. a zero bin (-inf)
+    avg = rng.integers(1, 1 << 40, (2, 256)).astype(np.int64)
+    avg[1, 7] = 0
+    smp = np.array([8, 24], dtype=np.int32)
+    crop = 0.3
+    i1, i2 = int(256 * crop * 0.5), 255 - int(256 * crop * 0.5)
+    out = np.zeros((2, i2 - i1 + 2), dtype=np.float64)
+    emu.emu_epilogue(vp(avg), vp(smp), vp(out), 8, i1, i2, 2400000, 2)
+    for h in range(2):
+        _, db = port_oracle.epilogue(avg[h], 8, crop, 2400000, int(smp[h]))
+        fin = np.isfinite(db)
+        assert np.array_equal(np.isfinite(out[h]), fin)
+        assert np.allclose(out[h][fin], db[fin], rtol=1e-12)

@@ -1,0 +1,78 @@
+"""world_size-2 gloo test of the hop sharding + per-interval gather (host logic
+of rtlsdr_b200/sweep.py).  The per-rank spectra come from the oracle here; on
+the GPU box the same code moves what rtlsdr_gpu_scan_collect_device() wrote."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from rtlsdr_b200.sweep import SpectrumGather, max_hops_per_rank, shard_hops
+
+
+def test_shard_hops_partitions_exactly():
+    for tc in (1, 2, 9, 10, 512, 623, 3000):
+        for world in (1, 2, 3, 4, 8):
+            seen = []
+            for r in range(world):
+                seen += list(shard_hops(tc, world, r))
+            assert seen == list(range(tc))
+            sizes = [len(shard_hops(tc, world, r)) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+            assert max(sizes) == max_hops_per_rank(tc, world)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, tune_count, bin_e, out_path):
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    sys.path.insert(0, os.path.dirname(here))
+    from oracles import PortOracle, SYNTH_BIASED
+    from scan_cases import expected, make_reads, plan_dict
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        port_o = PortOracle()
+        n = 1 << bin_e
+        plan = plan_dict(bin_e, tune_count=tune_count, crop=0.2, rate=2777777)
+        w = port_o.window_coefs("hamming", n)
+        reads, hops = make_reads(port_o.lib, plan, 2, SYNTH_BIASED, seed=11, param=12)
+        mine = shard_hops(tune_count, world, rank)
+        sel = np.isin(hops, list(mine))
+        # every rank only ever sees the reads of its own hops
+        sub = dict(plan)
+        avg, smp, db = expected(port_o, sub, w, reads[sel], hops[sel])
+        g = SpectrumGather(tune_count, n, db.shape[1], world, rank, "cpu")
+        a, d, s = g.views()
+        a.copy_(torch.from_numpy(avg[mine.start: mine.stop]))
+        d.copy_(torch.from_numpy(db[mine.start: mine.stop]))
+        s.copy_(torch.from_numpy(smp[mine.start: mine.stop].astype(np.int64)))
+        rep = g.gather()
+        if rank == 0:
+            full = expected(port_o, plan, w, reads, hops)
+            ok = (np.array_equal(rep.avg, full[0]) and np.array_equal(rep.samples, full[1])
+                  and np.array_equal(rep.db, full[2], equal_nan=True))
+            with open(out_path, "w") as f:
+                f.write("ok" if ok else "mismatch")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("tune_count", [2, 5])
+def test_gather_world_size_2(tmp_path, tune_count):
+    out = tmp_path / "result.txt"
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, tune_count, 8, str(out)), nprocs=2, join=True)
+    assert out.read_text() == "ok"
