@@ -894,6 +894,13 @@ int rtlsdr_gpu_scan_init(const rtlsdr_gpu_scan_cfg_t *cfg, rtlsdr_gpu_scan_t **o
 				int16_t wi = (int16_t)((int16_t)(-sine[j]) >> 1);
 				h->tw_host[j] = make_int2(wr, wi);
 			}
+			/* the kernels special-case the angle-0 and quarter-turn groups of the first
+			 * four stages: (wr, 0) and (0, wi).  True for every table sine_table()
+			 * builds (Sinewave[0] = Sinewave[N/2] = 0); reject tables where it is not. */
+			if (h->tw_host[0].y != 0 || (N >= 4 && h->tw_host[N / 4].x != 0)) {
+				rc = RTLSDR_GPU_ERR_CONFIG;
+				break;
+			}
 			memset(&h->tw0, 0, sizeof(h->tw0));
 			for (int b = 0; b < 4 && b < cfg->bin_e; b++)
 				for (int g = 0; g < (1 << b); g++)

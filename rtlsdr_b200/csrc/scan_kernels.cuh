@@ -56,6 +56,7 @@ SCAN_DEV int fix_mpy(int w, int x) { return (w * x + 16384) >> 15; }
  * (wr, wi) is the twiddle AFTER its halving (wr = Sinewave[j+N/4] >> 1,
  * wi = (-Sinewave[j]) >> 1, rtl_power.c:305-308).  tr/ti cannot leave int16
  * (|w| <= 16384); the four q +- t results wrap to int16 in c16_pack.
+ * Reference form; the hot loops use the high-half form below.
  */
 SCAN_DEV void butterfly(c16 &a, c16 &b, int wr, int wi)
 {
@@ -65,6 +66,71 @@ SCAN_DEV void butterfly(c16 &a, c16 &b, int wr, int wi)
 	const int qr = c16_re(a) >> 1, qi = c16_im(a) >> 1;
 	b = c16_pack(qr - tr, qi - ti);
 	a = c16_pack(qr + tr, qi + ti);
+}
+
+/*
+ * High-half ("X") form used inside a pass: a component v lives in the TOP 16
+ * bits of a 32-bit register, the low 16 bits are don't-care.  Then
+ *   - the int16 wrap of q +- t is the natural mod-2^32 wrap of x + (t << 16),
+ *   - the arithmetic halving q = v >> 1 is x >> 1 (the bit shifted out lands in
+ *     the don't-care half and can never carry back up),
+ *   - the sign-extended multiplicand is x >> 16.
+ * Per butterfly: 4 IMAD + 4 (t<<16 +- q) on the FMA pipe, 2+2+2+2 shifts /
+ * shift-adds on the ALU pipe: 8 + 8, balanced for the two half-rate integer
+ * pipes of an sm_100 SM sub-partition (tools/ubench.cu measures both at 64
+ * lanes/clk/SM and shows they dual-issue).
+ */
+struct X2 {
+	int re, im;
+};
+
+SCAN_DEV X2 x_unpack(c16 v)
+{
+	X2 x;
+	x.re = (int)(v << 16);
+	x.im = (int)v; /* low half = re bits: don't care */
+	return x;
+}
+
+SCAN_DEV c16 x_pack(X2 x)
+{
+	return __byte_perm((uint32_t)x.re, (uint32_t)x.im, 0x7632); /* one PRMT: bytes 2,3 of re | bytes 2,3 of im */
+}
+
+SCAN_DEV void butterfly_x(X2 &a, X2 &b, int wr, int wi)
+{
+	const int br = b.re >> 16, bi = b.im >> 16;
+	const int tr = ((wr * br + 16384) >> 15) - ((wi * bi + 16384) >> 15);
+	const int ti = ((wr * bi + 16384) >> 15) + ((wi * br + 16384) >> 15);
+	const int hr = a.re >> 1, hi = a.im >> 1;
+	b.re = hr - tr * 65536;
+	b.im = hi - ti * 65536;
+	a.re = hr + tr * 65536;
+	a.im = hi + ti * 65536;
+}
+
+/* twiddle (wr, 0): first group of every stage (angle 0) */
+SCAN_DEV void butterfly_x_re(X2 &a, X2 &b, int wr)
+{
+	const int tr = (wr * (b.re >> 16) + 16384) >> 15;
+	const int ti = (wr * (b.im >> 16) + 16384) >> 15;
+	const int hr = a.re >> 1, hi = a.im >> 1;
+	b.re = hr - tr * 65536;
+	b.im = hi - ti * 65536;
+	a.re = hr + tr * 65536;
+	a.im = hi + ti * 65536;
+}
+
+/* twiddle (0, wi): the quarter-turn group (Sinewave[N/2] = 0) */
+SCAN_DEV void butterfly_x_im(X2 &a, X2 &b, int wi)
+{
+	const int tr = -((wi * (b.im >> 16) + 16384) >> 15);
+	const int ti = (wi * (b.re >> 16) + 16384) >> 15;
+	const int hr = a.re >> 1, hi = a.im >> 1;
+	b.re = hr - tr * 65536;
+	b.im = hi - ti * 65536;
+	a.re = hr + tr * 65536;
+	a.im = hi + ti * 65536;
 }
 
 /* ---- working-set geometry ---------------------------------------------- */
@@ -95,9 +161,11 @@ SCAN_DEV int brev_bits(unsigned v, int bits)
  * low LE bits of the position (LE <= 12).  Pass K covers stages
  * [4K, min(4K+4, LE)).  TW::get<K>(s, pa) returns the halved twiddle of stage s
  * for the butterfly whose upper ("a") element sits at position pa.
+ * TW::kTrivial: pass-0 groups 0 and 2^(s-1) have twiddles (wr, 0) and (0, wi)
+ * (true for every table sine_table() builds; checked by the host at init).
  */
 template <int K, int LE, class TW>
-SCAN_DEV void run_pass(c16 (&v)[kPts], int t, const TW &tw)
+SCAN_DEV void run_pass(X2 (&x)[kPts], int t, const TW &tw)
 {
 	constexpr int s0 = 4 * K;
 	constexpr int ns = (LE - s0) < 4 ? (LE - s0) : 4;
@@ -107,38 +175,44 @@ SCAN_DEV void run_pass(c16 (&v)[kPts], int t, const TW &tw)
 		for (int r = 0; r < kPts; ++r) {
 			if ((r & (1 << b)) == 0) {
 				const int2 w = tw.template get<K>(s0 + b, pos<K>(t, r));
-				butterfly(v[r], v[r | (1 << b)], w.x, w.y);
+				const int g = r & ((1 << b) - 1);
+				if (K == 0 && TW::kTrivial && g == 0)
+					butterfly_x_re(x[r], x[r | (1 << b)], w.x);
+				else if (K == 0 && TW::kTrivial && b > 0 && g == (1 << (b - 1)))
+					butterfly_x_im(x[r], x[r | (1 << b)], w.y);
+				else
+					butterfly_x(x[r], x[r | (1 << b)], w.x, w.y);
 			}
 		}
 	}
 }
 
 template <int KA, int KB>
-SCAN_DEV void exchange(c16 (&v)[kPts], c16 *xch, int t)
+SCAN_DEV void exchange(X2 (&x)[kPts], c16 *xch, int t)
 {
 	__syncthreads(); /* every reader of the previous transpose is done */
 #pragma unroll
 	for (int r = 0; r < kPts; ++r)
-		xch[xch_idx(pos<KA>(t, r))] = v[r];
+		xch[xch_idx(pos<KA>(t, r))] = x_pack(x[r]);
 	__syncthreads();
 #pragma unroll
 	for (int r = 0; r < kPts; ++r)
-		v[r] = xch[xch_idx(pos<KB>(t, r))];
+		x[r] = x_unpack(xch[xch_idx(pos<KB>(t, r))]);
 }
 
 /* Runs stages 0..LE-1; on return register r of thread t holds position
  * pos<(LE-1)/4>(t, r). */
 template <int LE, class TW>
-SCAN_DEV void engine_fft(c16 (&v)[kPts], c16 *xch, int t, const TW &tw)
+SCAN_DEV void engine_fft(X2 (&x)[kPts], c16 *xch, int t, const TW &tw)
 {
-	run_pass<0, LE>(v, t, tw);
+	run_pass<0, LE>(x, t, tw);
 	if constexpr (LE > 4) {
-		exchange<0, 1>(v, xch, t);
-		run_pass<1, LE>(v, t, tw);
+		exchange<0, 1>(x, xch, t);
+		run_pass<1, LE>(x, t, tw);
 	}
 	if constexpr (LE > 8) {
-		exchange<1, 2>(v, xch, t);
-		run_pass<2, LE>(v, t, tw);
+		exchange<1, 2>(x, xch, t);
+		run_pass<2, LE>(x, t, tw);
 	}
 }
 
@@ -180,7 +254,8 @@ struct SmallSmem {
 	static constexpr int off_stage = 0;
 	static constexpr int off_xch = 2 * kStageBytes;
 	static constexpr int off_tw = off_xch + kXchWords * 4;
-	static constexpr int off_win = off_tw + (N / 2 > 0 ? N / 2 : 1) * 8;
+	static constexpr int tw_entries = N > 16 ? N - 16 : 1; /* stages 4..L-1, group m of stage s at (1<<s)-16+m */
+	static constexpr int off_win = off_tw + tw_entries * 8;
 	static constexpr int off_red = (off_win + N * 2 + 15) & ~15;
 	static constexpr int off_dck = off_red + 16 * 8; /* after red[8 warps][2] */
 	static constexpr int bytes = off_dck + 16;
@@ -188,7 +263,8 @@ struct SmallSmem {
 
 template <int L>
 struct TwSmall {
-	const int2 *tws;
+	static constexpr bool kTrivial = true;
+	const int2 *tws;   /* shared: stage s >= 4, group m at (1<<s)-16+m -> consecutive lanes, consecutive words */
 	const PassTw *tw0;
 	template <int K>
 	SCAN_DEV int2 get(int s, int pa) const
@@ -197,7 +273,7 @@ struct TwSmall {
 		if constexpr (K == 0)
 			return tw0->w[(1 << s) - 1 + m]; /* compile-time index: constant bank */
 		else
-			return tws[m << (L - 1 - s)];
+			return tws[(1 << s) - 16 + m];
 	}
 };
 
@@ -227,8 +303,11 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 	int *dck = (int *)(smem + SM::off_dck);
 
 	const int t = threadIdx.x;
-	for (int i = t; i < N / 2; i += kThreads)
-		tws[i] = prm.tw[i];
+	for (int i = t; i < N - 16; i += kThreads) {
+		/* entry i of the compact table: stage s with (1<<s)-16 <= i < (2<<s)-16 */
+		const int s = 31 - __clz(i + 16);
+		tws[i] = prm.tw[(i + 16 - (1 << s)) << (L - 1 - s)];
+	}
 	for (int i = t; i < N; i += kThreads)
 		wins[i] = prm.win[i];
 
@@ -331,7 +410,7 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 
 #pragma unroll 1
 			for (int ws = 0; ws < kWsPerUnit; ++ws) {
-				c16 v[kPts];
+				X2 x[kPts];
 				/* ---- convert, remove DC, window, bit-reversed placement ---- */
 #pragma unroll
 				for (int r = 0; r < kPts; ++r) {
@@ -360,15 +439,16 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 						re *= wv;
 						im *= wv;
 					}
-					v[r] = c16_pack(re, im);
+					x[r].re = re << 16;
+					x[r].im = im << 16;
 				}
 
-				engine_fft<L>(v, xch, t, tw);
+				engine_fft<L>(x, xch, t, tw);
 
 				/* ---- |X|^2 (rtl_power.c:636-640, 708-716) ---- */
 #pragma unroll
 				for (int r = 0; r < kPts; ++r) {
-					const int re = c16_re(v[r]), im = c16_im(v[r]);
+					const int re = x[r].re >> 16, im = x[r].im >> 16;
 					const unsigned pw = (unsigned)(re * re) + (unsigned)(im * im);
 					bool ok = true;
 					if constexpr (IN16)

@@ -86,6 +86,7 @@ dc_sums_u8_kernel(const SCAN_GRID_CONSTANT DcSumU8Params prm)
 /* ---- round A ----------------------------------------------------------- */
 
 struct TwLargeA {
+	static constexpr bool kTrivial = true;
 	const int2 *twc;     /* compact: stage s (4..7), group m at twc[(1<<s)-16+m] */
 	const PassTw *tw0;
 	template <int K>
@@ -156,7 +157,7 @@ large_round_a_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
 	const int kI = dck[0], kQ = dck[1];
 
 	/* convert + window; position 16t + r is column c = t >> 4, row bitrev8(q) */
-	c16 v[kPts];
+	X2 x[kPts];
 	const int c = t >> 4;
 	const int n_low = 16 * tile + c;
 #pragma unroll
@@ -173,13 +174,14 @@ large_round_a_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
 			re = (c16_re(raw) - kI) * wv;
 			im = (c16_im(raw) - kQ) * wv;
 		}
-		v[r] = c16_pack(re, im);
+		x[r].re = re << 16;
+		x[r].im = im << 16;
 	}
 
 	TwLargeA tw;
 	tw.twc = twc;
 	tw.tw0 = &prm.tw0;
-	engine_fft<8>(v, stage, t, tw);
+	engine_fft<8>(x, stage, t, tw);
 
 	/* scatter: column n_low lands on positions (bitrev(n_low) << 8) | q */
 	c16 *dst = prm.scratch + (long long)rel * N;
@@ -188,7 +190,7 @@ large_round_a_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
 		const int p = last_pos<8>(t, r);
 		const int cc = p >> 8, q = p & 255;
 		const long long P = ((long long)brev_bits((unsigned)(16 * tile + cc), L - 8) << 8) | q;
-		dst[P] = v[r];
+		dst[P] = x_pack(x[r]);
 	}
 }
 
@@ -196,6 +198,7 @@ large_round_a_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
 
 template <int LB>
 struct TwLargeB {
+	static constexpr bool kTrivial = false;
 	const int2 *tw;
 	int plow0, L;
 	template <int K>
@@ -238,21 +241,21 @@ large_round_b_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
 		stage[xch_idx((col << LB) | i)] = data[((long long)i << 8) + col];
 	}
 	__syncthreads();
-	c16 v[kPts];
+	X2 x[kPts];
 #pragma unroll
 	for (int r = 0; r < kPts; ++r)
-		v[r] = stage[xch_idx(pos<0>(t, r))];
+		x[r] = x_unpack(stage[xch_idx(pos<0>(t, r))]);
 
 	TwLargeB<LB> tw;
 	tw.tw = prm.tw;
 	tw.plow0 = plow0;
 	tw.L = L;
-	engine_fft<LB>(v, stage, t, tw);
+	engine_fft<LB>(x, stage, t, tw);
 
 	__syncthreads();
 #pragma unroll
 	for (int r = 0; r < kPts; ++r)
-		stage[xch_idx(last_pos<LB>(t, r))] = v[r];
+		stage[xch_idx(last_pos<LB>(t, r))] = x_pack(x[r]);
 	__syncthreads();
 	long long *out = nullptr;
 	if constexpr (LAST)

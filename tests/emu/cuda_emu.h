@@ -144,3 +144,12 @@ static inline T emu_atomic_max(T *p, T v)
 }
 static inline long long atomicMax(long long *p, long long v) { return emu_atomic_max(p, v); }
 static inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) { return emu_atomic_max(p, v); }
+static inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
+static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel)
+{
+	const unsigned long long v = ((unsigned long long)b << 32) | a;
+	unsigned r = 0;
+	for (int i = 0; i < 4; i++)
+		r |= (unsigned)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+	return r;
+}

@@ -201,3 +201,29 @@ def test_large_fft_with_decimation(scan_mod, port_oracle):
     got = run_gpu(scan_mod, plan, w, reads, hops)
     assert np.array_equal(got[0], want[0])
     assert np.array_equal(got[1], want[1])
+
+
+def test_cli_csv_matches_reference_rows(scan_mod, port_oracle, tmp_path):
+    """rtl_power_gpu (host/rtl_power_gpu.c): same command line, same CSV bytes as the
+    reference would print for the same synthetic bytes (fixed timestamp, sweep-count interval)."""
+    import os
+    import subprocess
+    from rtlsdr_b200 import _build
+    from rtlsdr_b200.planner import plan_scan
+    _build.build_host()
+    exe = os.path.join(_build.HOST_BUILD, "rtl_power_gpu")
+    out = tmp_path / "scan.csv"
+    env = dict(os.environ, RTLSDR_SYNTH_MODE="biased", RTLSDR_SYNTH_SEED="3", RTLSDR_SYNTH_PARAM="21",
+               RTL_POWER_PASSES="4", RTL_POWER_TIMESTAMP="2026-01-01, 00:00:00")
+    r = subprocess.run([exe, "-f", "88M:108M:25k", "-c", "20%", "-w", "hamming", "-1", str(out)],
+                       env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert "Number of frequency hops: 9" in r.stderr
+    plan = plan_scan("88M:108M:25k", 0.2)
+    pd = plan.as_dict()
+    pd["peak_hold"] = 0
+    w = port_oracle.window_coefs("hamming", 1 << pd["bin_e"])
+    reads, hops = make_reads(port_oracle.lib, pd, 4, SYNTH_BIASED, seed=3, param=21)
+    avg, smp, db = expected(port_oracle, pd, w, reads, hops)
+    want = "".join("2026-01-01, 00:00:00, " + plan.csv_row(h, int(smp[h]), db[h]) for h in range(pd["tune_count"]))
+    assert out.read_text() == want
