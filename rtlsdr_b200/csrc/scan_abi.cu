@@ -69,7 +69,8 @@ struct rtlsdr_gpu_scan {
 	cudaStream_t own_stream = nullptr, stream = nullptr;
 	cudaEvent_t ev_a = nullptr, ev_b = nullptr;
 
-	long long *d_avg = nullptr;
+	long long *d_avg = nullptr;     /* [tune_count * N] bins, then [tune_count] sample counters */
+	long long *d_smp64 = nullptr;   /* = d_avg + tune_count * N */
 	int2 *d_tw = nullptr;
 	uint16_t *d_win = nullptr;
 	double *d_db = nullptr;
@@ -493,6 +494,7 @@ int launch_batch(rtlsdr_gpu_scan *h, const uint8_t *base, const uint8_t *d_desc,
 		p.buf_len = h->cfg.buf_len;
 		p.peak = h->cfg.peak_hold;
 		p.avg = h->d_avg;
+		p.samples = h->d_smp64;
 		TimedScope ts(h);
 		rms_kernel<<<n_reads, 256, 0, h->stream>>>(p);
 		return check_launch(h, "rms_kernel");
@@ -506,6 +508,8 @@ int launch_batch(rtlsdr_gpu_scan *h, const uint8_t *base, const uint8_t *d_desc,
 		p.segs = d_segs;
 		p.n_segs = n_segs;
 		p.avg = h->d_avg;
+		p.samples = h->d_smp64;
+		p.samples_per_read = h->samples_per_read;
 		p.tw = h->d_tw;
 		p.win = h->d_win;
 		p.units_per_read = 1;
@@ -544,6 +548,8 @@ int launch_batch(rtlsdr_gpu_scan *h, const uint8_t *base, const uint8_t *d_desc,
 			p.segs = d_segs + si;
 			p.n_segs = (int)(sj - si);
 			p.avg = h->d_avg;
+			p.samples = h->d_smp64;
+			p.samples_per_read = h->samples_per_read;
 			p.tw = h->d_tw;
 			p.win = h->d_win;
 			p.dc_sums = sc.sums;
@@ -685,22 +691,23 @@ void free_all(rtlsdr_gpu_scan *h)
 	delete h;
 }
 
-int run_epilogue(rtlsdr_gpu_scan *h, int hop0, int nhops)
+/* dB rows (+ optional raw-bin / sample-count copies) of hops [hop0, hop0+nhops):
+ * one kernel, outputs indexed from hop0 */
+int run_epilogue(rtlsdr_gpu_scan *h, int hop0, int nhops, double *db, long long *avg_out, int *samples_out)
 {
-	/* samples for the dB division */
-	memcpy(h->h_samples_pinned, h->samples.data(), (size_t)h->cfg.tune_count * sizeof(int));
-	CU(cudaMemcpyAsync(h->d_samples, h->h_samples_pinned, (size_t)h->cfg.tune_count * sizeof(int),
-			   cudaMemcpyHostToDevice, h->stream));
 	EpilogueParams p;
 	p.avg = h->d_avg;
-	p.samples = h->d_samples;
-	p.db = h->d_db;
+	p.samples = h->d_smp64;
+	p.db = db;
+	p.avg_out = avg_out;
+	p.samples_out = samples_out;
 	p.bin_e = h->cfg.bin_e;
 	p.i1 = h->db_i1;
 	p.i2 = h->db_i2;
 	p.rate = h->cfg.rate;
 	p.hop0 = hop0;
-	dim3 grid((h->db_count + 255) / 256, nhops);
+	const int span = std::max(h->db_count, avg_out ? h->N : 0);
+	dim3 grid((span + 255) / 256, nhops);
 	epilogue_kernel<<<grid, 256, 0, h->stream>>>(p);
 	return check_launch(h, "epilogue_kernel");
 }
@@ -869,7 +876,7 @@ int rtlsdr_gpu_scan_init(const rtlsdr_gpu_scan_cfg_t *cfg, rtlsdr_gpu_scan_t **o
 		if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess)
 			break;
 		h->stream = h->own_stream;
-		const size_t avg_bytes = (size_t)cfg->tune_count * N * sizeof(long long);
+		const size_t avg_bytes = ((size_t)cfg->tune_count * N + (size_t)cfg->tune_count) * sizeof(long long);
 		if (cudaMalloc(&h->d_avg, avg_bytes) != cudaSuccess ||
 		    cudaMalloc(&h->d_db, (size_t)cfg->tune_count * h->db_count * sizeof(double)) != cudaSuccess ||
 		    cudaMalloc(&h->d_samples, (size_t)cfg->tune_count * sizeof(int)) != cudaSuccess ||
@@ -877,6 +884,7 @@ int rtlsdr_gpu_scan_init(const rtlsdr_gpu_scan_cfg_t *cfg, rtlsdr_gpu_scan_t **o
 			rc = RTLSDR_GPU_ERR_NOMEM;
 			break;
 		}
+		h->d_smp64 = h->d_avg + (size_t)cfg->tune_count * N;
 		if (cudaMemsetAsync(h->d_avg, 0, avg_bytes, h->stream) != cudaSuccess)
 			break;
 
@@ -1122,10 +1130,9 @@ static int collect_range(rtlsdr_gpu_scan_t *h, int hop0, int nhops, int64_t *avg
 		return rc;
 	const size_t N = (size_t)h->N;
 	if (db) {
-		if ((rc = run_epilogue(h, hop0, nhops)))
+		if ((rc = run_epilogue(h, hop0, nhops, h->d_db, nullptr, nullptr)))
 			return rc;
-		CU(cudaMemcpyAsync(db, h->d_db + (size_t)hop0 * h->db_count, (size_t)nhops * h->db_count * sizeof(double),
-				   cudaMemcpyDeviceToHost, h->stream));
+		CU(cudaMemcpyAsync(db, h->d_db, (size_t)nhops * h->db_count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
 		h->d2h += (uint64_t)nhops * h->db_count * sizeof(double);
 	}
 	if (avg) {
@@ -1133,7 +1140,13 @@ static int collect_range(rtlsdr_gpu_scan_t *h, int hop0, int nhops, int64_t *avg
 				   cudaMemcpyDeviceToHost, h->stream));
 		h->d2h += (uint64_t)nhops * N * sizeof(long long);
 	}
-	CU(cudaMemsetAsync(h->d_avg + (size_t)hop0 * N, 0, (size_t)nhops * N * sizeof(long long), h->stream));
+	/* read-and-zero, like csv_dbm (rtl_power.c:761-764) */
+	if (nhops == h->cfg.tune_count) {
+		CU(cudaMemsetAsync(h->d_avg, 0, ((size_t)nhops * N + (size_t)nhops) * sizeof(long long), h->stream));
+	} else {
+		CU(cudaMemsetAsync(h->d_avg + (size_t)hop0 * N, 0, (size_t)nhops * N * sizeof(long long), h->stream));
+		CU(cudaMemsetAsync(h->d_smp64 + hop0, 0, (size_t)nhops * sizeof(long long), h->stream));
+	}
 	CU(cudaStreamSynchronize(h->stream));
 	for (int i = 0; i < nhops; i++) {
 		if (samples)
@@ -1168,15 +1181,11 @@ int rtlsdr_gpu_scan_collect_device(rtlsdr_gpu_scan_t *h, void *dev_avg, void *de
 	if (rc)
 		return rc;
 	const size_t N = (size_t)h->N, tc = (size_t)h->cfg.tune_count;
-	if ((rc = run_epilogue(h, 0, (int)tc)))
+	/* one kernel writes dB rows, raw bins and sample counts straight into the
+	 * caller's buffers (e.g. the NCCL send buffer), one memset clears the state */
+	if ((rc = run_epilogue(h, 0, (int)tc, (double *)dev_db, (long long *)dev_avg, (int *)dev_samples)))
 		return rc;
-	if (dev_db)
-		CU(cudaMemcpyAsync(dev_db, h->d_db, tc * h->db_count * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-	if (dev_samples)
-		CU(cudaMemcpyAsync(dev_samples, h->d_samples, tc * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
-	if (dev_avg)
-		CU(cudaMemcpyAsync(dev_avg, h->d_avg, tc * N * sizeof(long long), cudaMemcpyDeviceToDevice, h->stream));
-	CU(cudaMemsetAsync(h->d_avg, 0, tc * N * sizeof(long long), h->stream));
+	CU(cudaMemsetAsync(h->d_avg, 0, (tc * N + tc) * sizeof(long long), h->stream));
 	std::fill(h->samples.begin(), h->samples.end(), 0);
 	return 0;
 }

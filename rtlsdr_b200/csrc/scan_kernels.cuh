@@ -187,10 +187,18 @@ SCAN_DEV void run_pass(X2 (&x)[kPts], int t, const TW &tw)
 	}
 }
 
-template <int KA, int KB>
+/*
+ * Transpose through shared memory between two passes.  LEAD = true puts a
+ * barrier in front (the buffer may still be read by slower threads).  The
+ * streaming kernel instead alternates between two buffers on every exchange:
+ * a buffer is rewritten only two exchanges later and the barrier of the
+ * exchange in between already orders those accesses, so one barrier suffices.
+ */
+template <int KA, int KB, bool LEAD>
 SCAN_DEV void exchange(X2 (&x)[kPts], c16 *xch, int t)
 {
-	__syncthreads(); /* every reader of the previous transpose is done */
+	if (LEAD)
+		__syncthreads();
 #pragma unroll
 	for (int r = 0; r < kPts; ++r)
 		xch[xch_idx(pos<KA>(t, r))] = x_pack(x[r]);
@@ -207,11 +215,29 @@ SCAN_DEV void engine_fft(X2 (&x)[kPts], c16 *xch, int t, const TW &tw)
 {
 	run_pass<0, LE>(x, t, tw);
 	if constexpr (LE > 4) {
-		exchange<0, 1>(x, xch, t);
+		exchange<0, 1, true>(x, xch, t);
 		run_pass<1, LE>(x, t, tw);
 	}
 	if constexpr (LE > 8) {
-		exchange<1, 2>(x, xch, t);
+		exchange<1, 2, true>(x, xch, t);
+		run_pass<2, LE>(x, t, tw);
+	}
+}
+
+/* Same, with two transpose buffers of kXchWords each; `flip` is the running
+ * exchange parity (uniform across the CTA, carried across working sets). */
+template <int LE, class TW>
+SCAN_DEV void engine_fft_db(X2 (&x)[kPts], c16 *xch2, int &flip, int t, const TW &tw)
+{
+	run_pass<0, LE>(x, t, tw);
+	if constexpr (LE > 4) {
+		exchange<0, 1, false>(x, xch2 + flip * kXchWords, t);
+		flip ^= 1;
+		run_pass<1, LE>(x, t, tw);
+	}
+	if constexpr (LE > 8) {
+		exchange<1, 2, false>(x, xch2 + flip * kXchWords, t);
+		flip ^= 1;
 		run_pass<2, LE>(x, t, tw);
 	}
 }
@@ -238,6 +264,8 @@ struct SmallParams {
 	const int4 *segs;           /* (hop, first entry, entry count, -) */
 	int n_segs;
 	long long *avg;             /* [tune_count << L] */
+	long long *samples;         /* [tune_count] tunes[i].samples (rtl_power.c:717) */
+	int samples_per_read;
 	const int2 *tw;             /* [N/2] halved twiddles (wr, wi) */
 	const uint16_t *win;        /* [N] low 16 bits of window_coefs */
 	/* IN16 only */
@@ -253,7 +281,7 @@ struct SmallSmem {
 	static constexpr int N = 1 << L;
 	static constexpr int off_stage = 0;
 	static constexpr int off_xch = 2 * kStageBytes;
-	static constexpr int off_tw = off_xch + kXchWords * 4;
+	static constexpr int off_tw = off_xch + 2 * kXchWords * 4; /* two transpose buffers */
 	static constexpr int tw_entries = N > 16 ? N - 16 : 1; /* stages 4..L-1, group m of stage s at (1<<s)-16+m */
 	static constexpr int off_win = off_tw + tw_entries * 8;
 	static constexpr int off_red = (off_win + N * 2 + 15) & ~15;
@@ -299,7 +327,7 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 	c16 *xch = (c16 *)(smem + SM::off_xch);
 	int2 *tws = (int2 *)(smem + SM::off_tw);
 	uint16_t *wins = (uint16_t *)(smem + SM::off_win);
-	long long *red = (long long *)(smem + SM::off_red); /* [8 warps][2] then K_I, K_Q */
+	int *red = (int *)(smem + SM::off_red); /* [8 warps][2] */
 	int *dck = (int *)(smem + SM::off_dck);
 
 	const int t = threadIdx.x;
@@ -324,6 +352,7 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 	}
 
 	constexpr int kWsPerUnit = IN16 ? 1 : 2; /* a 16 KiB slot = 8192 u8 pairs or 4096 c16 */
+	int flip = 0;
 
 	for (int seg = blockIdx.x; seg < prm.n_segs; seg += gridDim.x) {
 		const int4 sg = prm.segs[seg];
@@ -362,7 +391,7 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 			const uint8_t *st = stage + (u & 1) * kStageBytes;
 
 			/* ---- DC term of the whole read (rtl_power.c:692-693) ---- */
-			int limI = kWS, limQ = kWS, nvalid = kWS / N;
+			int limI = kWS, limQ = kWS, nvalid = kWS / N, kI, kQ;
 			if constexpr (!IN16) {
 				unsigned sI = 0, sQ = 0;
 #pragma unroll
@@ -383,19 +412,19 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 					sQ += __shfl_xor_sync(0xffffffffu, sQ, o);
 				}
 				if ((t & 31) == 0) {
-					red[(t >> 5) * 2 + 0] = (long long)sI;
-					red[(t >> 5) * 2 + 1] = (long long)sQ;
+					red[(t >> 5) * 2 + 0] = (int)sI;
+					red[(t >> 5) * 2 + 1] = (int)sQ;
 				}
 				__syncthreads();
-				if (t < 2) {
-					long long s = 0;
+				int tI = 0, tQ = 0;
 #pragma unroll
-					for (int w = 0; w < kThreads / 32; ++w)
-						s += red[w * 2 + t];
-					s -= 127ll * (kStageBytes / 2); /* sum of (b - 127) */
-					dck[t] = 127 + dc_average(s, kStageBytes - t);
+				for (int w = 0; w < kThreads / 32; ++w) {
+					tI += red[w * 2];
+					tQ += red[w * 2 + 1];
 				}
-				__syncthreads();
+				/* sum of (b - 127); int16 average, truncating division (rtl_power.c:589) */
+				kI = 127 + (int)(int16_t)((tI - 127 * (kStageBytes / 2)) / kStageBytes);
+				kQ = 127 + (int)(int16_t)((tQ - 127 * (kStageBytes / 2)) / (kStageBytes - 1));
 			} else {
 				const int e = first + u / prm.units_per_read;
 				const int w = u % prm.units_per_read;
@@ -405,8 +434,9 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 				limQ = (prm.l_len >> 1) - w * kWS;
 				nvalid = prm.n_blocks - w * (kWS / N);
 				__syncthreads();
+				kI = dck[0];
+				kQ = dck[1];
 			}
-			const int kI = dck[0], kQ = dck[1];
 
 #pragma unroll 1
 			for (int ws = 0; ws < kWsPerUnit; ++ws) {
@@ -443,7 +473,7 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 					x[r].im = im << 16;
 				}
 
-				engine_fft<L>(x, xch, t, tw);
+				engine_fft_db<L>(x, xch, flip, t, tw);
 
 				/* ---- |X|^2 (rtl_power.c:636-640, 708-716) ---- */
 #pragma unroll
@@ -462,6 +492,9 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 				}
 			}
 		}
+
+		if (t == 0)
+			atomicAdd((unsigned long long *)(prm.samples + hop), (unsigned long long)((long long)sg.z * prm.samples_per_read));
 
 		/* ---- flush this segment's sums ---- */
 		long long *out = prm.avg + ((long long)hop << L);
@@ -703,6 +736,7 @@ struct RmsParams {
 	int buf_len;
 	int peak;
 	long long *avg;      /* [tune_count] */
+	long long *samples;  /* [tune_count], += 1 per read (rtl_power.c:435) */
 };
 
 __global__ void __launch_bounds__(256)
@@ -746,6 +780,7 @@ rms_kernel(const SCAN_GRID_CONSTANT RmsParams prm)
 		const double dc = __ddiv_rn((double)t, n);
 		const double err = __dsub_rn(__dmul_rn((double)(t * 2), dc), __dmul_rn(__dmul_rn(dc, dc), n));
 		p -= (long long)round(err);
+		atomicAdd((unsigned long long *)(prm.samples + prm.hop_of[e]), 1ull);
 		long long *dst = prm.avg + prm.hop_of[e];
 		if (prm.peak)
 			atomicMax(dst, p);
@@ -759,15 +794,18 @@ rms_kernel(const SCAN_GRID_CONSTANT RmsParams prm)
  * ======================================================================== */
 
 struct EpilogueParams {
-	const long long *avg; /* [hops << bin_e] natural order */
-	const int *samples;   /* [hops] */
-	double *db;           /* [hops][db_count] */
+	const long long *avg;     /* [hops << bin_e] natural order */
+	const long long *samples; /* [hops] */
+	double *db;               /* [hops][db_count], indexed from hop0 */
+	long long *avg_out;       /* optional copy of the raw bins, indexed from hop0 */
+	int *samples_out;         /* optional, indexed from hop0 */
 	int bin_e;
-	int i1, i2;           /* first / last printed bin of the swapped spectrum */
+	int i1, i2;               /* first / last printed bin of the swapped spectrum */
 	int rate;
-	int hop0;             /* first hop to process */
+	int hop0;                 /* first hop to process */
 };
 
+/* one launch per report: dB row, raw-bin copy and sample count of every hop */
 __global__ void __launch_bounds__(256)
 epilogue_kernel(const SCAN_GRID_CONSTANT EpilogueParams prm)
 {
@@ -775,9 +813,13 @@ epilogue_kernel(const SCAN_GRID_CONSTANT EpilogueParams prm)
 	const int n = 1 << prm.bin_e;
 	const int count = prm.i2 - prm.i1 + 2;
 	const int k = blockIdx.x * blockDim.x + threadIdx.x;
-	if (k >= count)
-		return;
 	const long long *a = prm.avg + ((long long)hop << prm.bin_e);
+	if (prm.avg_out && k < n)
+		prm.avg_out[((long long)blockIdx.y << prm.bin_e) + k] = a[k];
+	if (prm.samples_out && k == 0)
+		prm.samples_out[blockIdx.y] = (int)prm.samples[hop];
+	if (k >= count || !prm.db)
+		return;
 	const int i = (k < count - 1) ? prm.i1 + k : prm.i2;
 	long long v;
 	if (prm.bin_e > 0) {
@@ -786,13 +828,13 @@ epilogue_kernel(const SCAN_GRID_CONSTANT EpilogueParams prm)
 	} else {
 		v = a[0];
 	}
-	const double rate = (double)prm.rate, smp = (double)prm.samples[hop];
+	const double rate = (double)prm.rate, smp = (double)(int)prm.samples[hop];
 	double d;
 	if (k < count - 1)
 		d = __ddiv_rn(__ddiv_rn((double)v, rate), smp);
 	else
 		d = __ddiv_rn((double)v, __dmul_rn(rate, smp));
-	prm.db[(long long)hop * count + k] = 10 * log10(d);
+	prm.db[(long long)blockIdx.y * count + k] = 10 * log10(d);
 }
 
 } // namespace rscan

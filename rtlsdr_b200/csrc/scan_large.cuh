@@ -35,6 +35,8 @@ struct LargeParams {
 	c16 *scratch;               /* [chunk][N] */
 	const long long *dc_sums;   /* [chunk][2] */
 	long long *avg;
+	long long *samples;         /* [tune_count] */
+	int samples_per_read;
 	const int2 *tw;             /* [N/2] */
 	const uint16_t *win;        /* [N] */
 	int L;
@@ -124,6 +126,8 @@ large_round_a_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
 		}
 		twc[t] = prm.tw[(size_t)(t - off) << (L - 1 - s)];
 	}
+	if (t == 0 && tile == 0)
+		atomicAdd((unsigned long long *)(prm.samples + prm.hop_of[e]), (unsigned long long)prm.samples_per_read);
 	if (t < 2) {
 		long long s = prm.dc_sums[2 * rel + t];
 		if constexpr (!IN16)

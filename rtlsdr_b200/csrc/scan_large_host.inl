@@ -80,6 +80,8 @@ int large_process(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_of
 		p.scratch = data;
 		p.dc_sums = sums;
 		p.avg = h->d_avg;
+		p.samples = h->d_smp64;
+		p.samples_per_read = h->samples_per_read;
 		p.tw = h->d_tw;
 		p.win = h->d_win;
 		p.L = L;

@@ -75,7 +75,10 @@ void emu_small_u8(int L, int peak, const uint8_t *reads, int n_reads, const int 
 	p.read_off = offs.data();
 	p.segs = (const int4 *)segs;
 	p.n_segs = n_segs;
+	std::vector<long long> smp(4096, 0);
 	p.avg = avg;
+	p.samples = smp.data();
+	p.samples_per_read = 1;
 	p.tw = (const int2 *)tw;
 	p.win = win;
 	p.units_per_read = 1;
@@ -167,7 +170,10 @@ void emu_small_decim(int L, int peak, const uint8_t *reads, int n_reads, int buf
 	p.entry_base = 0;
 	p.segs = (const int4 *)segs;
 	p.n_segs = n_segs;
+	std::vector<long long> smp(4096, 0);
 	p.avg = avg;
+	p.samples = smp.data();
+	p.samples_per_read = 1;
 	p.tw = (const int2 *)tw;
 	p.win = win;
 	p.dc_sums = sums.data();
@@ -188,24 +194,40 @@ void emu_rms(const uint8_t *reads, int n_reads, int buf_len, const int *hop_of, 
 	p.read_off = offs.data();
 	p.hop_of = hop_of;
 	p.buf_len = buf_len;
+	std::vector<long long> smp(4096, 0);
 	p.peak = peak;
 	p.avg = avg;
+	p.samples = smp.data();
 	cuda_emu::launch(dim3(n_reads), dim3(256), 0, [&]() { rms_kernel(p); });
 }
 
 void emu_epilogue(const long long *avg, const int *samples, double *db, int bin_e, int i1, int i2, int rate, int hops)
 {
 	EpilogueParams p;
+	std::vector<long long> smp(hops);
+	std::vector<long long> avg_copy((size_t)hops << bin_e, -1);
+	std::vector<int> smp_copy(hops, -1);
+	for (int i = 0; i < hops; i++)
+		smp[i] = samples[i];
 	p.avg = avg;
-	p.samples = samples;
+	p.samples = smp.data();
 	p.db = db;
+	p.avg_out = avg_copy.data();
+	p.samples_out = smp_copy.data();
 	p.bin_e = bin_e;
 	p.i1 = i1;
 	p.i2 = i2;
 	p.rate = rate;
 	p.hop0 = 0;
 	int count = i2 - i1 + 2;
-	cuda_emu::launch(dim3((count + 255) / 256, hops), dim3(256), 0, [&]() { epilogue_kernel(p); });
+	int span = count > (1 << bin_e) ? count : (1 << bin_e);
+	cuda_emu::launch(dim3((span + 255) / 256, hops), dim3(256), 0, [&]() { epilogue_kernel(p); });
+	for (size_t i = 0; i < avg_copy.size(); i++)
+		if (avg_copy[i] != avg[i])
+			db[0] = -12345.0; /* flag a broken raw-bin copy */
+	for (int i = 0; i < hops; i++)
+		if (smp_copy[i] != samples[i])
+			db[0] = -12345.0;
 }
 
 #include "emu_large.inl"

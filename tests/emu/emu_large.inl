@@ -17,7 +17,10 @@ void emu_large(int L, int peak, int in16, const uint8_t *reads, int n_reads, con
 	p.hop_of = hop_of;
 	p.scratch = scratch.data();
 	p.dc_sums = sums.data();
+	std::vector<long long> smp(4096, 0);
 	p.avg = avg;
+	p.samples = smp.data();
+	p.samples_per_read = 1;
 	p.tw = (const int2 *)tw;
 	p.win = win;
 	p.L = L;
