@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._pump, daemon=True)
             self.th.start()
@@ -104,16 +104,21 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------- reference arm
 
-def _ref_worker(args):
-    passes, seed = args
+_REF = {}
+
+
+def _ref_init(seed_base):
+    """pool initializer: one configured reference instance per worker process"""
+    import multiprocessing as mp
     from oracles import RefOracle, PortOracle, SYNTH_XORSHIFT  # noqa
+    ident = mp.current_process()._identity
+    seed = seed_base + (ident[0] if ident else 0)
     try:
         r = RefOracle()
         r.configure(RANGE, CROP, WINDOW)
         r.source(SYNTH_XORSHIFT, seed, 0)
         r.scan(2)
-        t = r.scan_timed(passes)
-        return t, passes * r.plan["tune_count"] * (r.plan["buf_len"] // 2), "reference"
+        _REF.update(kind="reference", ref=r, per_pass=r.plan["tune_count"] * (r.plan["buf_len"] // 2))
     except Exception:
         # compiled reference missing: time the C restatement instead
         import numpy as np
@@ -123,27 +128,41 @@ def _ref_worker(args):
         plan["peak_hold"] = 0
         w = p.window_coefs(WINDOW, 1 << plan["bin_e"])
         rng = np.random.default_rng(seed)
-        reads = rng.integers(0, 256, (plan["tune_count"] * 8, plan["buf_len"]), dtype=np.uint8)
+        reads = rng.integers(0, 256, (plan["tune_count"] * 4, plan["buf_len"]), dtype=np.uint8)
         hops = [i % plan["tune_count"] for i in range(len(reads))]
-        t0 = time.perf_counter()
-        n = 0
-        while n < passes:
-            p.scan(plan, w, reads, hops, plan["tune_count"])
-            n += 8
-        return time.perf_counter() - t0, n * plan["tune_count"] * (plan["buf_len"] // 2), "port"
+        _REF.update(kind="port", port=p, plan=plan, w=w, reads=reads, hops=hops,
+                    per_pass=plan["tune_count"] * (plan["buf_len"] // 2))
 
 
-def cpu_reference_rate(passes, procs):
-    """aggregate Msamples/s of `procs` independent reference processes, each `passes` sweeps."""
-    import multiprocessing as mp
-    ctx = mp.get_context("spawn")
+def _ref_step(passes):
+    """(seconds, samples, kind) for `passes` sweeps of the 9-hop plan in this worker"""
+    if _REF["kind"] == "reference":
+        return _REF["ref"].scan_timed(passes), passes * _REF["per_pass"], "reference"
     t0 = time.perf_counter()
-    with ctx.Pool(procs) as pool:
-        res = pool.map(_ref_worker, [(passes, 17 + i) for i in range(procs)])
-    wall = time.perf_counter() - t0
-    samples = sum(r[1] for r in res)
-    slowest = max(r[0] for r in res)
-    return samples / slowest / 1e6, res[0][2], samples, slowest, wall
+    n = 0
+    while n < passes:
+        _REF["port"].scan(_REF["plan"], _REF["w"], _REF["reads"], _REF["hops"], _REF["plan"]["tune_count"])
+        n += 4
+    return time.perf_counter() - t0, n * _REF["per_pass"], "port"
+
+
+class CpuReference:
+    """`procs` persistent worker processes, each an independent instance of the reference's
+    single-threaded scanner() (the reference has no threads: rtl_power.c:29-36, 844-846)."""
+
+    def __init__(self, procs):
+        import multiprocessing as mp
+        self.procs = procs
+        self.pool = mp.get_context("spawn").Pool(procs, initializer=_ref_init, initargs=(17,))
+        self.pool.map(_ref_step, [1] * procs)  # all workers up and configured
+
+    def step(self, passes):
+        res = self.pool.map(_ref_step, [passes] * self.procs, chunksize=1)
+        return max(r[0] for r in res), sum(r[1] for r in res), res[0][2]
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
 def run_reference(args):
@@ -151,23 +170,29 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    passes = 150  # per process per step: 150 x 9 x 8192 = 11 M samples, ~0.55 s/core
+    ref = CpuReference(cores)
+    # bounded sample per step: the whole run stays within ~2 minutes whatever K is
+    t_probe, s_probe, kind = ref.step(8)
+    per_pass_s = max(t_probe / 8, 1e-5)
+    budget_s = 100.0
+    passes = int(max(2, min(3000, budget_s / (args.steps + args.warmup) / per_pass_s)))
     for _ in range(args.warmup):
-        cpu_reference_rate(20, cores)
-    times, samples, kind = [], 0, "reference"
+        ref.step(passes)
+    total_t, total_s = 0.0, 0
     for _ in range(args.steps):
-        _, kind, smp, slowest, _ = cpu_reference_rate(passes, cores)
-        times.append(slowest)
-        samples += smp
-    value = samples / sum(times) / 1e6
+        t, smp, kind = ref.step(passes)
+        total_t += t
+        total_s += smp
+    ref.close()
+    value = total_s / total_t / 1e6
+    sample = f"{cores} independent processes x {passes} sweeps x 9 hops x 8192 samples per step"
     line = {
         "metric": "input Msamples/s", "value": value, "unit": "Msamples/s", "impl": "reference",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int16/int64 fixed point", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "hops": 9, "bins": 4096, "sample": f"{passes} sweeps x 9 hops per process per step"},
-        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": kind,
-                         "sample": f"{cores} independent processes x {passes} sweeps x 9 hops x 8192 samples per step"},
+        "config": {"workload": WORKLOAD, "hops": 9, "bins": 4096, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -211,18 +236,30 @@ def run_gpu(args):
     gen.manual_seed(1234 + rank)
     dev_in = torch.randint(0, 256, (n_sets, PASSES, tc, b), dtype=torch.uint8, device="cuda", generator=gen)
     out_words = tc * n + tc * db_count + tc
-    send = torch.zeros(out_words, dtype=torch.int64, device="cuda")
-    gather = [torch.zeros_like(send) for _ in range(world)] if (world > 1 and rank == 0) else None
-    p_avg = send.data_ptr()
-    p_db = p_avg + tc * n * 8
-    p_smp = p_db + tc * db_count * 8
+    # two report buffers: interval k's spectra are gathered (comm stream) while interval k+1 is transformed
+    sends = [torch.zeros(out_words, dtype=torch.int64, device="cuda") for _ in range(2)]
+    gathers = [[torch.zeros(out_words, dtype=torch.int64, device="cuda") for _ in range(world)]
+               if (world > 1 and rank == 0) else None for _ in range(2)]
+    comm = torch.cuda.Stream()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    gathered = [torch.cuda.Event() for _ in range(2)]
 
     def step_device(i):
+        k = i & 1
+        send = sends[k]
+        p_avg = send.data_ptr()
+        p_db = p_avg + tc * n * 8
+        p_smp = p_db + tc * db_count * 8
         with torch.cuda.stream(stream):
+            stream.wait_event(gathered[k])          # buffer k's previous gather has finished
             g.submit_device(0, tc, PASSES, dev_in[i % n_sets].data_ptr(), tc * b, b)
             g.collect_device(p_avg, p_smp, p_db)
-            if world > 1:
-                dist.gather(send, gather, dst=0)
+            ready[k].record(stream)
+        if world > 1:
+            with torch.cuda.stream(comm):
+                comm.wait_event(ready[k])
+                dist.gather(send, gathers[k], dst=0)
+                gathered[k].record(comm)
 
     def barrier():
         if world > 1:
@@ -245,6 +282,7 @@ def run_gpu(args):
     for i in range(args.steps):
         step_device(args.warmup + i)
     with torch.cuda.stream(stream):
+        stream.wait_stream(comm)                    # the last gathers are inside the timed region
         e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -260,7 +298,7 @@ def run_gpu(args):
     # ---- end to end through the host-buffer ABI ("e2e") ----
     host = rs.PinnedBuffer(step_bytes)
     host.array[:] = np.frombuffer(dev_in[0].cpu().numpy().tobytes(), dtype=np.uint8)
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = max(3, min(args.steps, 200))
 
     def step_host():
         g.submit_batch(0, tc, PASSES, host.ptr, tc * b, b)
@@ -296,7 +334,8 @@ def run_gpu(args):
                        "hops_per_gpu": tc, "bins": n, "reads_per_step_per_gpu": PASSES * tc,
                        "bytes_per_step_per_gpu": step_bytes,
                        "cache": f"inputs larger than L2: {n_sets} distinct interval sets ({n_sets * step_bytes >> 20} MiB) rotated",
-                       "gather": "one NCCL gather of int64 bins + dB per step" if world > 1 else "none"},
+                       "gather": ("one NCCL gather of int64 bins + dB per step, on a second stream, overlapped with "
+                                  "the next interval's transform") if world > 1 else "none"},
             "per_gpu_value": value / world,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": read_traffic(),
@@ -310,9 +349,11 @@ def run_gpu(args):
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
-            rate, kind, _, _, _ = cpu_reference_rate(1200, 1)
-            line["cpu_baseline"] = {"value": rate, "unit": "Msamples/s", "cores": 1, "kind": kind,
-                                    "sample": "1200 sweeps x 9 hops x 8192 samples (88.5 M samples), 1 thread"}
+            ref = CpuReference(1)
+            t, smp, kind = ref.step(4000)
+            ref.close()
+            line["cpu_baseline"] = {"value": smp / t / 1e6, "unit": "Msamples/s", "cores": 1, "kind": kind,
+                                    "sample": "4000 sweeps x 9 hops x 8192 samples (295 M samples), 1 thread"}
         print(json.dumps(line))
     g.close()
     if world > 1:
@@ -323,8 +364,8 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

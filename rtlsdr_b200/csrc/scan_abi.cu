@@ -92,10 +92,21 @@ struct rtlsdr_gpu_scan {
 
 	DescSlot desc[kDescSlots];
 	int desc_next = 0;
-	/* cached descriptors of the last regular device-resident batch */
-	RegularKey reg_key;
-	void *d_reg_desc = nullptr;
-	size_t reg_desc_cap = 0;
+	/* cached descriptors of recent regular (strided) batches, LRU */
+	struct RegCache {
+		RegularKey key;
+		void *d_desc = nullptr;
+		size_t cap = 0;
+		std::vector<int4> segs;
+		uint64_t stamp = 0;
+	};
+	std::vector<RegCache> reg_cache;
+	uint64_t reg_stamp = 0;
+	/* submit_batch: H2D copies run on their own stream, chunk by chunk, ahead of the kernels */
+	cudaStream_t copy_stream = nullptr;
+	cudaEvent_t bulk_free = nullptr;   /* last kernel that reads d_bulk has finished */
+	bool bulk_used = false;
+	std::vector<cudaEvent_t> chunk_ready;
 
 	/* scratch for decimation and the large-FFT path */
 	uint8_t *d_scratch = nullptr;
@@ -417,10 +428,20 @@ int run_decimators(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_o
 		p.out = sc.img;
 		p.out_stride = h->image_stride;
 		p.out_count = img_count;
+		p.l_len = h->l_len;
+		p.sums = sc.sums;
+		CU(cudaMemsetAsync(sc.sums, 0, (size_t)n * 16, h->stream));
 		dim3 grid((img_count + 255) / 256, n);
-		boxcar_kernel<<<grid, 256, 0, h->stream>>>(p);
-		if ((rc = check_launch(h, "boxcar_kernel")))
-			return rc;
+		const int bytes = 2 * h->cfg.downsample;
+		if (bytes % 16 == 0)
+			boxcar_kernel<16><<<grid, 256, 0, h->stream>>>(p);
+		else if (bytes % 8 == 0)
+			boxcar_kernel<8><<<grid, 256, 0, h->stream>>>(p);
+		else if (bytes % 4 == 0)
+			boxcar_kernel<4><<<grid, 256, 0, h->stream>>>(p);
+		else
+			boxcar_kernel<2><<<grid, 256, 0, h->stream>>>(p);
+		return check_launch(h, "boxcar_kernel"); /* DC sums are fused into the boxcar kernel */
 	} else {
 		const int passes = h->cfg.downsample_passes;
 		const c16 *cur = nullptr;
@@ -491,12 +512,14 @@ int launch_batch(rtlsdr_gpu_scan *h, const uint8_t *base, const uint8_t *d_desc,
 		p.base = base;
 		p.read_off = d_offs;
 		p.hop_of = d_hops;
+		p.n_reads = n_reads;
 		p.buf_len = h->cfg.buf_len;
 		p.peak = h->cfg.peak_hold;
 		p.avg = h->d_avg;
 		p.samples = h->d_smp64;
 		TimedScope ts(h);
-		rms_kernel<<<n_reads, 256, 0, h->stream>>>(p);
+		const int blocks = std::max(1, std::min((n_reads + 7) / 8, h->num_sms * 8));
+		rms_kernel<<<blocks, 256, 0, h->stream>>>(p);
 		return check_launch(h, "rms_kernel");
 	}
 
@@ -659,7 +682,14 @@ void free_all(rtlsdr_gpu_scan *h)
 	cudaFree(h->d_samples);
 	cudaFree(h->d_scratch);
 	cudaFree(h->d_bulk);
-	cudaFree(h->d_reg_desc);
+	for (auto &c : h->reg_cache)
+		cudaFree(c.d_desc);
+	if (h->copy_stream)
+		cudaStreamDestroy(h->copy_stream);
+	if (h->bulk_free)
+		cudaEventDestroy(h->bulk_free);
+	for (auto e : h->chunk_ready)
+		cudaEventDestroy(e);
 	if (h->h_samples_pinned)
 		cudaFreeHost(h->h_samples_pinned);
 	for (int i = 0; i < 2; i++) {
@@ -1008,18 +1038,13 @@ int rtlsdr_gpu_scan_sync(rtlsdr_gpu_scan_t *h)
 	return 0;
 }
 
-int rtlsdr_gpu_scan_submit_device(rtlsdr_gpu_scan_t *h, int hop_first, int hop_count, int passes,
-				  const void *dev_buf, int64_t pass_stride, int64_t hop_stride)
-{
-	if (!h || !dev_buf)
-		return RTLSDR_GPU_ERR_NULL;
-	if (((uintptr_t)dev_buf & 15) || (pass_stride & 15) || (hop_stride & 15))
-		return RTLSDR_GPU_ERR_ALIGN;
-	CU(cudaSetDevice(h->cfg.device));
-	int rc = flush_ring(h); /* keep submission order */
-	if (rc)
-		return rc;
+constexpr size_t kRegCacheEntries = 16;
+constexpr int kBatchChunks = 4;
 
+/* regular (strided) batch already on the device; descriptors are cached per (base, shape) */
+static int submit_regular(rtlsdr_gpu_scan_t *h, int hop_first, int hop_count, int passes, const void *dev_buf,
+			  int64_t pass_stride, int64_t hop_stride)
+{
 	RegularKey key;
 	key.base = dev_buf;
 	key.hop_first = hop_first;
@@ -1028,58 +1053,77 @@ int rtlsdr_gpu_scan_submit_device(rtlsdr_gpu_scan_t *h, int hop_first, int hop_c
 	key.pass_stride = pass_stride;
 	key.hop_stride = hop_stride;
 	key.valid = true;
-	const bool cacheable = h->path != PATH_SMALL_DECIM; /* decim path re-walks host segments */
-	if (cacheable && key == h->reg_key) {
-		rc = launch_batch(h, (const uint8_t *)dev_buf, (const uint8_t *)h->d_reg_desc, h->reg_key.n_reads,
-				  h->reg_key.n_segs, nullptr);
-		if (rc)
+	int rc;
+	rtlsdr_gpu_scan::RegCache *hit = nullptr;
+	for (auto &c : h->reg_cache)
+		if (c.key == key)
+			hit = &c;
+	if (!hit) {
+		std::vector<long long> offs, s_offs;
+		std::vector<int> hops, s_hops;
+		if ((rc = regular_offsets(h, hop_first, hop_count, passes, pass_stride, hop_stride, offs, hops)))
 			return rc;
-		for (int k = 0; k < hop_count; k++)
-			h->samples[hop_first + k] += h->samples_per_read * passes;
-		return 0;
+		if (h->reg_cache.size() < kRegCacheEntries) {
+			h->reg_cache.emplace_back();
+			hit = &h->reg_cache.back();
+		} else {
+			hit = &h->reg_cache[0];
+			for (auto &c : h->reg_cache)
+				if (c.stamp < hit->stamp)
+					hit = &c;
+		}
+		hit->key.valid = false;
+		const int n = (int)offs.size();
+		const int n_segs = build_desc(h, offs, hops, s_offs, s_hops, hit->segs);
+		DescLayout lay(n, n_segs);
+		if (hit->cap < lay.bytes) {
+			CU(cudaStreamSynchronize(h->stream)); /* an in-flight kernel may still read the old table */
+			cudaFree(hit->d_desc);
+			hit->d_desc = nullptr;
+			hit->cap = 0;
+			CU(cudaMalloc(&hit->d_desc, lay.bytes));
+			hit->cap = lay.bytes;
+		}
+		DescSlot *slot;
+		if ((rc = desc_acquire(h, lay.bytes, &slot)))
+			return rc;
+		uint8_t *hp = (uint8_t *)slot->h;
+		memcpy(hp + lay.off_reads, s_offs.data(), (size_t)n * 8);
+		memcpy(hp + lay.off_segs, hit->segs.data(), (size_t)n_segs * 16);
+		memcpy(hp + lay.off_hops, s_hops.data(), (size_t)n * 4);
+		CU(cudaMemcpyAsync(hit->d_desc, slot->h, lay.bytes, cudaMemcpyHostToDevice, h->stream));
+		CU(cudaEventRecord(slot->done, h->stream));
+		slot->used = true;
+		key.n_reads = n;
+		key.n_segs = n_segs;
+		hit->key = key;
 	}
-	std::vector<long long> offs;
-	std::vector<int> hops;
-	rc = regular_offsets(h, hop_first, hop_count, passes, pass_stride, hop_stride, offs, hops);
+	hit->stamp = ++h->reg_stamp;
+	rc = launch_batch(h, (const uint8_t *)dev_buf, (const uint8_t *)hit->d_desc, hit->key.n_reads, hit->key.n_segs,
+			  &hit->segs);
 	if (rc)
 		return rc;
-	if (!cacheable)
-		return process_batch(h, (const uint8_t *)dev_buf, offs, hops);
-
-	std::vector<long long> s_offs;
-	std::vector<int> s_hops;
-	std::vector<int4> segs;
-	const int n = (int)offs.size();
-	const int n_segs = build_desc(h, offs, hops, s_offs, s_hops, segs);
-	DescLayout lay(n, n_segs);
-	if (h->reg_desc_cap < lay.bytes) {
-		CU(cudaStreamSynchronize(h->stream));
-		cudaFree(h->d_reg_desc);
-		h->d_reg_desc = nullptr;
-		h->reg_desc_cap = 0;
-		CU(cudaMalloc(&h->d_reg_desc, lay.bytes));
-		h->reg_desc_cap = lay.bytes;
-	}
-	h->reg_key.valid = false;
-	DescSlot *slot;
-	if ((rc = desc_acquire(h, lay.bytes, &slot)))
-		return rc;
-	uint8_t *hp = (uint8_t *)slot->h;
-	memcpy(hp + lay.off_reads, s_offs.data(), (size_t)n * 8);
-	memcpy(hp + lay.off_segs, segs.data(), (size_t)n_segs * 16);
-	memcpy(hp + lay.off_hops, s_hops.data(), (size_t)n * 4);
-	CU(cudaMemcpyAsync(h->d_reg_desc, slot->h, lay.bytes, cudaMemcpyHostToDevice, h->stream));
-	CU(cudaEventRecord(slot->done, h->stream));
-	slot->used = true;
-	key.n_reads = n;
-	key.n_segs = n_segs;
-	h->reg_key = key;
-	rc = launch_batch(h, (const uint8_t *)dev_buf, (const uint8_t *)h->d_reg_desc, n, n_segs, &segs);
-	if (rc)
-		return rc;
-	for (int i = 0; i < n; i++)
-		h->samples[hops[i]] += h->samples_per_read;
+	for (int k = 0; k < hop_count; k++)
+		h->samples[hop_first + k] += h->samples_per_read * passes;
 	return 0;
+}
+
+int rtlsdr_gpu_scan_submit_device(rtlsdr_gpu_scan_t *h, int hop_first, int hop_count, int passes,
+				  const void *dev_buf, int64_t pass_stride, int64_t hop_stride)
+{
+	if (!h || !dev_buf)
+		return RTLSDR_GPU_ERR_NULL;
+	if (((uintptr_t)dev_buf & 15) || (pass_stride & 15) || (hop_stride & 15))
+		return RTLSDR_GPU_ERR_ALIGN;
+	if (hop_first < 0 || hop_count <= 0 || hop_first + hop_count > h->cfg.tune_count)
+		return RTLSDR_GPU_ERR_HOP;
+	if (passes <= 0)
+		return RTLSDR_GPU_ERR_CONFIG;
+	CU(cudaSetDevice(h->cfg.device));
+	int rc = flush_ring(h); /* keep submission order */
+	if (rc)
+		return rc;
+	return submit_regular(h, hop_first, hop_count, passes, dev_buf, pass_stride, hop_stride);
 }
 
 int rtlsdr_gpu_scan_submit_batch(rtlsdr_gpu_scan_t *h, int hop_first, int hop_count, int passes,
@@ -1094,11 +1138,13 @@ int rtlsdr_gpu_scan_submit_batch(rtlsdr_gpu_scan_t *h, int hop_first, int hop_co
 	if (passes <= 0 || pass_stride < 0 || hop_stride < 0)
 		return RTLSDR_GPU_ERR_CONFIG;
 	CU(cudaSetDevice(h->cfg.device));
-	/* extent of the strided region */
 	const size_t B = (size_t)h->cfg.buf_len;
-	const size_t extent = (size_t)(passes - 1) * (size_t)pass_stride + (size_t)(hop_count - 1) * (size_t)hop_stride + B;
+	const size_t pass_extent = (size_t)(hop_count - 1) * (size_t)hop_stride + B;
+	const size_t extent = (size_t)(passes - 1) * (size_t)pass_stride + pass_extent;
 	if (h->bulk_bytes < extent) {
 		CU(cudaStreamSynchronize(h->stream));
+		if (h->copy_stream)
+			CU(cudaStreamSynchronize(h->copy_stream));
 		cudaFree(h->d_bulk);
 		h->d_bulk = nullptr;
 		h->bulk_bytes = 0;
@@ -1107,14 +1153,43 @@ int rtlsdr_gpu_scan_submit_batch(rtlsdr_gpu_scan_t *h, int hop_first, int hop_co
 			return RTLSDR_GPU_ERR_NOMEM;
 		}
 		h->bulk_bytes = extent;
-		h->reg_key.valid = false;
+		for (auto &c : h->reg_cache)
+			c.key.valid = false;
+	}
+	if (!h->copy_stream) {
+		CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+		CU(cudaEventCreateWithFlags(&h->bulk_free, cudaEventDisableTiming));
+		h->chunk_ready.resize(kBatchChunks, nullptr);
+		for (auto &e : h->chunk_ready)
+			CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 	}
 	int rc = flush_ring(h);
 	if (rc)
 		return rc;
-	CU(cudaMemcpyAsync(h->d_bulk, buf, extent, cudaMemcpyHostToDevice, h->stream));
-	h->h2d += extent;
-	return rtlsdr_gpu_scan_submit_device(h, hop_first, hop_count, passes, h->d_bulk, pass_stride, hop_stride);
+	/* Chunks of whole passes: chunk c+1 crosses PCIe while chunk c is transformed.  Passes must
+	 * not interleave in memory for that (pass_stride covers one pass), else one chunk. */
+	int chunks = (passes >= 2 * kBatchChunks && (size_t)pass_stride >= pass_extent) ? kBatchChunks : 1;
+	if (h->bulk_used)
+		CU(cudaStreamWaitEvent(h->copy_stream, h->bulk_free, 0)); /* previous batch's kernels are done with d_bulk */
+	for (int c = 0; c < chunks; c++) {
+		const int p0 = (int)((long long)passes * c / chunks), p1 = (int)((long long)passes * (c + 1) / chunks);
+		const size_t off = (size_t)p0 * (size_t)pass_stride;
+		const size_t bytes = (size_t)(p1 - p0 - 1) * (size_t)pass_stride + pass_extent;
+		CU(cudaMemcpyAsync(h->d_bulk + off, buf + off, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+		CU(cudaEventRecord(h->chunk_ready[c], h->copy_stream));
+		h->h2d += bytes;
+	}
+	for (int c = 0; c < chunks; c++) {
+		const int p0 = (int)((long long)passes * c / chunks), p1 = (int)((long long)passes * (c + 1) / chunks);
+		CU(cudaStreamWaitEvent(h->stream, h->chunk_ready[c], 0));
+		rc = submit_regular(h, hop_first, hop_count, p1 - p0, h->d_bulk + (size_t)p0 * (size_t)pass_stride,
+				    pass_stride, hop_stride);
+		if (rc)
+			return rc;
+	}
+	CU(cudaEventRecord(h->bulk_free, h->stream));
+	h->bulk_used = true;
+	return 0;
 }
 
 int rtlsdr_gpu_scan_db_count(const rtlsdr_gpu_scan_t *h)

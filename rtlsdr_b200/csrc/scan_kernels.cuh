@@ -547,30 +547,116 @@ struct DecimParams {
 	c16 *out;                  /* entry e at out + e * out_stride */
 	long long out_stride;      /* in c16 units */
 	int out_count;             /* c16 slots to write per entry */
+	int l_len;                 /* buf_len / ds: interleaved int16 count remove_dc covers */
+	long long *sums;           /* [entry][2], zeroed by the host */
 };
 
-/* rtl_power.c:671-681 in closed form: slot k = wrap16(sum of inputs k*ds ..
- * k*ds+ds-1 that exist); slots past ceil(pairs/ds) are zero. */
+/*
+ * rtl_power.c:671-681 in closed form: slot k = wrap16(sum of inputs k*ds ..
+ * k*ds+ds-1 that exist); slots past ceil(pairs/ds) are zero.  One thread per
+ * output slot; VEC = widest load (bytes) that 2*ds bytes per slot stays aligned
+ * to, all loads of a slot issued before they are summed (IDP.4A byte sums).
+ * The DC sums the reference's remove_dc() takes over the decimated buffer
+ * (I over even int16 indices < l_len, Q over odd ones, rtl_power.c:586-588,
+ * 692-693) are reduced per CTA and added to prm.sums.
+ */
+template <int VEC>
+SCAN_DEV void boxcar_accumulate(const uint8_t *p, int nbytes, int &sb_i, int &sb_q)
+{
+	unsigned si = 0, sq = 0;
+	if constexpr (VEC == 16) {
+		for (int o = 0; o < nbytes; o += 64) {
+			uint4 q[4];
+#pragma unroll
+			for (int j = 0; j < 4; ++j)
+				q[j] = (o + 16 * j < nbytes) ? __ldg((const uint4 *)(p + o + 16 * j)) : uint4{ 0, 0, 0, 0 };
+#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				si = __dp4a(q[j].x, 0x00010001u, si); sq = __dp4a(q[j].x, 0x01000100u, sq);
+				si = __dp4a(q[j].y, 0x00010001u, si); sq = __dp4a(q[j].y, 0x01000100u, sq);
+				si = __dp4a(q[j].z, 0x00010001u, si); sq = __dp4a(q[j].z, 0x01000100u, sq);
+				si = __dp4a(q[j].w, 0x00010001u, si); sq = __dp4a(q[j].w, 0x01000100u, sq);
+			}
+		}
+	} else if constexpr (VEC == 8) {
+		for (int o = 0; o < nbytes; o += 64) {
+			uint2 q[8];
+#pragma unroll
+			for (int j = 0; j < 8; ++j)
+				q[j] = (o + 8 * j < nbytes) ? __ldg((const uint2 *)(p + o + 8 * j)) : uint2{ 0, 0 };
+#pragma unroll
+			for (int j = 0; j < 8; ++j) {
+				si = __dp4a(q[j].x, 0x00010001u, si); sq = __dp4a(q[j].x, 0x01000100u, sq);
+				si = __dp4a(q[j].y, 0x00010001u, si); sq = __dp4a(q[j].y, 0x01000100u, sq);
+			}
+		}
+	} else if constexpr (VEC == 4) {
+		for (int o = 0; o < nbytes; o += 32) {
+			unsigned q[8];
+#pragma unroll
+			for (int j = 0; j < 8; ++j)
+				q[j] = (o + 4 * j < nbytes) ? __ldg((const unsigned *)(p + o + 4 * j)) : 0u;
+#pragma unroll
+			for (int j = 0; j < 8; ++j) {
+				si = __dp4a(q[j], 0x00010001u, si);
+				sq = __dp4a(q[j], 0x01000100u, sq);
+			}
+		}
+	} else {
+		for (int o = 0; o < nbytes; o += 2) {
+			const unsigned raw = __ldg((const uint16_t *)(p + o));
+			si += raw & 0xFFu;
+			sq += raw >> 8;
+		}
+	}
+	sb_i = (int)si;
+	sb_q = (int)sq;
+}
+
+template <int VEC>
 __global__ void __launch_bounds__(256)
 boxcar_kernel(const SCAN_GRID_CONSTANT DecimParams prm)
 {
+	__shared__ long long red[2 * 8];
 	const int e = blockIdx.y;
 	const int k = blockIdx.x * blockDim.x + threadIdx.x;
-	if (k >= prm.out_count)
-		return;
-	const uint16_t *src = (const uint16_t *)(prm.base + prm.read_off[e]);
+	const uint8_t *src = prm.base + prm.read_off[e];
 	const int outs = (prm.pairs + prm.ds - 1) / prm.ds;
 	int si = 0, sq = 0;
 	if (k < outs) {
 		const int lo = k * prm.ds;
-		const int hi = (lo + prm.ds < prm.pairs) ? lo + prm.ds : prm.pairs;
-		for (int i = lo; i < hi; ++i) {
-			const unsigned raw = __ldg(src + i);
-			si += (int)(raw & 0xFFu) - 127;
-			sq += (int)(raw >> 8) - 127;
-		}
+		const int cnt = (lo + prm.ds <= prm.pairs) ? prm.ds : prm.pairs - lo;
+		int bi, bq;
+		if (cnt == prm.ds)
+			boxcar_accumulate<VEC>(src + 2ll * lo, 2 * cnt, bi, bq);
+		else
+			boxcar_accumulate<2>(src + 2ll * lo, 2 * cnt, bi, bq); /* partial tail group */
+		si = bi - 127 * cnt; /* sum of (b - 127), rtl_power.c:666-668 */
+		sq = bq - 127 * cnt;
 	}
-	prm.out[e * prm.out_stride + k] = c16_pack(si, sq);
+	const c16 v = c16_pack(si, sq);
+	if (k < prm.out_count)
+		prm.out[e * prm.out_stride + k] = v;
+	/* remove_dc sees the wrapped int16 values at indices < l_len */
+	long long dI = (2 * k < prm.l_len) ? (long long)c16_re(v) : 0;
+	long long dQ = (2 * k + 1 < prm.l_len) ? (long long)c16_im(v) : 0;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		dI += __shfl_xor_sync(0xffffffffu, dI, o);
+		dQ += __shfl_xor_sync(0xffffffffu, dQ, o);
+	}
+	if ((threadIdx.x & 31) == 0) {
+		red[(threadIdx.x >> 5) * 2] = dI;
+		red[(threadIdx.x >> 5) * 2 + 1] = dQ;
+	}
+	__syncthreads();
+	if (threadIdx.x < 2) {
+		long long t = 0;
+		for (int w = 0; w < (int)(blockDim.x >> 5); ++w)
+			t += red[2 * w + threadIdx.x];
+		if (t != 0)
+			atomicAdd((unsigned long long *)(prm.sums + 2 * e + threadIdx.x), (unsigned long long)t);
+	}
 }
 
 struct HalfbandParams {
@@ -733,59 +819,59 @@ struct RmsParams {
 	const uint8_t *base;
 	const long long *read_off;
 	const int *hop_of;   /* hop of entry e */
+	int n_reads;
 	int buf_len;
 	int peak;
 	long long *avg;      /* [tune_count] */
 	long long *samples;  /* [tune_count], += 1 per read (rtl_power.c:435) */
 };
 
+/* One warp per read: 512-byte coalesced rows, 8 x LDG.128 in flight per lane,
+ * sum(b) and sum(b*b) with IDP.4A, everything else exact int64 per read. */
 __global__ void __launch_bounds__(256)
 rms_kernel(const SCAN_GRID_CONSTANT RmsParams prm)
 {
-	__shared__ long long sh[2 * 8];
-	const int e = blockIdx.x;
-	const uint8_t *src = prm.base + prm.read_off[e];
-	long long tsum = 0, psum = 0;
-	for (int i = threadIdx.x * 16; i < prm.buf_len; i += blockDim.x * 16) {
-		const uint4 q = __ldg((const uint4 *)(src + i));
-		const unsigned w[4] = { q.x, q.y, q.z, q.w };
+	const int lane = threadIdx.x & 31;
+	const int warps = (gridDim.x * blockDim.x) >> 5;
+	for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < prm.n_reads; e += warps) {
+		const uint8_t *src = prm.base + prm.read_off[e];
+		unsigned sb = 0, sbb = 0; /* per lane <= 2^21/32 bytes: fits */
+		for (int i = lane * 16; i < prm.buf_len; i += 32 * 16 * 8) {
+			uint4 q[8];
 #pragma unroll
-		for (int j = 0; j < 4; ++j) {
+			for (int j = 0; j < 8; ++j)
+				q[j] = (i + j * 512 < prm.buf_len) ? __ldg((const uint4 *)(src + i + j * 512)) : uint4{ 0, 0, 0, 0 };
 #pragma unroll
-			for (int b = 0; b < 4; ++b) {
-				const int s = (int)((w[j] >> (8 * b)) & 0xFFu) - 127;
-				tsum += s;
-				psum += s * s;
+			for (int j = 0; j < 8; ++j) {
+				sb = __dp4a(q[j].x, 0x01010101u, sb); sbb = __dp4a(q[j].x, q[j].x, sbb);
+				sb = __dp4a(q[j].y, 0x01010101u, sb); sbb = __dp4a(q[j].y, q[j].y, sbb);
+				sb = __dp4a(q[j].z, 0x01010101u, sb); sbb = __dp4a(q[j].z, q[j].z, sbb);
+				sb = __dp4a(q[j].w, 0x01010101u, sb); sbb = __dp4a(q[j].w, q[j].w, sbb);
 			}
 		}
-	}
+		long long tb = sb, tbb = sbb;
 #pragma unroll
-	for (int o = 16; o > 0; o >>= 1) {
-		tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
-		psum += __shfl_xor_sync(0xffffffffu, psum, o);
-	}
-	if ((threadIdx.x & 31) == 0) {
-		sh[(threadIdx.x >> 5) * 2] = tsum;
-		sh[(threadIdx.x >> 5) * 2 + 1] = psum;
-	}
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		long long t = 0, p = 0;
-		for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
-			t += sh[2 * w];
-			p += sh[2 * w + 1];
+		for (int o = 16; o > 0; o >>= 1) {
+			tb += __shfl_xor_sync(0xffffffffu, tb, o);
+			tbb += __shfl_xor_sync(0xffffffffu, tbb, o);
 		}
-		/* same IEEE double operations, in the reference's order, no FMA contraction */
-		const double n = (double)prm.buf_len;
-		const double dc = __ddiv_rn((double)t, n);
-		const double err = __dsub_rn(__dmul_rn((double)(t * 2), dc), __dmul_rn(__dmul_rn(dc, dc), n));
-		p -= (long long)round(err);
-		atomicAdd((unsigned long long *)(prm.samples + prm.hop_of[e]), 1ull);
-		long long *dst = prm.avg + prm.hop_of[e];
-		if (prm.peak)
-			atomicMax(dst, p);
-		else
-			atomicAdd((unsigned long long *)dst, (unsigned long long)p);
+		if (lane == 0) {
+			/* s = b - 127:  sum s = sum b - 127 n,  sum s^2 = sum b^2 - 254 sum b + 127^2 n */
+			const long long n = prm.buf_len;
+			const long long t = tb - 127 * n;
+			long long p = tbb - 254 * tb + 16129 * n;
+			/* same IEEE double operations, in the reference's order, no FMA contraction */
+			const double dn = (double)prm.buf_len;
+			const double dc = __ddiv_rn((double)t, dn);
+			const double err = __dsub_rn(__dmul_rn((double)(t * 2), dc), __dmul_rn(__dmul_rn(dc, dc), dn));
+			p -= (long long)round(err);
+			atomicAdd((unsigned long long *)(prm.samples + prm.hop_of[e]), 1ull);
+			long long *dst = prm.avg + prm.hop_of[e];
+			if (prm.peak)
+				atomicMax(dst, p);
+			else
+				atomicAdd((unsigned long long *)dst, (unsigned long long)p);
+		}
 	}
 }
 

@@ -25,6 +25,7 @@ struct dim3 {
 struct int2 { int x, y; };
 struct int4 { int x, y, z, w; };
 struct uint4 { unsigned x, y, z, w; };
+struct uint2 { unsigned x, y; };
 static inline int2 make_int2(int x, int y) { return int2{ x, y }; }
 static inline int4 make_int4(int x, int y, int z, int w) { return int4{ x, y, z, w }; }
 

@@ -115,7 +115,18 @@ void emu_small_decim(int L, int peak, const uint8_t *reads, int n_reads, int buf
 		d.out = img.data();
 		d.out_stride = stride;
 		d.out_count = (int)stride;
-		cuda_emu::launch(dim3((unsigned)((stride + 255) / 256), n_reads), dim3(256), 0, [&]() { boxcar_kernel(d); });
+		d.l_len = l_len;
+		d.sums = sums.data();
+		dim3 grid((unsigned)((stride + 255) / 256), n_reads);
+		const int bytes = 2 * ds;
+		if (bytes % 16 == 0)
+			cuda_emu::launch(grid, dim3(256), 0, [&]() { boxcar_kernel<16>(d); });
+		else if (bytes % 8 == 0)
+			cuda_emu::launch(grid, dim3(256), 0, [&]() { boxcar_kernel<8>(d); });
+		else if (bytes % 4 == 0)
+			cuda_emu::launch(grid, dim3(256), 0, [&]() { boxcar_kernel<4>(d); });
+		else
+			cuda_emu::launch(grid, dim3(256), 0, [&]() { boxcar_kernel<2>(d); });
 	} else {
 		std::vector<c16> a((size_t)n_reads * (pairs / 2)), b((size_t)n_reads * (pairs / 4 + 4));
 		const c16 *cur = nullptr;
@@ -151,12 +162,14 @@ void emu_small_decim(int L, int peak, const uint8_t *reads, int n_reads, int buf
 		f.f4 = fir5 ? fir5[3] : 0; f.f5 = fir5 ? fir5[4] : 0;
 		cuda_emu::launch(dim3((count + 255) / 256, n_reads), dim3(256), 0, [&]() { fir9_kernel(f); });
 	}
-	DcSumParams dc;
-	dc.img = img.data();
-	dc.stride = stride;
-	dc.l_len = l_len;
-	dc.sums = sums.data();
-	cuda_emu::launch(dim3(3, n_reads), dim3(256), 0, [&]() { dc_sums_c16_kernel(dc); });
+	if (mode != 0) {
+		DcSumParams dc;
+		dc.img = img.data();
+		dc.stride = stride;
+		dc.l_len = l_len;
+		dc.sums = sums.data();
+		cuda_emu::launch(dim3(3, n_reads), dim3(256), 0, [&]() { dc_sums_c16_kernel(dc); });
+	}
 	if (image_out)
 		memcpy(image_out, img.data(), img.size() * 4);
 	if (sums_out)
@@ -193,12 +206,13 @@ void emu_rms(const uint8_t *reads, int n_reads, int buf_len, const int *hop_of, 
 	p.base = reads;
 	p.read_off = offs.data();
 	p.hop_of = hop_of;
+	p.n_reads = n_reads;
 	p.buf_len = buf_len;
 	std::vector<long long> smp(4096, 0);
 	p.peak = peak;
 	p.avg = avg;
 	p.samples = smp.data();
-	cuda_emu::launch(dim3(n_reads), dim3(256), 0, [&]() { rms_kernel(p); });
+	cuda_emu::launch(dim3((n_reads + 7) / 8 > 2 ? 2 : 1), dim3(256), 0, [&]() { rms_kernel(p); });
 }
 
 void emu_epilogue(const long long *avg, const int *samples, double *db, int bin_e, int i1, int i2, int rate, int hops)
