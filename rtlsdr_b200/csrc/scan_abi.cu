@@ -61,7 +61,7 @@ struct rtlsdr_gpu_scan {
 	rtlsdr_gpu_scan_cfg_t cfg;
 	int N = 1;
 	Path path = PATH_SMALL_U8;
-	int l_len = 0, n_blocks = 0, units_per_read = 1, samples_per_read = 0;
+	int l_len = 0, n_blocks = 0, blocks_padded = 0, samples_per_read = 0;
 	long long image_stride = 0; /* c16 per decimated image */
 	int db_i1 = 0, db_i2 = 0, db_count = 2;
 	int num_sms = 148, ctas_per_sm = 2;
@@ -394,22 +394,37 @@ int launch_small(rtlsdr_gpu_scan *h, const SmallParams &prm, bool in16)
 struct DecimScratch {
 	c16 *img, *a, *b;
 	long long *sums;
+	int *ave;
+	static bool halfband(const rtlsdr_gpu_scan *h)
+	{
+		return !(h->cfg.boxcar && h->cfg.downsample > 1) && h->cfg.downsample_passes > 0;
+	}
+	/* bytes per entry (the 16 KiB of slack after the images is added by the caller) */
 	static size_t per_entry(const rtlsdr_gpu_scan *h)
 	{
 		size_t pairs = (size_t)h->cfg.buf_len / 2;
-		return (size_t)h->image_stride * 4 + (pairs / 2) * 4 + (pairs / 4 + 4) * 4 + 32;
+		size_t b = (size_t)h->image_stride * 4 + 16 + 8;
+		if (halfband(h))
+			b += (pairs / 2) * 4 + (pairs / 4 + 4) * 4;
+		return b;
 	}
+	static size_t slack() { return kStageBytes + 1024; }
 	DecimScratch(const rtlsdr_gpu_scan *h, int n, uint8_t *p)
 	{
 		size_t pairs = (size_t)h->cfg.buf_len / 2;
 		img = (c16 *)p;
-		p += (size_t)n * h->image_stride * 4;
-		a = (c16 *)p;
-		p += (size_t)n * (pairs / 2) * 4;
-		b = (c16 *)p;
-		p += (size_t)n * (pairs / 4 + 4) * 4;
+		p += (size_t)n * h->image_stride * 4 + kStageBytes; /* a unit may read past the last image */
+		a = b = nullptr;
+		if (halfband(h)) {
+			a = (c16 *)p;
+			p += (size_t)n * (pairs / 2) * 4;
+			b = (c16 *)p;
+			p += (size_t)n * (pairs / 4 + 4) * 4;
+		}
 		p = (uint8_t *)(((uintptr_t)p + 15) & ~(uintptr_t)15);
 		sums = (long long *)p;
+		p += (size_t)n * 16;
+		ave = (int *)p;
 	}
 };
 
@@ -433,7 +448,9 @@ int run_decimators(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_o
 		CU(cudaMemsetAsync(sc.sums, 0, (size_t)n * 16, h->stream));
 		dim3 grid((img_count + 255) / 256, n);
 		const int bytes = 2 * h->cfg.downsample;
-		if (bytes % 16 == 0)
+		if (h->cfg.downsample <= kBoxcarStageMaxDs)
+			boxcar_staged_kernel<<<grid, 256, 512 * h->cfg.downsample, h->stream>>>(p);
+		else if (bytes % 16 == 0)
 			boxcar_kernel<16><<<grid, 256, 0, h->stream>>>(p);
 		else if (bytes % 8 == 0)
 			boxcar_kernel<8><<<grid, 256, 0, h->stream>>>(p);
@@ -441,7 +458,8 @@ int run_decimators(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_o
 			boxcar_kernel<4><<<grid, 256, 0, h->stream>>>(p);
 		else
 			boxcar_kernel<2><<<grid, 256, 0, h->stream>>>(p);
-		return check_launch(h, "boxcar_kernel"); /* DC sums are fused into the boxcar kernel */
+		if ((rc = check_launch(h, "boxcar_kernel"))) /* DC sums are fused into the boxcar kernel */
+			return rc;
 	} else {
 		const int passes = h->cfg.downsample_passes;
 		const c16 *cur = nullptr;
@@ -481,17 +499,25 @@ int run_decimators(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_o
 		fir9_kernel<<<grid, 256, 0, h->stream>>>(f);
 		if ((rc = check_launch(h, "fir9_kernel")))
 			return rc;
+		CU(cudaMemsetAsync(sc.sums, 0, (size_t)n * 16, h->stream));
+		DcSumParams d;
+		d.img = sc.img;
+		d.stride = h->image_stride;
+		d.l_len = h->l_len;
+		d.sums = sc.sums;
+		int nI = (h->l_len + 1) / 2;
+		dim3 grid_dc(std::max(1, std::min((nI + 1023) / 1024, 64)), n);
+		dc_sums_c16_kernel<<<grid_dc, 256, 0, h->stream>>>(d);
+		if ((rc = check_launch(h, "dc_sums_c16_kernel")))
+			return rc;
 	}
-	CU(cudaMemsetAsync(sc.sums, 0, (size_t)n * 16, h->stream));
-	DcSumParams d;
-	d.img = sc.img;
-	d.stride = h->image_stride;
-	d.l_len = h->l_len;
-	d.sums = sc.sums;
-	int nI = (h->l_len + 1) / 2;
-	dim3 grid(std::max(1, std::min((nI + 1023) / 1024, 64)), n);
-	dc_sums_c16_kernel<<<grid, 256, 0, h->stream>>>(d);
-	return check_launch(h, "dc_sums_c16_kernel");
+	DcFinalizeParams f;
+	f.sums = sc.sums;
+	f.ave = sc.ave;
+	f.n = n;
+	f.l_len = h->l_len;
+	dc_finalize_kernel<<<(2 * n + 255) / 256, 256, 0, h->stream>>>(f);
+	return check_launch(h, "dc_finalize_kernel");
 }
 
 /*
@@ -535,7 +561,6 @@ int launch_batch(rtlsdr_gpu_scan *h, const uint8_t *base, const uint8_t *d_desc,
 		p.samples_per_read = h->samples_per_read;
 		p.tw = h->d_tw;
 		p.win = h->d_win;
-		p.units_per_read = 1;
 		p.tw0 = h->tw0;
 		TimedScope ts(h);
 		return launch_small(h, p, false);
@@ -556,7 +581,7 @@ int launch_batch(rtlsdr_gpu_scan *h, const uint8_t *base, const uint8_t *d_desc,
 				cnt += (*segs_host)[sj].z;
 				sj++;
 			}
-			if ((rc = ensure_scratch(h, per * (size_t)cnt + 256)))
+			if ((rc = ensure_scratch(h, per * (size_t)cnt + DecimScratch::slack())))
 				return rc;
 			DecimScratch sc(h, cnt, h->d_scratch);
 			TimedScope ts(h);
@@ -565,7 +590,7 @@ int launch_batch(rtlsdr_gpu_scan *h, const uint8_t *base, const uint8_t *d_desc,
 			SmallParams p;
 			memset(&p, 0, sizeof(p));
 			p.base = (const uint8_t *)sc.img;
-			p.read_off = nullptr; /* images are regular: entry e at (e - e0) * image bytes */
+			p.read_off = nullptr; /* images are contiguous: entry e at (e - e0) * image bytes */
 			p.regular_stride = h->image_stride * 4;
 			p.entry_base = e0;
 			p.segs = d_segs + si;
@@ -575,10 +600,10 @@ int launch_batch(rtlsdr_gpu_scan *h, const uint8_t *base, const uint8_t *d_desc,
 			p.samples_per_read = h->samples_per_read;
 			p.tw = h->d_tw;
 			p.win = h->d_win;
-			p.dc_sums = sc.sums;
+			p.dc_ave = sc.ave;
 			p.l_len = h->l_len;
 			p.n_blocks = h->n_blocks;
-			p.units_per_read = h->units_per_read;
+			p.blocks_padded = h->blocks_padded;
 			p.tw0 = h->tw0;
 			if ((rc = launch_small(h, p, true)))
 				return rc;
@@ -880,8 +905,11 @@ int rtlsdr_gpu_scan_init(const rtlsdr_gpu_scan_cfg_t *cfg, rtlsdr_gpu_scan_t **o
 				h->path = PATH_SMALL_U8;
 			} else {
 				h->path = PATH_SMALL_DECIM;
-				h->units_per_read = (int)(((long long)h->n_blocks * N + kWS - 1) / kWS);
-				h->image_stride = (long long)h->units_per_read * kWS;
+				/* images of consecutive reads are contiguous; keep each 16-byte aligned */
+				h->blocks_padded = h->n_blocks;
+				while (((long long)h->blocks_padded * N) % 4)
+					h->blocks_padded++;
+				h->image_stride = (long long)h->blocks_padded * N;
 			}
 		} else {
 			h->path = PATH_LARGE;

@@ -268,11 +268,11 @@ struct SmallParams {
 	int samples_per_read;
 	const int2 *tw;             /* [N/2] halved twiddles (wr, wi) */
 	const uint16_t *win;        /* [N] low 16 bits of window_coefs */
-	/* IN16 only */
-	const long long *dc_sums;   /* [entry - entry_base][2]: sums the reference's remove_dc sees */
+	/* IN16 only: images of consecutive entries are contiguous, blocks_padded * N c16 each */
+	const int *dc_ave;          /* [entry - entry_base][2]: int16 averages remove_dc subtracts (I, Q) */
 	int l_len;                  /* buf_len / downsample (interleaved int16 count) */
-	int n_blocks;               /* FFT blocks per read */
-	int units_per_read;         /* 4096-sample working sets per decimated image */
+	int n_blocks;               /* FFT blocks per read (rtl_power.c:695) */
+	int blocks_padded;          /* >= n_blocks: image length / N (16-byte alignment padding for N = 2) */
 	PassTw tw0;
 };
 
@@ -328,7 +328,6 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 	int2 *tws = (int2 *)(smem + SM::off_tw);
 	uint16_t *wins = (uint16_t *)(smem + SM::off_win);
 	int *red = (int *)(smem + SM::off_red); /* [8 warps][2] */
-	int *dck = (int *)(smem + SM::off_dck);
 
 	const int t = threadIdx.x;
 	for (int i = t; i < N - 16; i += kThreads) {
@@ -357,7 +356,9 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 	for (int seg = blockIdx.x; seg < prm.n_segs; seg += gridDim.x) {
 		const int4 sg = prm.segs[seg];
 		const int hop = sg.x, first = sg.y;
-		const int units = IN16 ? sg.z * prm.units_per_read : sg.z;
+		/* IN16: the segment's images form one contiguous run of blocks, cut into 4096-sample units */
+		const int seg_blocks = IN16 ? sg.z * prm.blocks_padded : 0;
+		const int units = IN16 ? (int)(((long long)seg_blocks * N + kWS - 1) / kWS) : sg.z;
 
 		unsigned long long acc[kPts];
 #pragma unroll
@@ -377,10 +378,11 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 			cp_async_wait_all();
 			__syncthreads(); /* slot u&1 landed; slot (u+1)&1 no longer read */
 			if (u + 1 < units) {
-				int e = first + (IN16 ? (u + 1) / prm.units_per_read : (u + 1));
-				long long o = entry_offset(prm, e);
+				long long o;
 				if (IN16)
-					o += (long long)((u + 1) % prm.units_per_read) * kStageBytes;
+					o = entry_offset(prm, first) + (long long)(u + 1) * kStageBytes;
+				else
+					o = entry_offset(prm, first + u + 1);
 				const uint8_t *src = prm.base + o;
 				uint8_t *dst = stage + ((u + 1) & 1) * kStageBytes;
 #pragma unroll
@@ -391,7 +393,7 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 			const uint8_t *st = stage + (u & 1) * kStageBytes;
 
 			/* ---- DC term of the whole read (rtl_power.c:692-693) ---- */
-			int limI = kWS, limQ = kWS, nvalid = kWS / N, kI, kQ;
+			int limI = kWS, limQ = kWS, kI, kQ;
 			if constexpr (!IN16) {
 				unsigned sI = 0, sQ = 0;
 #pragma unroll
@@ -426,16 +428,20 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 				kI = 127 + (int)(int16_t)((tI - 127 * (kStageBytes / 2)) / kStageBytes);
 				kQ = 127 + (int)(int16_t)((tQ - 127 * (kStageBytes / 2)) / (kStageBytes - 1));
 			} else {
-				const int e = first + u / prm.units_per_read;
-				const int w = u % prm.units_per_read;
-				if (t < 2)
-					dck[t] = dc_average(prm.dc_sums[2 * (e - prm.entry_base) + t], prm.l_len - t);
-				limI = ((prm.l_len + 1) >> 1) - w * kWS;
-				limQ = (prm.l_len >> 1) - w * kWS;
-				nvalid = prm.n_blocks - w * (kWS / N);
-				__syncthreads();
-				kI = dck[0];
-				kQ = dck[1];
+				/* working-set block b is block gb = u * (4096/N) + b of the segment */
+				if constexpr (L >= 4) {
+					const int gb = u * (kWS / N) + (t >> (L - 4));
+					const int rd = gb / prm.blocks_padded, bir = gb - rd * prm.blocks_padded;
+					const bool live = gb < seg_blocks && bir < prm.n_blocks;
+					const int e = first + (live ? rd : 0) - prm.entry_base;
+					kI = __ldg(prm.dc_ave + 2 * e);
+					kQ = __ldg(prm.dc_ave + 2 * e + 1);
+					/* remove_dc covers int16 indices < l_len of the read (rtl_power.c:692-693) */
+					limI = live ? ((prm.l_len + 1) >> 1) - bir * N : 0;
+					limQ = live ? (prm.l_len >> 1) - bir * N : 0;
+				} else {
+					kI = kQ = 0; /* per element below */
+				}
 			}
 
 #pragma unroll 1
@@ -462,10 +468,24 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 						const c16 raw = ((const c16 *)st)[n];
 						re = c16_re(raw);
 						im = c16_im(raw);
-						if (n < limI)
-							re -= kI;
-						if (n < limQ)
-							im -= kQ;
+						if constexpr (L >= 4) {
+							if (nblk < limI)
+								re -= kI;
+							if (nblk < limQ)
+								im -= kQ;
+						} else {
+							/* several blocks per thread: look the read up per element */
+							const int gb = u * (kWS / N) + (n >> L);
+							const int rd = gb / prm.blocks_padded, bir = gb - rd * prm.blocks_padded;
+							if (gb < seg_blocks && bir < prm.n_blocks) {
+								const int e = first + rd - prm.entry_base;
+								const int k = bir * N + nblk;
+								if (2 * k < prm.l_len)
+									re -= __ldg(prm.dc_ave + 2 * e);
+								if (2 * k + 1 < prm.l_len)
+									im -= __ldg(prm.dc_ave + 2 * e + 1);
+							}
+						}
 						re *= wv;
 						im *= wv;
 					}
@@ -481,8 +501,12 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 					const int re = x[r].re >> 16, im = x[r].im >> 16;
 					const unsigned pw = (unsigned)(re * re) + (unsigned)(im * im);
 					bool ok = true;
-					if constexpr (IN16)
-						ok = (last_pos<L>(t, r) >> L) < nvalid;
+					if constexpr (IN16) {
+						const int gb = u * (kWS / N) + (last_pos<L>(t, r) >> L);
+						ok = gb < seg_blocks;
+						if (prm.blocks_padded != prm.n_blocks)
+							ok = ok && (gb % prm.blocks_padded) < prm.n_blocks;
+					}
 					if (ok) {
 						if constexpr (PEAK)
 							acc[r] = acc[r] > pw ? acc[r] : (unsigned long long)pw;
@@ -659,6 +683,81 @@ boxcar_kernel(const SCAN_GRID_CONSTANT DecimParams prm)
 	}
 }
 
+/*
+ * Same result, for ds <= 64: the 256 slots of a CTA cover 512*ds contiguous input
+ * bytes.  They are fetched with fully coalesced 16-byte cp.async copies into
+ * shared memory and summed from there, so DRAM sees only full-line streaming
+ * reads (this is the HBM-bound regime of the pipeline: 2*ds input bytes per
+ * decimated sample).
+ */
+constexpr int kBoxcarStageMaxDs = 64;
+
+__global__ void __launch_bounds__(256)
+boxcar_staged_kernel(const SCAN_GRID_CONSTANT DecimParams prm)
+{
+	SCAN_DYN_SMEM(smem);
+	__shared__ long long red[2 * 8];
+	const int e = blockIdx.y;
+	const int t = threadIdx.x;
+	const int k = blockIdx.x * blockDim.x + t;
+	const uint8_t *src = prm.base + prm.read_off[e];
+	const int outs = (prm.pairs + prm.ds - 1) / prm.ds;
+	const int span0 = blockIdx.x * 512 * prm.ds;                 /* first input byte of this CTA */
+	int span = 2 * prm.pairs - span0;                            /* bytes that exist */
+	if (span > 512 * prm.ds)
+		span = 512 * prm.ds;
+	for (int o = t * 16; o < span; o += 256 * 16)               /* span0 and buf_len are multiples of 16 */
+		cp_async16(smem + o, src + span0 + o);
+	cp_async_commit();
+	cp_async_wait_all();
+	__syncthreads();
+	int si = 0, sq = 0;
+	if (k < outs) {
+		const int lo = t * 2 * prm.ds;
+		int nb = span - lo;
+		if (nb > 2 * prm.ds)
+			nb = 2 * prm.ds;
+		unsigned ui = 0, uq = 0;
+		if ((prm.ds & 1) == 0) {
+			for (int o = 0; o < nb; o += 4) {
+				const unsigned q = *(const unsigned *)(smem + lo + o);
+				ui = __dp4a(q, 0x00010001u, ui);
+				uq = __dp4a(q, 0x01000100u, uq);
+			}
+		} else {
+			for (int o = 0; o < nb; o += 2) {
+				const unsigned raw = *(const uint16_t *)(smem + lo + o);
+				ui += raw & 0xFFu;
+				uq += raw >> 8;
+			}
+		}
+		si = (int)ui - 127 * (nb >> 1);
+		sq = (int)uq - 127 * (nb >> 1);
+	}
+	const c16 v = c16_pack(si, sq);
+	if (k < prm.out_count)
+		prm.out[e * prm.out_stride + k] = v;
+	long long dI = (2 * k < prm.l_len) ? (long long)c16_re(v) : 0;
+	long long dQ = (2 * k + 1 < prm.l_len) ? (long long)c16_im(v) : 0;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		dI += __shfl_xor_sync(0xffffffffu, dI, o);
+		dQ += __shfl_xor_sync(0xffffffffu, dQ, o);
+	}
+	if ((t & 31) == 0) {
+		red[(t >> 5) * 2] = dI;
+		red[(t >> 5) * 2 + 1] = dQ;
+	}
+	__syncthreads();
+	if (t < 2) {
+		long long s = 0;
+		for (int w = 0; w < (int)(blockDim.x >> 5); ++w)
+			s += red[2 * w + t];
+		if (s != 0)
+			atomicAdd((unsigned long long *)(prm.sums + 2 * e + t), (unsigned long long)s);
+	}
+}
+
 struct HalfbandParams {
 	const void *in;            /* u8 pairs (first pass) or c16 */
 	const long long *read_off; /* first pass: byte offsets of the u8 reads */
@@ -809,6 +908,23 @@ dc_sums_c16_kernel(const SCAN_GRID_CONSTANT DcSumParams prm)
 		atomicAdd((unsigned long long *)(prm.sums + 2 * e), (unsigned long long)sI);
 		atomicAdd((unsigned long long *)(prm.sums + 2 * e + 1), (unsigned long long)sQ);
 	}
+}
+
+struct DcFinalizeParams {
+	const long long *sums; /* [n][2] */
+	int *ave;              /* [n][2] */
+	int n;
+	int l_len;
+};
+
+/* ave = (int16)(sum / length), C division; I over l_len, Q over l_len - 1 (rtl_power.c:589, 692-693) */
+__global__ void __launch_bounds__(256)
+dc_finalize_kernel(const SCAN_GRID_CONSTANT DcFinalizeParams prm)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= 2 * prm.n)
+		return;
+	prm.ave[i] = dc_average(prm.sums[i], prm.l_len - (i & 1));
 }
 
 /* ======================================================================== *

@@ -61,11 +61,12 @@ int large_process(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_of
 	const size_t N = (size_t)1 << L;
 	const bool decim = (h->cfg.boxcar && h->cfg.downsample > 1) || h->cfg.downsample_passes > 0;
 	const size_t per = N * 4 + 16 + (decim ? DecimScratch::per_entry(h) : 0);
+	const size_t extra = decim ? DecimScratch::slack() + 512 : 512;
 	const int chunk_max = (int)std::max<size_t>(1, kScratchBudget / per);
 	int rc;
 	for (int e0 = 0; e0 < n_reads; e0 += chunk_max) {
 		const int cnt = std::min(chunk_max, n_reads - e0);
-		if ((rc = ensure_scratch(h, per * (size_t)cnt + 512)))
+		if ((rc = ensure_scratch(h, per * (size_t)cnt + extra)))
 			return rc;
 		uint8_t *sp = h->d_scratch;
 		c16 *data = (c16 *)sp;

@@ -81,7 +81,6 @@ void emu_small_u8(int L, int peak, const uint8_t *reads, int n_reads, const int 
 	p.samples_per_read = 1;
 	p.tw = (const int2 *)tw;
 	p.win = win;
-	p.units_per_read = 1;
 	fill_tw0(p.tw0, p.tw, L);
 	run_small(L, p, peak, 0);
 }
@@ -97,12 +96,14 @@ void emu_small_decim(int L, int peak, const uint8_t *reads, int n_reads, int buf
 	const int N = 1 << L, pairs = buf_len / 2;
 	const int l_len = buf_len / ds;
 	const int n_blocks = (l_len + 2 * N - 1) / (2 * N);
-	const int units = (int)(((long long)n_blocks * N + kWS - 1) / kWS);
-	const long long stride = (long long)units * kWS;
+	int blocks_padded = n_blocks;
+	while (((long long)blocks_padded * N) % 4)
+		blocks_padded++;
+	const long long stride = (long long)blocks_padded * N;
 	std::vector<long long> offs(n_reads);
 	for (int i = 0; i < n_reads; i++)
 		offs[i] = (long long)i * buf_len;
-	std::vector<c16> img((size_t)n_reads * stride, 0xDEADBEEFu); /* padding must not matter */
+	std::vector<c16> img((size_t)n_reads * stride + kWS, 0xDEADBEEFu); /* padding must not matter */
 	std::vector<long long> sums((size_t)n_reads * 2, 0);
 
 	if (mode == 0) {
@@ -119,7 +120,9 @@ void emu_small_decim(int L, int peak, const uint8_t *reads, int n_reads, int buf
 		d.sums = sums.data();
 		dim3 grid((unsigned)((stride + 255) / 256), n_reads);
 		const int bytes = 2 * ds;
-		if (bytes % 16 == 0)
+		if (ds <= kBoxcarStageMaxDs)
+			cuda_emu::launch(grid, dim3(256), 512 * ds, [&]() { boxcar_staged_kernel(d); });
+		else if (bytes % 16 == 0)
 			cuda_emu::launch(grid, dim3(256), 0, [&]() { boxcar_kernel<16>(d); });
 		else if (bytes % 8 == 0)
 			cuda_emu::launch(grid, dim3(256), 0, [&]() { boxcar_kernel<8>(d); });
@@ -171,7 +174,7 @@ void emu_small_decim(int L, int peak, const uint8_t *reads, int n_reads, int buf
 		cuda_emu::launch(dim3(3, n_reads), dim3(256), 0, [&]() { dc_sums_c16_kernel(dc); });
 	}
 	if (image_out)
-		memcpy(image_out, img.data(), img.size() * 4);
+		memcpy(image_out, img.data(), (size_t)n_reads * stride * 4);
 	if (sums_out)
 		memcpy(sums_out, sums.data(), sums.size() * 8);
 
@@ -189,10 +192,17 @@ void emu_small_decim(int L, int peak, const uint8_t *reads, int n_reads, int buf
 	p.samples_per_read = 1;
 	p.tw = (const int2 *)tw;
 	p.win = win;
-	p.dc_sums = sums.data();
+	std::vector<int> ave((size_t)n_reads * 2, 0);
+	DcFinalizeParams fz;
+	fz.sums = sums.data();
+	fz.ave = ave.data();
+	fz.n = n_reads;
+	fz.l_len = l_len;
+	cuda_emu::launch(dim3((2 * n_reads + 255) / 256), dim3(256), 0, [&]() { dc_finalize_kernel(fz); });
+	p.dc_ave = ave.data();
 	p.l_len = l_len;
 	p.n_blocks = n_blocks;
-	p.units_per_read = units;
+	p.blocks_padded = blocks_padded;
 	fill_tw0(p.tw0, p.tw, L);
 	run_small(L, p, peak, 1);
 }

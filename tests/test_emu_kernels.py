@@ -80,7 +80,9 @@ def test_small_u8_kernel(emu, port_oracle, bin_e):
     ("100M:100.1M:100", "rectangle", -1, 0), ("100M:100.1M:100", "blackman", 9, 0),
     ("100M:100.1M:100", "youssef", 0, 1), ("100M:100.5M:10k", "bartlett", -1, 0),
     ("100M:100.3M:3k", "hamming", -1, 1), ("100M:100.9M:30k", "hamming", -1, 0),
-    ("100M:100.01M:50", "hamming", 9, 0)])
+    ("100M:100.01M:50", "hamming", 9, 0),
+    ("100M:100.02M:100", "hamming", -1, 0),    # boxcar ds=140: thread-per-slot kernel, 16-byte loads
+    ("100M:100.03M:100", "blackman", -1, 1)])  # boxcar ds=93
 def test_decimating_kernels(emu, port_oracle, freq, window, fir, peak):
     from rtlsdr_b200.planner import plan_scan
     plan = plan_scan(freq, 0.0, None if fir < 0 else fir).as_dict()
@@ -145,3 +147,23 @@ def test_rms_and_epilogue_kernels(emu, port_oracle):
         fin = np.isfinite(db)
         assert np.array_equal(np.isfinite(out[h]), fin)
         assert np.allclose(out[h][fin], db[fin], rtol=1e-12)
+
+
+@pytest.mark.parametrize("bin_e,ds", [(1, 7), (2, 3), (3, 5), (4, 2), (6, 11), (12, 2)])
+def test_decimating_small_n_multi_segment(emu, port_oracle, bin_e, ds):
+    """boxcar images of consecutive reads are packed back to back: FFT blocks of several
+    reads share a working set (and, for N < 16, a thread); two hops, uneven segments."""
+    n = 1 << bin_e
+    buf_len = max(16384, 2 * n * ds)
+    plan = plan_dict(bin_e, buf_len=buf_len, downsample=ds, tune_count=2, peak_hold=bin_e % 2)
+    win = port_oracle.window_coefs("hamming", n)
+    reads, hops = make_reads(port_oracle.lib, plan, 3, SYNTH_BIASED, seed=bin_e, param=45)
+    reads, hops = reads[:5], hops[:5]
+    want, _, _ = expected(port_oracle, plan, win, reads, hops)
+    sreads, shops, segs = sort_by_hop(reads, hops, 2, split=2)
+    tw = twiddles(port_oracle.sine_table(bin_e), bin_e)
+    w16 = (win & 0xFFFF).astype(np.uint16)
+    avg = np.zeros((2, n), dtype=np.int64)
+    emu.emu_small_decim(bin_e, plan["peak_hold"], vp(sreads), len(sreads), buf_len, ds, 0, 0, None, vp(segs),
+                        len(segs), vp(tw), vp(w16), vp(avg), None, None)
+    assert np.array_equal(avg, want)

@@ -99,6 +99,8 @@ def test_survey_known_answers(scan_mod, port_oracle, row):
     ("100M:100.3M:3k", "hamming", -1, 1),      # ds=9
     ("100M:100.9M:30k", "hamming", -1, 0),     # ds=3, odd l_len
     ("100M:100.01M:50", "hamming", 9, 0),      # 8 passes, B=131072
+    ("100M:100.02M:100", "hamming", -1, 0),    # boxcar ds=140: thread-per-slot kernel, 16-byte loads
+    ("100M:100.03M:100", "blackman", -1, 1),   # boxcar ds=93
 ])
 @pytest.mark.parametrize("mode,param", [(SYNTH_XORSHIFT, 0), (SYNTH_BIASED, 40), (SYNTH_CONST, 255)])
 def test_decimating_paths(scan_mod, port_oracle, freq, window, fir, peak, mode, param):
@@ -227,3 +229,18 @@ def test_cli_csv_matches_reference_rows(scan_mod, port_oracle, tmp_path):
     avg, smp, db = expected(port_oracle, pd, w, reads, hops)
     want = "".join("2026-01-01, 00:00:00, " + plan.csv_row(h, int(smp[h]), db[h]) for h in range(pd["tune_count"]))
     assert out.read_text() == want
+
+
+@pytest.mark.parametrize("bin_e,ds", [(1, 7), (2, 3), (3, 5), (4, 2), (6, 11), (12, 2)])
+def test_decimating_small_n(scan_mod, port_oracle, bin_e, ds):
+    """packed decimated images: several reads per working set, N down to 2 (alignment padding)"""
+    n = 1 << bin_e
+    buf_len = max(16384, 2 * n * ds)
+    plan = plan_dict(bin_e, buf_len=buf_len, downsample=ds, tune_count=3, peak_hold=bin_e % 2, crop=0.0)
+    w = port_oracle.window_coefs("blackman", n)
+    reads, hops = make_reads(port_oracle.lib, plan, 5, SYNTH_BIASED, seed=bin_e, param=45)
+    want = expected(port_oracle, plan, w, reads, hops)
+    got = run_gpu(scan_mod, plan, w, reads, hops)
+    assert np.array_equal(got[0], want[0])
+    assert np.array_equal(got[1], want[1])
+    assert db_close(got[2], want[2])
