@@ -25,6 +25,8 @@ int launch_round_b(rtlsdr_gpu_scan *h, const LargeParams &p, dim3 grid, int lb, 
 	case 6: return last ? launch_round_b_t<6, true>(h, p, grid) : RTLSDR_GPU_ERR_CONFIG;
 	case 7: return last ? launch_round_b_t<7, true>(h, p, grid) : RTLSDR_GPU_ERR_CONFIG;
 	case 8: return last ? launch_round_b_t<8, true>(h, p, grid) : launch_round_b_t<8, false>(h, p, grid);
+	case 9: return last ? launch_round_b_t<9, true>(h, p, grid) : RTLSDR_GPU_ERR_CONFIG;
+	case 10: return last ? launch_round_b_t<10, true>(h, p, grid) : RTLSDR_GPU_ERR_CONFIG;
 	default: return RTLSDR_GPU_ERR_CONFIG;
 	}
 }
@@ -124,10 +126,11 @@ int large_process(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_of
 			if ((rc = check_launch(h, "large_round_a_kernel")))
 				return rc;
 		}
+		/* (letting round B take 9-10 stages to save round C was measured slower: 32-byte runs) */
 		const int lb = std::min(8, L - 8);
 		if ((rc = launch_round_b(h, p, grid_tiles, lb, 8 + lb == L)))
 			return rc;
-		if (L > 16) {
+		if (8 + lb < L) {
 			dim3 g(65536 / kThreads, (unsigned)cnt);
 			if ((rc = launch_round_c(h, p, g, L - 16)))
 				return rc;

@@ -51,10 +51,12 @@ void emu_large(int L, int peak, int in16, const uint8_t *reads, int n_reads, con
 	if (lb == 5) RB(5, true);
 	else if (lb == 6) RB(6, true);
 	else if (lb == 7) RB(7, true);
+	else if (lb == 9) RB(9, true);
+	else if (lb == 10) RB(10, true);
 	else if (last) RB(8, true);
 	else RB(8, false);
 #undef RB
-	if (L > 16) {
+	if (8 + lb < L) {
 		dim3 g(65536 / kThreads, n_reads);
 #define RC(LCV)                                                                                         \
 	do {                                                                                            \
