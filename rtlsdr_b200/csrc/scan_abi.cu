@@ -31,6 +31,10 @@ namespace {
 constexpr int kDescSlots = 4;
 constexpr size_t kDefaultRing = 32u << 20;
 constexpr size_t kScratchBudget = 512ull << 20; /* device bytes for decimation / large-FFT scratch */
+constexpr int kChainMaxPasses = 7;           /* fused fifth_order chain up to 128x decimation */
+constexpr int kChainCap0 = 8192;             /* level-0 samples a chain tile may span (32 KiB) */
+constexpr int kDecimChunks = 4;              /* only for batches >= kDecimOverlapBytes (measured: a loss below) */
+constexpr size_t kDecimOverlapBytes = 1ull << 30;
 
 enum Path { PATH_RMS, PATH_SMALL_U8, PATH_SMALL_DECIM, PATH_LARGE };
 
@@ -103,6 +107,10 @@ struct rtlsdr_gpu_scan {
 	std::vector<RegCache> reg_cache;
 	uint64_t reg_stamp = 0;
 	/* submit_batch: H2D copies run on their own stream, chunk by chunk, ahead of the kernels */
+	/* decimating path: the (memory-bound) decimators of chunk k+1 overlap the (compute-bound)
+	 * transform of chunk k on two auxiliary streams */
+	cudaStream_t aux[2] = { nullptr, nullptr };
+	cudaEvent_t fork_ev = nullptr, join_ev[2] = { nullptr, nullptr };
 	cudaStream_t copy_stream = nullptr;
 	cudaEvent_t bulk_free = nullptr;   /* last kernel that reads d_bulk has finished */
 	bool bulk_used = false;
@@ -325,7 +333,9 @@ int build_desc(rtlsdr_gpu_scan *h, const std::vector<long long> &offs, const std
 		s_offs[p] = offs[i];
 		s_hops[p] = hops[i];
 	}
-	const int target = std::max(1, h->num_sms * h->ctas_per_sm);
+	/* the decimating path runs in kDecimChunks chunks, each should still fill the GPU */
+	const bool big_decim = h->path == PATH_SMALL_DECIM && (size_t)n * (size_t)h->cfg.buf_len >= kDecimOverlapBytes;
+	const int target = std::max(1, h->num_sms * h->ctas_per_sm) * (big_decim ? kDecimChunks : 1);
 	const int chunk = std::max(1, (n + target - 1) / target);
 	segs.clear();
 	for (int hp = 0; hp < tc; hp++) {
@@ -397,7 +407,7 @@ struct DecimScratch {
 	int *ave;
 	static bool halfband(const rtlsdr_gpu_scan *h)
 	{
-		return !(h->cfg.boxcar && h->cfg.downsample > 1) && h->cfg.downsample_passes > 0;
+		return !(h->cfg.boxcar && h->cfg.downsample > 1) && h->cfg.downsample_passes > kChainMaxPasses;
 	}
 	/* bytes per entry (the 16 KiB of slack after the images is added by the caller) */
 	static size_t per_entry(const rtlsdr_gpu_scan *h)
@@ -459,6 +469,34 @@ int run_decimators(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_o
 		else
 			boxcar_kernel<2><<<grid, 256, 0, h->stream>>>(p);
 		if ((rc = check_launch(h, "boxcar_kernel"))) /* DC sums are fused into the boxcar kernel */
+			return rc;
+	} else if (h->cfg.downsample_passes <= kChainMaxPasses) {
+		/* fused fifth_order chain + FIR + DC sums, one kernel */
+		const int passes = h->cfg.downsample_passes;
+		const int M = pairs >> passes;
+		HalfbandChainParams p;
+		p.base = base;
+		p.read_off = d_offs;
+		p.pairs = pairs;
+		p.passes = passes;
+		p.use_fir = (h->cfg.comp_fir_size == 9 && passes <= 10) ? 1 : 0;
+		const int *row = kCic9[passes];
+		p.f1 = row[0]; p.f2 = row[1]; p.f3 = row[2]; p.f4 = row[3]; p.f5 = row[4];
+		p.out = sc.img;
+		p.out_stride = h->image_stride;
+		p.l_len = h->l_len;
+		p.sums = sc.sums;
+		/* level-0 span of a tile: (tile + 9) * 2^P + 5 * (2^P - 1) + 9 samples at most */
+		int tile = std::min(256, std::max(8, (kChainCap0 >> passes) - 16));
+		tile = std::min(tile, M);
+		p.tile = tile;
+		p.cap0 = kChainCap0;
+		const int smem = (kChainCap0 + kChainCap0 / 2 + 16) * 4;
+		CU(cudaFuncSetAttribute(halfband_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		CU(cudaMemsetAsync(sc.sums, 0, (size_t)n * 16, h->stream));
+		dim3 grid((M + tile - 1) / tile, n);
+		halfband_chain_kernel<<<grid, 256, smem, h->stream>>>(p);
+		if ((rc = check_launch(h, "halfband_chain_kernel")))
 			return rc;
 	} else {
 		const int passes = h->cfg.downsample_passes;
@@ -567,49 +605,90 @@ int launch_batch(rtlsdr_gpu_scan *h, const uint8_t *base, const uint8_t *d_desc,
 	}
 
 	if (h->path == PATH_SMALL_DECIM) {
-		/* entries are processed in chunks bounded by the scratch budget; segments
-		 * never straddle a chunk because chunks are cut at segment boundaries */
+		/* Entries are processed in chunks cut at segment boundaries.  Chunks alternate between
+		 * two auxiliary streams and two scratch halves, so the decimators of one chunk (HBM
+		 * bound) run while the transform of the previous one (issue bound) is still busy. */
 		const size_t per = DecimScratch::per_entry(h);
-		const int max_entries = (int)std::max<size_t>(1, kScratchBudget / per);
+		const int max_entries = (int)std::max<size_t>(1, (kScratchBudget / 2) / per);
 		if (!segs_host)
 			return RTLSDR_GPU_ERR_CONFIG;
-		size_t si = 0;
-		while (si < segs_host->size()) {
+		const int n_chunks = ((size_t)n_reads * (size_t)h->cfg.buf_len >= kDecimOverlapBytes) ? kDecimChunks : 1;
+		const int want = std::max(1, std::min(max_entries, (n_reads + n_chunks - 1) / n_chunks));
+		/* chunk boundaries first: the scratch must fit the largest one */
+		std::vector<std::pair<size_t, size_t>> chunks;
+		int cnt_max = 0;
+		for (size_t si = 0; si < segs_host->size();) {
 			size_t sj = si;
-			int e0 = (*segs_host)[si].y, cnt = 0;
-			while (sj < segs_host->size() && (cnt == 0 || cnt + (*segs_host)[sj].z <= max_entries)) {
+			int cnt = 0;
+			while (sj < segs_host->size() && (cnt == 0 || cnt + (*segs_host)[sj].z <= want)) {
 				cnt += (*segs_host)[sj].z;
 				sj++;
 			}
-			if ((rc = ensure_scratch(h, per * (size_t)cnt + DecimScratch::slack())))
-				return rc;
-			DecimScratch sc(h, cnt, h->d_scratch);
-			TimedScope ts(h);
-			if ((rc = run_decimators(h, base, d_offs + e0, cnt, sc)))
-				return rc;
-			SmallParams p;
-			memset(&p, 0, sizeof(p));
-			p.base = (const uint8_t *)sc.img;
-			p.read_off = nullptr; /* images are contiguous: entry e at (e - e0) * image bytes */
-			p.regular_stride = h->image_stride * 4;
-			p.entry_base = e0;
-			p.segs = d_segs + si;
-			p.n_segs = (int)(sj - si);
-			p.avg = h->d_avg;
-			p.samples = h->d_smp64;
-			p.samples_per_read = h->samples_per_read;
-			p.tw = h->d_tw;
-			p.win = h->d_win;
-			p.dc_ave = sc.ave;
-			p.l_len = h->l_len;
-			p.n_blocks = h->n_blocks;
-			p.blocks_padded = h->blocks_padded;
-			p.tw0 = h->tw0;
-			if ((rc = launch_small(h, p, true)))
-				return rc;
+			cnt_max = std::max(cnt_max, cnt);
+			chunks.push_back({ si, sj });
 			si = sj;
 		}
-		return 0;
+		const size_t half = ((per * (size_t)cnt_max + DecimScratch::slack()) + 255) & ~(size_t)255;
+		if ((rc = ensure_scratch(h, 2 * half)))
+			return rc;
+		if (!h->aux[0]) {
+			for (int i = 0; i < 2; i++) {
+				CU(cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking));
+				CU(cudaEventCreateWithFlags(&h->join_ev[i], cudaEventDisableTiming));
+			}
+			CU(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
+		}
+		cudaStream_t main_stream = h->stream;
+		TimedScope ts(h);
+		const bool overlap = chunks.size() > 1;
+		if (overlap) {
+			CU(cudaEventRecord(h->fork_ev, main_stream));
+			CU(cudaStreamWaitEvent(h->aux[0], h->fork_ev, 0));
+			CU(cudaStreamWaitEvent(h->aux[1], h->fork_ev, 0));
+		}
+		for (size_t c = 0; c < chunks.size() && !rc; c++) {
+			const size_t si = chunks[c].first, sj = chunks[c].second;
+			const int e0 = (*segs_host)[si].y;
+			int cnt = 0;
+			for (size_t k = si; k < sj; k++)
+				cnt += (*segs_host)[k].z;
+			if (overlap)
+				h->stream = h->aux[c & 1];
+			DecimScratch sc(h, cnt, h->d_scratch + (overlap ? (c & 1) * half : 0));
+			rc = run_decimators(h, base, d_offs + e0, cnt, sc);
+			if (!rc) {
+				SmallParams p;
+				memset(&p, 0, sizeof(p));
+				p.base = (const uint8_t *)sc.img;
+				p.read_off = nullptr; /* images are contiguous: entry e at (e - e0) * image bytes */
+				p.regular_stride = h->image_stride * 4;
+				p.entry_base = e0;
+				p.segs = d_segs + si;
+				p.n_segs = (int)(sj - si);
+				p.avg = h->d_avg;
+				p.samples = h->d_smp64;
+				p.samples_per_read = h->samples_per_read;
+				p.tw = h->d_tw;
+				p.win = h->d_win;
+				p.dc_ave = sc.ave;
+				p.l_len = h->l_len;
+				p.n_blocks = h->n_blocks;
+				p.blocks_padded = h->blocks_padded;
+				p.tw0 = h->tw0;
+				rc = launch_small(h, p, true);
+			}
+		}
+		h->stream = main_stream;
+		if (overlap) {
+			for (int i = 0; i < 2; i++) {
+				if (cudaEventRecord(h->join_ev[i], h->aux[i]) != cudaSuccess ||
+				    cudaStreamWaitEvent(main_stream, h->join_ev[i], 0) != cudaSuccess) {
+					h->last_error = "stream join failed";
+					return RTLSDR_GPU_ERR_CUDA;
+				}
+			}
+		}
+		return rc;
 	}
 
 	/* PATH_LARGE */
@@ -709,6 +788,14 @@ void free_all(rtlsdr_gpu_scan *h)
 	cudaFree(h->d_bulk);
 	for (auto &c : h->reg_cache)
 		cudaFree(c.d_desc);
+	for (int i = 0; i < 2; i++) {
+		if (h->aux[i])
+			cudaStreamDestroy(h->aux[i]);
+		if (h->join_ev[i])
+			cudaEventDestroy(h->join_ev[i]);
+	}
+	if (h->fork_ev)
+		cudaEventDestroy(h->fork_ev);
 	if (h->copy_stream)
 		cudaStreamDestroy(h->copy_stream);
 	if (h->bulk_free)

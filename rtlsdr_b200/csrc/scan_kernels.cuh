@@ -832,6 +832,168 @@ halfband_kernel(const SCAN_GRID_CONSTANT HalfbandParams prm)
 	prm.out[e * prm.out_stride + n] = c16_pack(re, im);
 }
 
+/*
+ * The whole -F chain of one read tile in one kernel (downsample_passes <= 7):
+ * fifth_order x P (rtl_power.c:554-579, 683-685) and the optional 9-tap
+ * generic_fir (rtl_power.c:598-626, 687-690), with the decimated c16 image and
+ * the remove_dc sums as output.  A CTA produces `tile` final samples; the input
+ * span it needs (tile * 2^P samples plus a halo of 5 * (2^P - 1) + 9 * 2^P) is
+ * read once with coalesced loads and all intermediate levels stay in shared
+ * memory (int16 wrap at every level, like the reference's in-place buffer).
+ */
+struct HalfbandChainParams {
+	const uint8_t *base;
+	const long long *read_off;
+	int pairs;                 /* complex samples per read */
+	int passes;                /* P */
+	int tile;                  /* final samples per CTA */
+	int use_fir;
+	int f1, f2, f3, f4, f5;
+	c16 *out;
+	long long out_stride;
+	int l_len;
+	long long *sums;
+	int cap0;                  /* capacity (c16) of the level-0 buffer; level 1 buffer = cap0/2 + 8 */
+};
+
+/* one fifth_order output n from level buffer `src` whose element 0 is absolute index `lo` */
+SCAN_DEV c16 halfband_output(const c16 *src, int lo, int n)
+{
+	int i0, i1, i2, i3, i4, i5;
+	if (n >= 5) {
+		i0 = 2 * n - 5; i1 = 2 * n - 4; i2 = 2 * n - 3; i3 = 2 * n - 2; i4 = 2 * n - 1; i5 = 2 * n;
+	} else if (n == 4) {
+		i0 = 4; i1 = 5; i2 = 5; i3 = 6; i4 = 7; i5 = 8;
+	} else if (n == 3) {
+		i0 = 2; i1 = 3; i2 = 4; i3 = 5; i4 = 5; i5 = 6;
+	} else {
+		i0 = 0; i1 = 1; i2 = 2; i3 = 3; i4 = 4; i5 = 5;
+	}
+	const c16 v0 = src[i0 - lo], v1 = src[i1 - lo], v2 = src[i2 - lo], v3 = src[i3 - lo], v4 = src[i4 - lo],
+		  v5 = src[i5 - lo];
+	const int r0 = c16_re(v0), r1 = c16_re(v1), r2 = c16_re(v2), r3 = c16_re(v3), r4 = c16_re(v4), r5 = c16_re(v5);
+	const int q0 = c16_im(v0), q1 = c16_im(v1), q2 = c16_im(v2), q3 = c16_im(v3), q4 = c16_im(v4), q5 = c16_im(v5);
+	int re, im;
+	if (n == 0) {
+		re = ((r0 + r1) * 10 + (r2 + r3) * 5 + r3 + r5) >> 4;
+		im = ((q0 + q1) * 10 + (q2 + q3) * 5 + q3 + q5) >> 4;
+	} else if (n == 1) {
+		re = ((r1 + r2) * 10 + (r0 + r3) * 5 + r4 + r5) >> 4;
+		im = ((q1 + q2) * 10 + (q0 + q3) * 5 + q4 + q5) >> 4;
+	} else {
+		re = (r0 + (r1 + r4) * 5 + (r2 + r3) * 10 + r5) >> 4;
+		im = (q0 + (q1 + q4) * 5 + (q2 + q3) * 10 + q5) >> 4;
+	}
+	return c16_pack(re, im);
+}
+
+__global__ void __launch_bounds__(256)
+halfband_chain_kernel(const SCAN_GRID_CONSTANT HalfbandChainParams prm)
+{
+	SCAN_DYN_SMEM(smem);
+	__shared__ long long red[2 * 8];
+	__shared__ int lo_s[12], hi_s[12];
+	c16 *buf0 = (c16 *)smem;
+	c16 *buf1 = buf0 + prm.cap0;
+	const int e = blockIdx.y, t = threadIdx.x, P = prm.passes;
+	const int M = prm.pairs >> P;
+	const int k0 = blockIdx.x * prm.tile;
+	const int k1 = (k0 + prm.tile < M) ? k0 + prm.tile : M;
+
+	/* index ranges [lo_j, hi_j] needed at every level, top down */
+	if (t == 0) {
+		int lo = prm.use_fir ? (k0 >= 9 ? k0 - 9 : 0) : k0, hi = k1 - 1;
+		lo_s[P] = lo;
+		hi_s[P] = hi;
+		for (int j = P; j >= 1; --j) {
+			const int cnt = prm.pairs >> (j - 1);
+			int nlo = 2 * lo - 5, nhi = 2 * hi;
+			if (nlo < 0)
+				nlo = 0;
+			if (lo <= 4 && nhi < 8)
+				nhi = 8; /* the eased-in outputs 0..4 read inputs 0..8 */
+			if (nhi > cnt - 1)
+				nhi = cnt - 1;
+			lo = nlo;
+			hi = nhi;
+			lo_s[j - 1] = lo;
+			hi_s[j - 1] = hi;
+		}
+	}
+	__syncthreads();
+
+	/* level 0: u8 pairs -> c16 minus 127 (rtl_power.c:666-668) */
+	{
+		const uint16_t *src = (const uint16_t *)(prm.base + prm.read_off[e]);
+		const int lo = lo_s[0], n = hi_s[0] - lo + 1;
+		for (int i = t; i < n; i += 256) {
+			const unsigned raw = __ldg(src + lo + i);
+			buf0[i] = c16_pack((int)(raw & 0xFFu) - 127, (int)(raw >> 8) - 127);
+		}
+	}
+	__syncthreads();
+	c16 *cur = buf0, *nxt = buf1;
+	for (int j = 1; j <= P; ++j) {
+		const int lo = lo_s[j], n = hi_s[j] - lo + 1, plo = lo_s[j - 1];
+		for (int i = t; i < n; i += 256)
+			nxt[i] = halfband_output(cur, plo, lo + i);
+		__syncthreads();
+		c16 *tmp = cur;
+		cur = nxt;
+		nxt = tmp;
+	}
+
+	/* droop-compensation FIR (or plain copy), image store, DC sums */
+	long long dI = 0, dQ = 0;
+	const int lo = lo_s[P];
+	for (int k = k0 + t; k < k1; k += 256) {
+		c16 o = cur[k - lo];
+		if (prm.use_fir && k >= 9) {
+			const c16 *hsrc = cur + (k - 9 - lo);
+			int hr[9], hi[9];
+#pragma unroll
+			for (int i = 0; i < 9; ++i) {
+				hr[i] = c16_re(hsrc[i]);
+				hi[i] = c16_im(hsrc[i]);
+			}
+			unsigned sr = 0, si = 0;
+			sr += (unsigned)(hr[0] + hr[8]) * (unsigned)prm.f1;
+			sr += (unsigned)(hr[1] + hr[7]) * (unsigned)prm.f2;
+			sr += (unsigned)(hr[2] + hr[6]) * (unsigned)prm.f3;
+			sr += (unsigned)(hr[3] + hr[5]) * (unsigned)prm.f4;
+			sr += (unsigned)hr[4] * (unsigned)prm.f5;
+			si += (unsigned)(hi[0] + hi[8]) * (unsigned)prm.f1;
+			si += (unsigned)(hi[1] + hi[7]) * (unsigned)prm.f2;
+			si += (unsigned)(hi[2] + hi[6]) * (unsigned)prm.f3;
+			si += (unsigned)(hi[3] + hi[5]) * (unsigned)prm.f4;
+			si += (unsigned)hi[4] * (unsigned)prm.f5;
+			o = c16_pack((int)sr >> 15, (int)si >> 15);
+		}
+		prm.out[e * prm.out_stride + k] = o;
+		if (2 * k < prm.l_len)
+			dI += c16_re(o);
+		if (2 * k + 1 < prm.l_len)
+			dQ += c16_im(o);
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		dI += __shfl_xor_sync(0xffffffffu, dI, o);
+		dQ += __shfl_xor_sync(0xffffffffu, dQ, o);
+	}
+	if ((t & 31) == 0) {
+		red[(t >> 5) * 2] = dI;
+		red[(t >> 5) * 2 + 1] = dQ;
+	}
+	__syncthreads();
+	if (t < 2) {
+		long long s = 0;
+		for (int w = 0; w < 8; ++w)
+			s += red[2 * w + t];
+		if (s != 0)
+			atomicAdd((unsigned long long *)(prm.sums + 2 * e + t), (unsigned long long)s);
+	}
+}
+
 struct FirParams {
 	const c16 *in;
 	long long in_stride;

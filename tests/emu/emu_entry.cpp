@@ -130,6 +130,28 @@ void emu_small_decim(int L, int peak, const uint8_t *reads, int n_reads, int buf
 			cuda_emu::launch(grid, dim3(256), 0, [&]() { boxcar_kernel<4>(d); });
 		else
 			cuda_emu::launch(grid, dim3(256), 0, [&]() { boxcar_kernel<2>(d); });
+	} else if (ds_p <= 7) {
+		const int M = pairs >> ds_p, cap0 = 8192;
+		HalfbandChainParams hp;
+		hp.base = reads;
+		hp.read_off = offs.data();
+		hp.pairs = pairs;
+		hp.passes = ds_p;
+		hp.use_fir = fir5 ? 1 : 0;
+		hp.f1 = fir5 ? fir5[0] : 0; hp.f2 = fir5 ? fir5[1] : 0; hp.f3 = fir5 ? fir5[2] : 0;
+		hp.f4 = fir5 ? fir5[3] : 0; hp.f5 = fir5 ? fir5[4] : 0;
+		hp.out = img.data();
+		hp.out_stride = stride;
+		hp.l_len = l_len;
+		hp.sums = sums.data();
+		int tile = (cap0 >> ds_p) - 16;
+		if (tile > 256) tile = 256;
+		if (tile < 8) tile = 8;
+		if (tile > M) tile = M;
+		hp.tile = tile;
+		hp.cap0 = cap0;
+		cuda_emu::launch(dim3((M + tile - 1) / tile, n_reads), dim3(256), (cap0 + cap0 / 2 + 16) * 4,
+				 [&]() { halfband_chain_kernel(hp); });
 	} else {
 		std::vector<c16> a((size_t)n_reads * (pairs / 2)), b((size_t)n_reads * (pairs / 4 + 4));
 		const c16 *cur = nullptr;
@@ -165,7 +187,7 @@ void emu_small_decim(int L, int peak, const uint8_t *reads, int n_reads, int buf
 		f.f4 = fir5 ? fir5[3] : 0; f.f5 = fir5 ? fir5[4] : 0;
 		cuda_emu::launch(dim3((count + 255) / 256, n_reads), dim3(256), 0, [&]() { fir9_kernel(f); });
 	}
-	if (mode != 0) {
+	if (mode != 0 && ds_p > 7) {
 		DcSumParams dc;
 		dc.img = img.data();
 		dc.stride = stride;

@@ -167,3 +167,27 @@ def test_decimating_small_n_multi_segment(emu, port_oracle, bin_e, ds):
     emu.emu_small_decim(bin_e, plan["peak_hold"], vp(sreads), len(sreads), buf_len, ds, 0, 0, None, vp(segs),
                         len(segs), vp(tw), vp(w16), vp(avg), None, None)
     assert np.array_equal(avg, want)
+
+
+@pytest.mark.parametrize("passes,fir", [(1, 9), (2, 0), (3, 9), (4, 5), (5, 9), (6, 9), (7, 9), (8, 9)])
+def test_fifth_order_chain_every_depth(emu, port_oracle, passes, fir):
+    """fused fifth_order x P (+ FIR) tile kernel for P <= 7, per-pass kernels beyond"""
+    bin_e = 6
+    n, ds = 1 << bin_e, 1 << passes
+    buf_len = max(16384, 2 * n * ds)
+    plan = plan_dict(bin_e, buf_len=buf_len, downsample=ds, downsample_passes=passes, boxcar=0,
+                     comp_fir_size=fir, tune_count=1)
+    win = port_oracle.window_coefs("blackman", n)
+    reads, hops = make_reads(port_oracle.lib, plan, 2, SYNTH_BIASED, seed=passes, param=30)
+    reads[1, 100:300] = 255
+    want, _, _ = expected(port_oracle, plan, win, reads, hops)
+    segs = np.array([(0, 0, 2, 0)], dtype=np.int32)
+    tw = twiddles(port_oracle.sine_table(bin_e), bin_e)
+    w16 = (win & 0xFFFF).astype(np.uint16)
+    avg = np.zeros((1, n), dtype=np.int64)
+    fir5 = None
+    if fir == 9 and passes <= 10:
+        fir5 = np.array(list(port_oracle.lib.oracle_cic9(passes).contents)[1:6], dtype=np.int32)
+    emu.emu_small_decim(bin_e, 0, vp(reads), 2, buf_len, ds, passes, 1, vp(fir5), vp(segs), 1, vp(tw), vp(w16),
+                        vp(avg), None, None)
+    assert np.array_equal(avg, want)

@@ -244,3 +244,21 @@ def test_decimating_small_n(scan_mod, port_oracle, bin_e, ds):
     assert np.array_equal(got[0], want[0])
     assert np.array_equal(got[1], want[1])
     assert db_close(got[2], want[2])
+
+
+@pytest.mark.parametrize("passes,fir", [(1, 9), (2, 0), (3, 9), (4, 5), (5, 9), (6, 9), (7, 9), (8, 9), (9, 0)])
+def test_fifth_order_chain_every_depth(scan_mod, port_oracle, passes, fir):
+    """-F path at every decimation depth: fused tile kernel (P <= 7) and per-pass kernels"""
+    bin_e = 7
+    n, ds = 1 << bin_e, 1 << passes
+    buf_len = max(16384, 2 * n * ds)
+    plan = plan_dict(bin_e, buf_len=buf_len, downsample=ds, downsample_passes=passes, boxcar=0,
+                     comp_fir_size=fir, tune_count=2, peak_hold=passes % 2)
+    w = port_oracle.window_coefs("hamming", n)
+    reads, hops = make_reads(port_oracle.lib, plan, 3, SYNTH_BIASED, seed=passes, param=30)
+    reads[1, 100:300] = 255
+    want = expected(port_oracle, plan, w, reads, hops)
+    got = run_gpu(scan_mod, plan, w, reads, hops)
+    assert np.array_equal(got[0], want[0])
+    assert np.array_equal(got[1], want[1])
+    assert db_close(got[2], want[2])
