@@ -201,6 +201,47 @@ def run_reference(args):
 
 # --------------------------------------------------------------------------- GPU arm
 
+def companion(rs, plan_scan, torch, name, freq, crop, window, fir, peak, passes, steps, peak_gbs):
+    """Device-resident throughput of another rtl_power configuration (same method as `value`):
+    the HBM-bound regimes of the path that BASELINE.json's bench workload (ds = 1) never enters."""
+    plan = plan_scan(freq, crop, fir)
+    pd = plan.as_dict()
+    pd["peak_hold"] = peak
+    tc, b, n = pd["tune_count"], pd["buf_len"], 1 << pd["bin_e"]
+    g = rs.GpuScan.from_plan(pd, window_coefs=rs.window_coefs(window, n) if pd["bin_e"] else None)
+    stream = torch.cuda.Stream()
+    g.set_stream(stream.cuda_stream)
+    step_bytes = passes * tc * b
+    n_sets = max(1, -(-(300 << 20) // step_bytes))
+    dev_in = torch.randint(0, 256, (n_sets, passes, tc, b), dtype=torch.uint8, device="cuda")
+    out = torch.zeros(tc * (n + g.db_count + 1), dtype=torch.int64, device="cuda")
+    p_avg = out.data_ptr()
+    p_db = p_avg + tc * n * 8
+    p_smp = p_db + tc * g.db_count * 8
+
+    def step(i):
+        g.submit_device(0, tc, passes, dev_in[i % n_sets].data_ptr(), tc * b, b)
+        g.collect_device(p_avg, p_smp, p_db)
+
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(steps):
+        step(3 + i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    g.close()
+    del dev_in
+    gbs = step_bytes / (ms * 1e-3) / 1e9
+    return {"workload": name, "cli": f"-f {freq}" + (f" -F {fir}" if fir is not None else "") + (" -P" if peak else ""),
+            "plan": {k: pd[k] for k in ("tune_count", "bin_e", "buf_len", "downsample", "downsample_passes")},
+            "value": step_bytes / 2 / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms,
+            "bytes_per_step": step_bytes, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / peak_gbs}
+
+
 def run_gpu(args):
     import numpy as np
     import torch
@@ -296,27 +337,42 @@ def run_gpu(args):
     ms_max = float(t.item())
 
     # ---- end to end through the host-buffer ABI ("e2e") ----
-    host = rs.PinnedBuffer(step_bytes)
-    host.array[:] = np.frombuffer(dev_in[0].cpu().numpy().tobytes(), dtype=np.uint8)
-    e2e_steps = max(3, min(args.steps, 200))
+    # A stream of integration intervals: every interval's bytes start in pinned host memory and
+    # its report (int64 bins, sample counts, dB rows) ends in host memory.  Two handles alternate,
+    # so interval k+1 crosses PCIe while interval k is transformed and collected -- what a
+    # continuously running rtl_power does.  Each step pays its own H2D and D2H.
+    handles = [g, rs.GpuScan.from_plan(pd, window_coefs=window, device=local)]
+    hosts, outs = [], []
+    for k in range(2):
+        hb = rs.PinnedBuffer(step_bytes)
+        hb.array[:] = np.frombuffer(dev_in[k % n_sets].cpu().numpy().tobytes(), dtype=np.uint8)
+        ob = rs.PinnedBuffer(tc * n * 8 + tc * db_count * 8 + tc * 4)
+        hosts.append(hb)
+        outs.append((ob, (ob.view(np.int64, (tc, n)), ob.view(np.int32, (tc,), tc * n * 8 + tc * db_count * 8),
+                          ob.view(np.float64, (tc, db_count), tc * n * 8))))
+    e2e_steps = max(4, min(args.steps, 400))
 
-    def step_host():
-        g.submit_batch(0, tc, PASSES, host.ptr, tc * b, b)
-        avg, smp, db = g.collect_all()
-        return avg, smp, db
+    def run_host(steps):
+        handles[0].submit_batch(0, tc, PASSES, hosts[0].ptr, tc * b, b)
+        res = None
+        for i in range(steps):
+            if i + 1 < steps:
+                handles[(i + 1) & 1].submit_batch(0, tc, PASSES, hosts[(i + 1) & 1].ptr, tc * b, b)
+            res = handles[i & 1].collect_all(out=outs[i & 1][1])
+        return res
 
-    for _ in range(max(args.warmup, 3)):
-        step_host()
+    run_host(max(args.warmup, 4))
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        res = step_host()
+    res = run_host(e2e_steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    assert int(res[1][0]) == 2 * PASSES, "e2e report does not cover one whole interval"
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
+    handles[1].close()
     d2h = tc * n * 8 + tc * db_count * 8
 
     if rank == 0:
@@ -344,10 +400,25 @@ def run_gpu(args):
                          "note": "integer-issue bound, not HBM bound: see DESIGN.md"},
             "e2e": {"value": e2e, "unit": "Msamples/s", "h2d_bytes_per_step": step_bytes,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "api": "rtlsdr_gpu_scan_submit_batch + rtlsdr_gpu_scan_collect_all"},
+                    "api": "rtlsdr_gpu_scan_submit_batch (pinned host input) + rtlsdr_gpu_scan_collect_all "
+                           "(pinned host output), two handles alternating so copies overlap the transform"},
             "gpu_launches": launches,
             "clocks": clocks,
         }
+        if world == 1 and not args.no_companions:
+            try:
+                line["companions"] = [
+                    companion(rs, plan_scan, torch, "narrow_scan_boxcar_ds28_1024bins", "100M:100.1M:100", 0.0,
+                              "rectangle", None, 0, 8192, 10, peak),
+                    companion(rs, plan_scan, torch, "rms_1MHz_bins_10hops", "100M:110M:1M", 0.0,
+                              "rectangle", None, 0, 4096, 10, peak),
+                    companion(rs, plan_scan, torch, "narrow_scan_fifth_order_x4_fir9_1024bins", "100M:100.1M:100", 0.0,
+                              "blackman", 9, 0, 8192, 10, peak),
+                    companion(rs, plan_scan, torch, "large_fft_2^17_blackman-harris_peak_hold", "100M:102.4M:19", 0.0,
+                              "blackman-harris", None, 1, 256, 10, peak),
+                ]
+            except Exception as exc:  # companions are extra evidence, never fail the bench line
+                line["companions"] = [{"error": repr(exc)}]
         if world == 1 and not args.no_cpu:
             ref = CpuReference(1)
             t, smp, kind = ref.step(4000)
@@ -368,6 +439,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-companions", action="store_true", help="skip the other-configuration measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -94,6 +94,12 @@ class PinnedBuffer:
         self.nbytes = nbytes
         self.array = np.ctypeslib.as_array((ctypes.c_uint8 * nbytes).from_address(self.ptr))
 
+    def view(self, dtype, shape, offset=0):
+        """typed numpy view of a slice of the pinned block"""
+        count = int(np.prod(shape))
+        nbytes = count * np.dtype(dtype).itemsize
+        return self.array[offset: offset + nbytes].view(dtype).reshape(shape)
+
     def free(self):
         if self.ptr:
             self.array = None
@@ -181,12 +187,17 @@ class GpuScan:
                                                      db.ctypes.data if want_db else None), "collect")
         return avg, smp.value, db
 
-    def collect_all(self, want_db=True):
-        avg = np.zeros((self.tune_count, self.n), dtype=np.int64)
-        smp = np.zeros(self.tune_count, dtype=np.int32)
-        db = np.zeros((self.tune_count, self.db_count), dtype=np.float64) if want_db else None
+    def collect_all(self, want_db=True, out=None):
+        """out: optional (avg int64 [tc, N], samples int32 [tc], db float64 [tc, db_count]) arrays to
+        fill, e.g. views of pinned memory (PinnedBuffer) so the device-to-host copies are asynchronous."""
+        if out is not None:
+            avg, smp, db = out
+        else:
+            avg = np.zeros((self.tune_count, self.n), dtype=np.int64)
+            smp = np.zeros(self.tune_count, dtype=np.int32)
+            db = np.zeros((self.tune_count, self.db_count), dtype=np.float64) if want_db else None
         self._check(self.lib.rtlsdr_gpu_scan_collect_all(self.h, avg.ctypes.data, smp.ctypes.data,
-                                                         db.ctypes.data if want_db else None), "collect_all")
+                                                         db.ctypes.data if db is not None else None), "collect_all")
         return avg, smp, db
 
     def collect_device(self, dev_avg=None, dev_samples=None, dev_db=None):
