@@ -76,6 +76,7 @@ struct rtlsdr_gpu_scan {
 	long long *d_avg = nullptr;     /* [tune_count * N] bins, then [tune_count] sample counters */
 	long long *d_smp64 = nullptr;   /* = d_avg + tune_count * N */
 	int2 *d_tw = nullptr;
+	int2 *d_twb = nullptr;          /* large path: round-B twiddles re-ordered [se][plow][ilow] */
 	uint16_t *d_win = nullptr;
 	double *d_db = nullptr;
 	int *d_samples = nullptr;
@@ -781,6 +782,7 @@ void free_all(rtlsdr_gpu_scan *h)
 		cudaStreamSynchronize(h->stream);
 	cudaFree(h->d_avg);
 	cudaFree(h->d_tw);
+	cudaFree(h->d_twb);
 	cudaFree(h->d_win);
 	cudaFree(h->d_db);
 	cudaFree(h->d_samples);
@@ -1068,6 +1070,23 @@ int rtlsdr_gpu_scan_init(const rtlsdr_gpu_scan_cfg_t *cfg, rtlsdr_gpu_scan_t **o
 			}
 			if (cudaMemcpy(h->d_tw, h->tw_host.data(), (size_t)half * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess ||
 			    cudaMemcpy(h->d_win, win.data(), (size_t)N * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess)
+				break;
+		}
+
+		if (h->path == PATH_LARGE) {
+			/* twb[se][plow][ilow] = tw[((ilow << 8) | plow) << (L-9-se)], se = 4 .. min(8, L-8)-1 */
+			const int L = cfg->bin_e, lb = std::min(8, L - 8);
+			std::vector<int2> twb((size_t)256 * 240, make_int2(0, 0));
+			for (int se = 4; se < lb; se++)
+				for (int plow = 0; plow < 256; plow++)
+					for (int ilow = 0; ilow < (1 << se); ilow++)
+						twb[(size_t)256 * ((1 << se) - 16) + ((size_t)plow << se) + ilow] =
+							h->tw_host[((size_t)((ilow << 8) | plow)) << (L - 9 - se)];
+			if (cudaMalloc(&h->d_twb, twb.size() * sizeof(int2)) != cudaSuccess) {
+				rc = RTLSDR_GPU_ERR_NOMEM;
+				break;
+			}
+			if (cudaMemcpy(h->d_twb, twb.data(), twb.size() * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess)
 				break;
 		}
 

@@ -38,8 +38,10 @@ struct LargeParams {
 	long long *samples;         /* [tune_count] */
 	int samples_per_read;
 	const int2 *tw;             /* [N/2] */
+	const int2 *twb;            /* round-B re-ordered copy, see TwLargeB */
 	const uint16_t *win;        /* [N] */
 	int L;
+	int n_entries;              /* entries in this chunk */
 	PassTw tw0;
 };
 
@@ -63,16 +65,23 @@ dc_sums_u8_kernel(const SCAN_GRID_CONSTANT DcSumU8Params prm)
 	const int rel = blockIdx.y;
 	const uint8_t *src = prm.base + prm.read_off[prm.entry_base + rel];
 	unsigned sI = 0, sQ = 0; /* <= 2^21 bytes of 255 per component: fits */
-	for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 16; i < prm.buf_len; i += gridDim.x * blockDim.x * 16) {
-		const uint4 q = __ldg((const uint4 *)(src + i));
-		sI = __dp4a(q.x, 0x00010001u, sI);
-		sQ = __dp4a(q.x, 0x01000100u, sQ);
-		sI = __dp4a(q.y, 0x00010001u, sI);
-		sQ = __dp4a(q.y, 0x01000100u, sQ);
-		sI = __dp4a(q.z, 0x00010001u, sI);
-		sQ = __dp4a(q.z, 0x01000100u, sQ);
-		sI = __dp4a(q.w, 0x00010001u, sI);
-		sQ = __dp4a(q.w, 0x01000100u, sQ);
+	const int stride = gridDim.x * blockDim.x * 16;
+	for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 16; i < prm.buf_len; i += 4 * stride) {
+		uint4 q[4];
+#pragma unroll
+		for (int j = 0; j < 4; ++j)
+			q[j] = (i + j * stride < prm.buf_len) ? __ldg((const uint4 *)(src + i + j * stride)) : uint4{ 0, 0, 0, 0 };
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			sI = __dp4a(q[j].x, 0x00010001u, sI);
+			sQ = __dp4a(q[j].x, 0x01000100u, sQ);
+			sI = __dp4a(q[j].y, 0x00010001u, sI);
+			sQ = __dp4a(q[j].y, 0x01000100u, sQ);
+			sI = __dp4a(q[j].z, 0x00010001u, sI);
+			sQ = __dp4a(q[j].z, 0x01000100u, sQ);
+			sI = __dp4a(q[j].w, 0x00010001u, sI);
+			sQ = __dp4a(q[j].w, 0x01000100u, sQ);
+		}
 	}
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) {
@@ -136,50 +145,50 @@ large_round_a_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
 			dck[t] = dc_average(s, (int)(2 * N) - t);
 	}
 
-	/* gather: thread t owns row i = t, 16 consecutive input samples */
+	__syncthreads();
+	const int kI = dck[0], kQ = dck[1];
+
+	/* gather: thread t owns row i = t = 16 consecutive input samples and their 16 window
+	 * coefficients (two 16-byte loads each); convert, remove DC, window, and park the c16
+	 * results column-major so that the engine finds column c, row i at stage[c*256 + i] */
 	{
 		const long long n0 = ((long long)t << (L - 8)) + 16 * tile;
+		const uint4 wa = __ldg((const uint4 *)(prm.win + n0));
+		const uint4 wb = __ldg((const uint4 *)(prm.win + n0 + 8));
+		const unsigned ww[8] = { wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w };
 		if constexpr (!IN16) {
 			const uint4 a = __ldg((const uint4 *)(src + 2 * n0));
 			const uint4 b = __ldg((const uint4 *)(src + 2 * n0 + 16));
 			const unsigned w[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
 #pragma unroll
-			for (int c = 0; c < 16; ++c)
-				stage[xch_idx(c * 256 + t)] = (w[c >> 1] >> (16 * (c & 1))) & 0xFFFFu;
+			for (int c = 0; c < 16; ++c) {
+				const unsigned raw = (w[c >> 1] >> (16 * (c & 1))) & 0xFFFFu;
+				const int wv = (int)((ww[c >> 1] >> (16 * (c & 1))) & 0xFFFFu);
+				stage[xch_idx(c * 256 + t)] = c16_pack(((int)(raw & 0xFFu) - kI) * wv, ((int)(raw >> 8) - kQ) * wv);
+			}
 		} else {
 #pragma unroll
 			for (int k = 0; k < 4; ++k) {
 				const uint4 a = __ldg((const uint4 *)(src + 4 * n0 + 16 * k));
-				stage[xch_idx((4 * k + 0) * 256 + t)] = a.x;
-				stage[xch_idx((4 * k + 1) * 256 + t)] = a.y;
-				stage[xch_idx((4 * k + 2) * 256 + t)] = a.z;
-				stage[xch_idx((4 * k + 3) * 256 + t)] = a.w;
+				const unsigned raw[4] = { a.x, a.y, a.z, a.w };
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					const int c = 4 * k + j;
+					const int wv = (int)((ww[c >> 1] >> (16 * (c & 1))) & 0xFFFFu);
+					stage[xch_idx(c * 256 + t)] = c16_pack((c16_re(raw[j]) - kI) * wv, (c16_im(raw[j]) - kQ) * wv);
+				}
 			}
 		}
 	}
 	__syncthreads();
-	const int kI = dck[0], kQ = dck[1];
 
-	/* convert + window; position 16t + r is column c = t >> 4, row bitrev8(q) */
+	/* position 16t + r is column c = t >> 4, row bitrev8(q) */
 	X2 x[kPts];
 	const int c = t >> 4;
-	const int n_low = 16 * tile + c;
 #pragma unroll
 	for (int r = 0; r < kPts; ++r) {
 		const int i = (brev4(r) << 4) | brev_bits((unsigned)(t & 15), 4);
-		const unsigned raw = stage[xch_idx(c * 256 + i)];
-		const long long n = ((long long)i << (L - 8)) | n_low;
-		const int wv = __ldg(prm.win + n);
-		int re, im;
-		if constexpr (!IN16) {
-			re = ((int)(raw & 0xFFu) - kI) * wv;
-			im = ((int)(raw >> 8) - kQ) * wv;
-		} else {
-			re = (c16_re(raw) - kI) * wv;
-			im = (c16_im(raw) - kQ) * wv;
-		}
-		x[r].re = re << 16;
-		x[r].im = im << 16;
+		x[r] = x_unpack(stage[xch_idx(c * 256 + i)]);
 	}
 
 	TwLargeA tw;
@@ -200,16 +209,29 @@ large_round_a_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
 
 /* ---- round B ----------------------------------------------------------- */
 
+/*
+ * Round-B twiddles.  Stage 8+se pairs positions whose low 8+se bits m = (ilow << 8) | plow
+ * select tw[m << (L-9-se)].  For se >= 4 the lanes of a warp differ in ilow, i.e. their
+ * entries are 2^(L-1-se) apart in tw[]: one 32-byte sector per lane.  The host therefore
+ * also provides the same values re-ordered as twb[se][plow][ilow] (ilow fastest), so that a
+ * warp reads one or two contiguous 128-byte runs.
+ */
+SCAN_DEV constexpr long long twb_offset(int se) { return 256ll * ((1 << se) - 16); } /* se >= 4 */
+
 template <int LB>
 struct TwLargeB {
 	static constexpr bool kTrivial = false;
 	const int2 *tw;
+	const int2 *twb;
 	int plow0, L;
 	template <int K>
 	SCAN_DEV int2 get(int se, int pa) const
 	{
 		const int col = pa >> LB, i = pa & ((1 << LB) - 1);
-		const long long m = ((long long)(i & ((1 << se) - 1)) << 8) | (plow0 + col);
+		const int ilow = i & ((1 << se) - 1);
+		if (K >= 1)
+			return __ldg(twb + twb_offset(se) + ((long long)(plow0 + col) << se) + ilow);
+		const long long m = ((long long)ilow << 8) | (plow0 + col);
 		return __ldg(tw + (m << (L - 9 - se)));
 	}
 };
@@ -223,6 +245,11 @@ SCAN_DEV void accumulate_bin(long long *dst, c16 x, bool peak)
 	else
 		atomicAdd((unsigned long long *)dst, (unsigned long long)pw);
 }
+
+/* Tile transposes of round B: columns are 2^LB words apart, so on top of the engine's
+ * p>>4 padding the column index is spread over the banks with 2 * (p >> 8). */
+SCAN_DEV int tile_idx(int p) { return p + (p >> 4) + 2 * (p >> 8); }
+constexpr int kLargeSmemB = (kWS + kWS / 16 + 2 * (kWS / 256) + 16) * 4;
 
 template <int LB, bool LAST, bool PEAK>
 __global__ void __launch_bounds__(kThreads, 2)
@@ -242,16 +269,17 @@ large_round_b_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
 	for (int k = 0; k < kPts; ++k) {
 		const int eidx = t + kThreads * k;
 		const int col = eidx % ncols, i = eidx / ncols;
-		stage[xch_idx((col << LB) | i)] = data[((long long)i << 8) + col];
+		stage[tile_idx((col << LB) | i)] = data[((long long)i << 8) + col];
 	}
 	__syncthreads();
 	X2 x[kPts];
 #pragma unroll
 	for (int r = 0; r < kPts; ++r)
-		x[r] = x_unpack(stage[xch_idx(pos<0>(t, r))]);
+		x[r] = x_unpack(stage[tile_idx(pos<0>(t, r))]);
 
 	TwLargeB<LB> tw;
 	tw.tw = prm.tw;
+	tw.twb = prm.twb;
 	tw.plow0 = plow0;
 	tw.L = L;
 	engine_fft<LB>(x, stage, t, tw);
@@ -259,7 +287,7 @@ large_round_b_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
 	__syncthreads();
 #pragma unroll
 	for (int r = 0; r < kPts; ++r)
-		stage[xch_idx(last_pos<LB>(t, r))] = x_pack(x[r]);
+		stage[tile_idx(last_pos<LB>(t, r))] = x_pack(x[r]);
 	__syncthreads();
 	long long *out = nullptr;
 	if constexpr (LAST)
@@ -268,7 +296,7 @@ large_round_b_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
 	for (int k = 0; k < kPts; ++k) {
 		const int eidx = t + kThreads * k;
 		const int col = eidx % ncols, i = eidx / ncols;
-		const c16 x = stage[xch_idx((col << LB) | i)];
+		const c16 x = stage[tile_idx((col << LB) | i)];
 		if constexpr (LAST)
 			accumulate_bin(out + ((long long)i << 8) + col, x, PEAK);
 		else
@@ -278,34 +306,84 @@ large_round_b_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
 
 /* ---- round C ----------------------------------------------------------- */
 
+constexpr int kRoundCReads = 16; /* reads one CTA of round C walks through */
+
 template <int LC, bool PEAK>
 __global__ void __launch_bounds__(kThreads)
 large_round_c_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
 {
 	constexpr int R = 1 << LC;
-	const int L = prm.L, rel = blockIdx.y;
+	constexpr bool kHoist = LC <= 3; /* twiddles depend on the position only: keep them in registers */
+	const int L = prm.L;
 	const int plow = blockIdx.x * kThreads + threadIdx.x; /* 0 .. 65535 */
 	const long long N = 1ll << L;
-	const c16 *data = prm.scratch + (long long)rel * N + plow;
-	c16 v[R];
+	int2 wreg[kHoist ? R - 1 : 1];
+	if constexpr (kHoist) {
+#pragma unroll
+		for (int se = 0; se < LC; ++se)
+#pragma unroll
+			for (int g = 0; g < (1 << se); ++g) {
+				const long long m = ((long long)g << 16) | plow;
+				wreg[(1 << se) - 1 + g] = __ldg(prm.tw + (m << (L - 17 - se)));
+			}
+	}
+	unsigned long long acc[R];
 #pragma unroll
 	for (int r = 0; r < R; ++r)
-		v[r] = data[(long long)r << 16];
+		acc[r] = 0ull;
+	int cur_hop = -1;
+	const int rel0 = blockIdx.y * kRoundCReads;
+	const int rel1 = (rel0 + kRoundCReads < prm.n_entries) ? rel0 + kRoundCReads : prm.n_entries;
+	for (int rel = rel0; rel <= rel1; ++rel) {
+		const int hop = (rel < rel1) ? prm.hop_of[prm.entry_base + rel] : -1;
+		if (hop != cur_hop) {
+			if (cur_hop >= 0) {
+				long long *out = prm.avg + ((long long)cur_hop << L) + plow;
 #pragma unroll
-	for (int se = 0; se < LC; ++se) {
+				for (int r = 0; r < R; ++r) {
+					if (PEAK)
+						atomicMax(out + ((long long)r << 16), (long long)acc[r]);
+					else
+						atomicAdd((unsigned long long *)(out + ((long long)r << 16)), acc[r]);
+					acc[r] = 0ull;
+				}
+			}
+			cur_hop = hop;
+		}
+		if (rel == rel1)
+			break;
+		const c16 *data = prm.scratch + (long long)rel * N + plow;
+		c16 v[R];
 #pragma unroll
-		for (int r = 0; r < R; ++r) {
-			if ((r & (1 << se)) == 0) {
-				const long long m = ((long long)(r & ((1 << se) - 1)) << 16) | plow;
-				const int2 w = __ldg(prm.tw + (m << (L - 17 - se)));
-				butterfly(v[r], v[r | (1 << se)], w.x, w.y);
+		for (int r = 0; r < R; ++r)
+			v[r] = data[(long long)r << 16];
+#pragma unroll
+		for (int se = 0; se < LC; ++se) {
+#pragma unroll
+			for (int r = 0; r < R; ++r) {
+				if ((r & (1 << se)) == 0) {
+					const int g = r & ((1 << se) - 1);
+					int2 w;
+					if constexpr (kHoist) {
+						w = wreg[(1 << se) - 1 + g];
+					} else {
+						const long long m = ((long long)g << 16) | plow;
+						w = __ldg(prm.tw + (m << (L - 17 - se)));
+					}
+					butterfly(v[r], v[r | (1 << se)], w.x, w.y);
+				}
 			}
 		}
-	}
-	long long *out = prm.avg + ((long long)prm.hop_of[prm.entry_base + rel] << L) + plow;
 #pragma unroll
-	for (int r = 0; r < R; ++r)
-		accumulate_bin(out + ((long long)r << 16), v[r], PEAK);
+		for (int r = 0; r < R; ++r) {
+			const int re = c16_re(v[r]), im = c16_im(v[r]);
+			const unsigned pw = (unsigned)(re * re) + (unsigned)(im * im);
+			if (PEAK)
+				acc[r] = acc[r] > pw ? acc[r] : (unsigned long long)pw;
+			else
+				acc[r] += pw;
+		}
+	}
 }
 
 } // namespace rscan

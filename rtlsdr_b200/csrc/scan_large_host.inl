@@ -5,7 +5,7 @@ namespace {
 template <int LB, bool LAST>
 int launch_round_b_t(rtlsdr_gpu_scan *h, const LargeParams &p, dim3 grid)
 {
-	const int smem = kXchWords * 4;
+	const int smem = kLargeSmemB;
 	if (h->cfg.peak_hold) {
 		auto k = large_round_b_kernel<LB, LAST, true>;
 		CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -86,8 +86,10 @@ int large_process(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_of
 		p.samples = h->d_smp64;
 		p.samples_per_read = h->samples_per_read;
 		p.tw = h->d_tw;
+		p.twb = h->d_twb;
 		p.win = h->d_win;
 		p.L = L;
+		p.n_entries = cnt;
 		p.tw0 = h->tw0;
 
 		const int smem_a = kLargeSmemA;
@@ -131,7 +133,7 @@ int large_process(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_of
 		if ((rc = launch_round_b(h, p, grid_tiles, lb, 8 + lb == L)))
 			return rc;
 		if (8 + lb < L) {
-			dim3 g(65536 / kThreads, (unsigned)cnt);
+			dim3 g(65536 / kThreads, (unsigned)((cnt + kRoundCReads - 1) / kRoundCReads));
 			if ((rc = launch_round_c(h, p, g, L - 16)))
 				return rc;
 		}

@@ -22,8 +22,19 @@ void emu_large(int L, int peak, int in16, const uint8_t *reads, int n_reads, con
 	p.samples = smp.data();
 	p.samples_per_read = 1;
 	p.tw = (const int2 *)tw;
+	std::vector<int2> twb((size_t)256 * 240, int2{ 0, 0 });
+	{
+		const int lbb = L - 8 < 8 ? L - 8 : 8;
+		for (int se = 4; se < lbb; se++)
+			for (int plow = 0; plow < 256; plow++)
+				for (int ilow = 0; ilow < (1 << se); ilow++)
+					twb[(size_t)256 * ((1 << se) - 16) + ((size_t)plow << se) + ilow] =
+						p.tw[((size_t)((ilow << 8) | plow)) << (L - 9 - se)];
+	}
+	p.twb = twb.data();
 	p.win = win;
 	p.L = L;
+	p.n_entries = n_reads;
 	fill_tw0(p.tw0, p.tw, L);
 	dim3 tiles((unsigned)(N / kWS), n_reads);
 	if (!in16) {
@@ -44,9 +55,9 @@ void emu_large(int L, int peak, int in16, const uint8_t *reads, int n_reads, con
 #define RB(LBV, LASTV)                                                                                  \
 	do {                                                                                            \
 		if (peak)                                                                               \
-			cuda_emu::launch(tiles, dim3(kThreads), kXchWords * 4, [&]() { large_round_b_kernel<LBV, LASTV, true>(p); }); \
+			cuda_emu::launch(tiles, dim3(kThreads), kLargeSmemB, [&]() { large_round_b_kernel<LBV, LASTV, true>(p); }); \
 		else                                                                                    \
-			cuda_emu::launch(tiles, dim3(kThreads), kXchWords * 4, [&]() { large_round_b_kernel<LBV, LASTV, false>(p); }); \
+			cuda_emu::launch(tiles, dim3(kThreads), kLargeSmemB, [&]() { large_round_b_kernel<LBV, LASTV, false>(p); }); \
 	} while (0)
 	if (lb == 5) RB(5, true);
 	else if (lb == 6) RB(6, true);
@@ -57,7 +68,7 @@ void emu_large(int L, int peak, int in16, const uint8_t *reads, int n_reads, con
 	else RB(8, false);
 #undef RB
 	if (8 + lb < L) {
-		dim3 g(65536 / kThreads, n_reads);
+		dim3 g(65536 / kThreads, (n_reads + kRoundCReads - 1) / kRoundCReads);
 #define RC(LCV)                                                                                         \
 	do {                                                                                            \
 		if (peak)                                                                               \
