@@ -19,7 +19,9 @@
  * reference's:
  *   RTLSDR_SYNTH_MODE   xorshift | counter | const | biased | tone | replay
  *   RTLSDR_SYNTH_SEED   integer      RTLSDR_SYNTH_PARAM  integer
- *   RTLSDR_SYNTH_REPLAY path of a raw interleaved u8 IQ file (rtl_sdr format)
+ *   RTLSDR_SYNTH_REPLAY path of a recording: raw rtl_sdr output, rtl_sdr WAV, or a captured
+ *                       rtl_tcp stream (host/replay_file.c)
+ *   RTL_POWER_ASYNC     1 = fetch every hop visit through rtlsdr_read_async + callback
  *   RTL_POWER_PASSES    report after this many sweeps instead of by wall clock
  *   RTL_POWER_TIMESTAMP fixed "date, time" prefix (byte-reproducible output)
  *   RTLSDR_GPU_DEVICE   CUDA device ordinal
@@ -33,6 +35,7 @@
 #include <time.h>
 #include <unistd.h>
 
+#include "replay_file.h"
 #include "rtl_power_plan.h"
 #include "rtlsdr_gpu_scan.h"
 #include "synth_source.h"
@@ -86,30 +89,6 @@ static int synth_mode_from_env(void)
 	return SYNTH_XORSHIFT;
 }
 
-static uint8_t *load_replay(const char *path, size_t read_len, size_t *n_reads)
-{
-	FILE *f = fopen(path, "rb");
-	uint8_t *buf;
-	long size;
-	if (!f)
-		return NULL;
-	fseek(f, 0, SEEK_END);
-	size = ftell(f);
-	fseek(f, 0, SEEK_SET);
-	*n_reads = (size_t)size / read_len;
-	if (*n_reads == 0) {
-		fclose(f);
-		return NULL;
-	}
-	buf = (uint8_t *)malloc(*n_reads * read_len);
-	if (buf && fread(buf, read_len, *n_reads, f) != *n_reads) {
-		free(buf);
-		buf = NULL;
-	}
-	fclose(f);
-	return buf;
-}
-
 /* retune(): rtl_power.c:542-552 */
 static void settle_on(rtlsdr_dev_t *dev, int freq)
 {
@@ -123,6 +102,27 @@ static void settle_on(rtlsdr_dev_t *dev, int freq)
 		fprintf(stderr, "Error: bad retune.\n");
 }
 
+/* async variant of one hop visit: the callback contract of rtlsdr_read_async
+ * (include/rtl-sdr.h:472-500): the library owns the buffer and re-arms it as soon as
+ * the callback returns, so the callback hands the bytes to the GPU path (which copies
+ * them) and cancels the stream after the one buffer rtl_power wants per visit */
+struct visit_ctx {
+	rtlsdr_dev_t *dev;
+	rtlsdr_gpu_scan_t *gpu;
+	int hop, rc, taken;
+	uint32_t want;
+};
+
+static void on_samples(unsigned char *buf, uint32_t len, void *ctx)
+{
+	struct visit_ctx *v = (struct visit_ctx *)ctx;
+	if (v->taken)
+		return;
+	v->taken = 1;
+	v->rc = (len == v->want) ? rtlsdr_gpu_scan_submit(v->gpu, v->hop, buf, len) : RTLSDR_GPU_ERR_LENGTH;
+	rtlsdr_cancel_async(v->dev);
+}
+
 /* one sweep over all hops: the control flow of scanner(), rtl_power.c:642-659 */
 static int sweep(rtlsdr_dev_t *dev, rtlsdr_gpu_scan_t *gpu, const rp_plan_t *plan, uint8_t *buf8)
 {
@@ -132,6 +132,15 @@ static int sweep(rtlsdr_dev_t *dev, rtlsdr_gpu_scan_t *gpu, const rp_plan_t *pla
 			return 0;
 		if ((int)rtlsdr_get_center_freq(dev) != plan->freq[hop])
 			settle_on(dev, plan->freq[hop]);
+		if (getenv("RTL_POWER_ASYNC")) {
+			struct visit_ctx v = { dev, gpu, hop, 0, 0, (uint32_t)plan->buf_len };
+			rtlsdr_read_async(dev, on_samples, &v, 4, (uint32_t)plan->buf_len);
+			if (v.rc) {
+				fprintf(stderr, "rtlsdr_gpu_scan_submit: %s\n", rtlsdr_gpu_scan_strerror(v.rc));
+				return v.rc;
+			}
+			continue;
+		}
 		got = 0;
 		rtlsdr_read_sync(dev, buf8, plan->buf_len, &got);
 		if (got != plan->buf_len)
@@ -219,7 +228,8 @@ int main(int argc, char **argv)
 	if (synth_mode_from_env() == SYNTH_REPLAY) {
 		size_t n_reads = 0;
 		const char *path = getenv("RTLSDR_SYNTH_REPLAY");
-		replay = path ? load_replay(path, (size_t)plan->buf_len, &n_reads) : NULL;
+		replay_info_t rinfo;
+		replay = path ? replay_load(path, (size_t)plan->buf_len, &n_reads, &rinfo) : NULL;
 		if (!replay) {
 			fprintf(stderr, "Failed to load replay file.\n");
 			return 1;

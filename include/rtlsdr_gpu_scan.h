@@ -93,8 +93,12 @@ typedef struct rtlsdr_gpu_scan_cfg {
 	const int32_t *window_coefs;
 	const int16_t *sinewave;
 	uint32_t ring_bytes;        /* pinned staging ring size per half, 0 = default (32 MiB) */
-	uint32_t flags;             /* reserved, 0 */
+	uint32_t flags;             /* RTLSDR_GPU_FLAG_* */
 } rtlsdr_gpu_scan_cfg_t;
+
+/* cfg.flags: also count, per hop, the byte statistics librtlsdr's soft AGC looks at
+ * (src/librtlsdr.c:3288-3306); read them with rtlsdr_gpu_scan_level_stats() */
+#define RTLSDR_GPU_FLAG_LEVEL_STATS 1u
 
 /* ---- lifecycle --------------------------------------------------------- */
 
@@ -159,6 +163,15 @@ RTLSDR_GPU_API int rtlsdr_gpu_scan_collect_all(rtlsdr_gpu_scan_t *h, int64_t *av
 /* Same, into device buffers (for the per-interval NCCL gather); asynchronous
  * on the handle's stream, no host synchronisation. */
 RTLSDR_GPU_API int rtlsdr_gpu_scan_collect_device(rtlsdr_gpu_scan_t *h, void *dev_avg, void *dev_samples, void *dev_db);
+
+/*
+ * Soft-AGC statistics of hop `hop` since its last collect (needs RTLSDR_GPU_FLAG_LEVEL_STATS):
+ * overload = bytes equal to 0 or 255 (0 dBFS), high_level = bytes < 64 or > 191 (-6 dBFS), as
+ * softagc() counts them per buffer (src/librtlsdr.c:3299-3306), bytes = bytes looked at.
+ * Blocks until submitted work is done; collect() of the hop resets the counters.
+ */
+RTLSDR_GPU_API int rtlsdr_gpu_scan_level_stats(rtlsdr_gpu_scan_t *h, int hop, uint64_t *overload,
+		uint64_t *high_level, uint64_t *bytes);
 
 /* ---- helpers ----------------------------------------------------------- */
 

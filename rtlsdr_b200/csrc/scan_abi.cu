@@ -75,6 +75,8 @@ struct rtlsdr_gpu_scan {
 
 	long long *d_avg = nullptr;     /* [tune_count * N] bins, then [tune_count] sample counters */
 	long long *d_smp64 = nullptr;   /* = d_avg + tune_count * N */
+	unsigned long long *d_level = nullptr; /* [tune_count][2] soft-AGC byte counts (optional) */
+	std::vector<uint64_t> level_bytes;
 	int2 *d_tw = nullptr;
 	int2 *d_twb = nullptr;          /* large path: round-B twiddles re-ordered [se][plow][ilow] */
 	uint16_t *d_win = nullptr;
@@ -572,6 +574,20 @@ int launch_batch(rtlsdr_gpu_scan *h, const uint8_t *base, const uint8_t *d_desc,
 	const int *d_hops = (const int *)(d_desc + lay.off_hops);
 	int rc = 0;
 
+	if (h->d_level) {
+		LevelParams lp;
+		lp.base = base;
+		lp.read_off = d_offs;
+		lp.hop_of = d_hops;
+		lp.n_reads = n_reads;
+		lp.buf_len = h->cfg.buf_len;
+		lp.level = h->d_level;
+		const int blocks = std::max(1, std::min((n_reads + 7) / 8, h->num_sms * 8));
+		level_stats_kernel<<<blocks, 256, 0, h->stream>>>(lp);
+		if ((rc = check_launch(h, "level_stats_kernel")))
+			return rc;
+	}
+
 	if (h->path == PATH_RMS) {
 		RmsParams p;
 		p.base = base;
@@ -724,8 +740,11 @@ int process_batch(rtlsdr_gpu_scan *h, const uint8_t *base, const std::vector<lon
 	slot->used = true;
 	if (rc)
 		return rc;
-	for (int i = 0; i < n; i++)
+	for (int i = 0; i < n; i++) {
 		h->samples[hops[i]] += h->samples_per_read;
+		if (h->d_level)
+			h->level_bytes[hops[i]] += (uint64_t)h->cfg.buf_len;
+	}
 	return 0;
 }
 
@@ -782,6 +801,7 @@ void free_all(rtlsdr_gpu_scan *h)
 		cudaStreamSynchronize(h->stream);
 	cudaFree(h->d_avg);
 	cudaFree(h->d_tw);
+	cudaFree(h->d_level);
 	cudaFree(h->d_twb);
 	cudaFree(h->d_win);
 	cudaFree(h->d_db);
@@ -1034,6 +1054,16 @@ int rtlsdr_gpu_scan_init(const rtlsdr_gpu_scan_cfg_t *cfg, rtlsdr_gpu_scan_t **o
 		h->d_smp64 = h->d_avg + (size_t)cfg->tune_count * N;
 		if (cudaMemsetAsync(h->d_avg, 0, avg_bytes, h->stream) != cudaSuccess)
 			break;
+		if (cfg->flags & RTLSDR_GPU_FLAG_LEVEL_STATS) {
+			const size_t lb = (size_t)cfg->tune_count * 2 * sizeof(unsigned long long);
+			if (cudaMalloc(&h->d_level, lb) != cudaSuccess) {
+				rc = RTLSDR_GPU_ERR_NOMEM;
+				break;
+			}
+			if (cudaMemsetAsync(h->d_level, 0, lb, h->stream) != cudaSuccess)
+				break;
+			h->level_bytes.assign(cfg->tune_count, 0);
+		}
 
 		if (cfg->bin_e > 0) {
 			/* twiddles: wr = Sinewave[j+N/4] >> 1, wi = (-Sinewave[j]) >> 1 (rtl_power.c:305-308) */
@@ -1237,8 +1267,11 @@ static int submit_regular(rtlsdr_gpu_scan_t *h, int hop_first, int hop_count, in
 			  &hit->segs);
 	if (rc)
 		return rc;
-	for (int k = 0; k < hop_count; k++)
+	for (int k = 0; k < hop_count; k++) {
 		h->samples[hop_first + k] += h->samples_per_read * passes;
+		if (h->d_level)
+			h->level_bytes[hop_first + k] += (uint64_t)h->cfg.buf_len * (uint64_t)passes;
+	}
 	return 0;
 }
 
@@ -1356,11 +1389,15 @@ static int collect_range(rtlsdr_gpu_scan_t *h, int hop0, int nhops, int64_t *avg
 		CU(cudaMemsetAsync(h->d_avg + (size_t)hop0 * N, 0, (size_t)nhops * N * sizeof(long long), h->stream));
 		CU(cudaMemsetAsync(h->d_smp64 + hop0, 0, (size_t)nhops * sizeof(long long), h->stream));
 	}
+	if (h->d_level)
+		CU(cudaMemsetAsync(h->d_level + 2 * (size_t)hop0, 0, (size_t)nhops * 2 * sizeof(unsigned long long), h->stream));
 	CU(cudaStreamSynchronize(h->stream));
 	for (int i = 0; i < nhops; i++) {
 		if (samples)
 			samples[i] = h->samples[hop0 + i];
 		h->samples[hop0 + i] = 0;
+		if (h->d_level)
+			h->level_bytes[hop0 + i] = 0;
 	}
 	return 0;
 }
@@ -1395,7 +1432,35 @@ int rtlsdr_gpu_scan_collect_device(rtlsdr_gpu_scan_t *h, void *dev_avg, void *de
 	if ((rc = run_epilogue(h, 0, (int)tc, (double *)dev_db, (long long *)dev_avg, (int *)dev_samples)))
 		return rc;
 	CU(cudaMemsetAsync(h->d_avg, 0, (tc * N + tc) * sizeof(long long), h->stream));
+	if (h->d_level) {
+		CU(cudaMemsetAsync(h->d_level, 0, tc * 2 * sizeof(unsigned long long), h->stream));
+		std::fill(h->level_bytes.begin(), h->level_bytes.end(), 0);
+	}
 	std::fill(h->samples.begin(), h->samples.end(), 0);
+	return 0;
+}
+
+int rtlsdr_gpu_scan_level_stats(rtlsdr_gpu_scan_t *h, int hop, uint64_t *overload, uint64_t *high_level, uint64_t *bytes)
+{
+	if (!h)
+		return RTLSDR_GPU_ERR_NULL;
+	if (hop < 0 || hop >= h->cfg.tune_count)
+		return RTLSDR_GPU_ERR_HOP;
+	if (!h->d_level)
+		return RTLSDR_GPU_ERR_CONFIG;
+	CU(cudaSetDevice(h->cfg.device));
+	int rc = flush_ring(h);
+	if (rc)
+		return rc;
+	unsigned long long v[2] = { 0, 0 };
+	CU(cudaMemcpyAsync(v, h->d_level + 2 * (size_t)hop, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	if (overload)
+		*overload = v[0];
+	if (high_level)
+		*high_level = v[1];
+	if (bytes)
+		*bytes = h->level_bytes[hop];
 	return 0;
 }
 

@@ -1154,6 +1154,49 @@ rms_kernel(const SCAN_GRID_CONSTANT RmsParams prm)
 }
 
 /* ======================================================================== *
+ *  Soft-AGC byte statistics (src/librtlsdr.c:3288-3306), optional            *
+ * ======================================================================== */
+
+struct LevelParams {
+	const uint8_t *base;
+	const long long *read_off;
+	const int *hop_of;
+	int n_reads;
+	int buf_len;
+	unsigned long long *level; /* [tune_count][2]: overload, high level */
+};
+
+/* one warp per read; four bytes per compare with the SIMD-in-a-word intrinsics */
+__global__ void __launch_bounds__(256)
+level_stats_kernel(const SCAN_GRID_CONSTANT LevelParams prm)
+{
+	const int lane = threadIdx.x & 31;
+	const int warps = (gridDim.x * blockDim.x) >> 5;
+	for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < prm.n_reads; e += warps) {
+		const uint8_t *src = prm.base + prm.read_off[e];
+		unsigned over = 0, high = 0;
+		for (int i = lane * 16; i < prm.buf_len; i += 32 * 16) {
+			const uint4 q = __ldg((const uint4 *)(src + i));
+			const unsigned w[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				over += __popc(__vcmpeq4(w[j], 0u) | __vcmpeq4(w[j], 0xFFFFFFFFu)) >> 3;   /* u == 0 || u == 255 */
+				high += __popc(__vcmpltu4(w[j], 0x40404040u) | __vcmpgtu4(w[j], 0xBFBFBFBFu)) >> 3; /* u < 64 || u > 191 */
+			}
+		}
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			over += __shfl_xor_sync(0xffffffffu, over, o);
+			high += __shfl_xor_sync(0xffffffffu, high, o);
+		}
+		if (lane == 0) {
+			atomicAdd(prm.level + 2 * prm.hop_of[e], (unsigned long long)over);
+			atomicAdd(prm.level + 2 * prm.hop_of[e] + 1, (unsigned long long)high);
+		}
+	}
+}
+
+/* ======================================================================== *
  *  Report epilogue: DC nuke, half swap, crop, dB (rtl_power.c:722-760)      *
  * ======================================================================== */
 

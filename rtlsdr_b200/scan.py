@@ -61,6 +61,7 @@ def load_library():
     L.rtlsdr_gpu_scan_sine_table.restype = None
     L.rtlsdr_gpu_scan_window.argtypes = [ctypes.c_char_p, i, vp]
     L.rtlsdr_gpu_scan_stats.argtypes = [vp, vp, vp, vp]
+    L.rtlsdr_gpu_scan_level_stats.argtypes = [vp, i, vp, vp, vp]
     L.rtlsdr_gpu_scan_kernel_time.argtypes = [vp, vp, vp]
     L.rtlsdr_gpu_scan_strerror.argtypes = [i]
     L.rtlsdr_gpu_scan_strerror.restype = ctypes.c_char_p
@@ -119,7 +120,7 @@ class GpuScan:
 
     def __init__(self, tune_count, bin_e, buf_len, downsample=1, downsample_passes=0, boxcar=1,
                  comp_fir_size=0, peak_hold=0, rate=2400000, crop=0.0, window_coefs=None,
-                 sinewave=None, device=0, ring_bytes=0):
+                 sinewave=None, device=0, ring_bytes=0, level_stats=False):
         self.lib = load_library()
         self.tune_count, self.bin_e, self.buf_len = tune_count, bin_e, buf_len
         self.n = 1 << bin_e
@@ -139,6 +140,7 @@ class GpuScan:
             self._s = np.ascontiguousarray(sinewave, dtype=np.int16)
             cfg.sinewave = self._s.ctypes.data
         cfg.ring_bytes = ring_bytes
+        cfg.flags = 1 if level_stats else 0  # RTLSDR_GPU_FLAG_LEVEL_STATS
         self.h = ctypes.c_void_p()
         rc = self.lib.rtlsdr_gpu_scan_init(ctypes.byref(cfg), ctypes.byref(self.h))
         if rc:
@@ -205,6 +207,13 @@ class GpuScan:
 
     def set_stream(self, cuda_stream):
         self._check(self.lib.rtlsdr_gpu_scan_set_stream(self.h, cuda_stream), "set_stream")
+
+    def level_stats(self, hop):
+        """(overload, high_level, bytes) soft-AGC byte counts of `hop` since its last collect"""
+        a, b, c = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        self._check(self.lib.rtlsdr_gpu_scan_level_stats(self.h, hop, ctypes.byref(a), ctypes.byref(b),
+                                                         ctypes.byref(c)), "level_stats")
+        return a.value, b.value, c.value
 
     def stats(self):
         k, a, b = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()

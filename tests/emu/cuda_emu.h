@@ -154,3 +154,16 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel)
 		r |= (unsigned)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xFF) << (8 * i);
 	return r;
 }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+template <class F>
+static inline unsigned emu_vcmp4(unsigned a, unsigned b, F f)
+{
+	unsigned r = 0;
+	for (int i = 0; i < 4; i++)
+		if (f((a >> (8 * i)) & 0xFF, (b >> (8 * i)) & 0xFF))
+			r |= 0xFFu << (8 * i);
+	return r;
+}
+static inline unsigned __vcmpeq4(unsigned a, unsigned b) { return emu_vcmp4(a, b, [](unsigned x, unsigned y) { return x == y; }); }
+static inline unsigned __vcmpltu4(unsigned a, unsigned b) { return emu_vcmp4(a, b, [](unsigned x, unsigned y) { return x < y; }); }
+static inline unsigned __vcmpgtu4(unsigned a, unsigned b) { return emu_vcmp4(a, b, [](unsigned x, unsigned y) { return x > y; }); }

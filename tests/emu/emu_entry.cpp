@@ -276,6 +276,21 @@ void emu_epilogue(const long long *avg, const int *samples, double *db, int bin_
 			db[0] = -12345.0;
 }
 
+void emu_level_stats(const uint8_t *reads, int n_reads, int buf_len, const int *hop_of, unsigned long long *level)
+{
+	std::vector<long long> offs(n_reads);
+	for (int i = 0; i < n_reads; i++)
+		offs[i] = (long long)i * buf_len;
+	LevelParams p;
+	p.base = reads;
+	p.read_off = offs.data();
+	p.hop_of = hop_of;
+	p.n_reads = n_reads;
+	p.buf_len = buf_len;
+	p.level = level;
+	cuda_emu::launch(dim3(2), dim3(256), 0, [&]() { level_stats_kernel(p); });
+}
+
 #include "emu_large.inl"
 
 } /* extern "C" */

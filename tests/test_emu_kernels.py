@@ -191,3 +191,17 @@ def test_fifth_order_chain_every_depth(emu, port_oracle, passes, fir):
     emu.emu_small_decim(bin_e, 0, vp(reads), 2, buf_len, ds, passes, 1, vp(fir5), vp(segs), 1, vp(tw), vp(w16),
                         vp(avg), None, None)
     assert np.array_equal(avg, want)
+
+
+def test_level_stats_kernel(emu):
+    rng = np.random.default_rng(4)
+    reads = rng.integers(0, 256, (9, 16384), dtype=np.uint8)
+    reads[2, :5000] = 255
+    reads[5, 100:900] = 0
+    hop_of = np.array([0, 1, 2, 0, 1, 2, 0, 1, 2], dtype=np.int32)
+    level = np.zeros((3, 2), dtype=np.uint64)
+    emu.emu_level_stats(vp(reads), 9, 16384, vp(hop_of), vp(level))
+    for h in range(3):
+        b = reads[hop_of == h]
+        assert level[h, 0] == np.count_nonzero((b == 0) | (b == 255))     # librtlsdr.c:3302
+        assert level[h, 1] == np.count_nonzero((b < 64) | (b > 191))      # librtlsdr.c:3304

@@ -262,3 +262,61 @@ def test_fifth_order_chain_every_depth(scan_mod, port_oracle, passes, fir):
     assert np.array_equal(got[0], want[0])
     assert np.array_equal(got[1], want[1])
     assert db_close(got[2], want[2])
+
+
+def test_level_stats_soft_agc_counts(scan_mod, port_oracle):
+    """optional byte statistics (what softagc() counts per buffer, librtlsdr.c:3299-3306)"""
+    plan = plan_dict(10, tune_count=3)
+    reads, hops = make_reads(port_oracle.lib, plan, 4, SYNTH_TONE, seed=3, param=140)  # clipped tone: 0 / 255 bytes
+    g = scan_mod.GpuScan.from_plan(plan, window_coefs=None, level_stats=True)
+    try:
+        for r, h in zip(reads, hops):
+            g.submit(int(h), r)
+        for h in range(3):
+            b = reads[hops == h]
+            over, high, nbytes = g.level_stats(h)
+            assert over == np.count_nonzero((b == 0) | (b == 255))
+            assert high == np.count_nonzero((b < 64) | (b > 191))
+            assert nbytes == b.size
+        g.collect(1)
+        assert g.level_stats(1) == (0, 0, 0)
+        assert g.level_stats(0)[2] == reads[hops == 0].size
+    finally:
+        g.close()
+    g = scan_mod.GpuScan.from_plan(plan)
+    with pytest.raises(scan_mod.ScanError):
+        g.level_stats(0)   # not enabled
+    g.close()
+
+
+def test_cli_async_callback_mode_and_replay(scan_mod, port_oracle, tmp_path):
+    """rtl_power_gpu fed through rtlsdr_read_async callbacks, and from a recorded rtl_tcp capture,
+    prints the same rows as the read_sync path"""
+    import os
+    import struct
+    import subprocess
+    from rtlsdr_b200 import _build
+    _build.build_host()
+    exe = os.path.join(_build.HOST_BUILD, "rtl_power_gpu")
+    base_env = dict(os.environ, RTLSDR_SYNTH_MODE="biased", RTLSDR_SYNTH_SEED="6", RTLSDR_SYNTH_PARAM="-15",
+                    RTL_POWER_PASSES="3", RTL_POWER_TIMESTAMP="2026-01-01, 00:00:00")
+    args = ["-f", "433M:435M:4k", "-w", "blackman", "-P", "-1"]
+    outs = {}
+    for name, extra in (("sync", {}), ("async", {"RTL_POWER_ASYNC": "1"})):
+        out = tmp_path / f"{name}.csv"
+        r = subprocess.run([exe] + args + [str(out)], env=dict(base_env, **extra), capture_output=True, text=True,
+                           timeout=120)
+        assert r.returncode == 0, r.stderr
+        outs[name] = out.read_text()
+    assert outs["sync"] == outs["async"] and len(outs["sync"]) > 1000
+    # the same bytes recorded as an rtl_tcp capture and replayed
+    from rtlsdr_b200.planner import plan_scan
+    plan = plan_scan("433M:435M:4k").as_dict()
+    reads, _ = make_reads(port_oracle.lib, plan, 3, SYNTH_BIASED, seed=6, param=-15)
+    cap = tmp_path / "capture.rtltcp"
+    cap.write_bytes(b"RTL0" + struct.pack(">II", 5, 29) + reads.tobytes())
+    out = tmp_path / "replay.csv"
+    env = dict(base_env, RTLSDR_SYNTH_MODE="replay", RTLSDR_SYNTH_REPLAY=str(cap))
+    r = subprocess.run([exe] + args + [str(out)], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert out.read_text() == outs["sync"]
