@@ -78,6 +78,7 @@ struct rtlsdr_gpu_scan {
 	unsigned long long *d_level = nullptr; /* [tune_count][2] soft-AGC byte counts (optional) */
 	std::vector<uint64_t> level_bytes;
 	int2 *d_tw = nullptr;
+	int2 *d_twc = nullptr;          /* small path: per-stage compact twiddles (shared-memory image) */
 	int2 *d_twb = nullptr;          /* large path: round-B twiddles re-ordered [se][plow][ilow] */
 	uint16_t *d_win = nullptr;
 	double *d_db = nullptr;
@@ -615,6 +616,7 @@ int launch_batch(rtlsdr_gpu_scan *h, const uint8_t *base, const uint8_t *d_desc,
 		p.samples = h->d_smp64;
 		p.samples_per_read = h->samples_per_read;
 		p.tw = h->d_tw;
+		p.twc = h->d_twc;
 		p.win = h->d_win;
 		p.tw0 = h->tw0;
 		TimedScope ts(h);
@@ -686,6 +688,7 @@ int launch_batch(rtlsdr_gpu_scan *h, const uint8_t *base, const uint8_t *d_desc,
 				p.samples = h->d_smp64;
 				p.samples_per_read = h->samples_per_read;
 				p.tw = h->d_tw;
+				p.twc = h->d_twc;
 				p.win = h->d_win;
 				p.dc_ave = sc.ave;
 				p.l_len = h->l_len;
@@ -803,6 +806,7 @@ void free_all(rtlsdr_gpu_scan *h)
 	cudaFree(h->d_tw);
 	cudaFree(h->d_level);
 	cudaFree(h->d_twb);
+	cudaFree(h->d_twc);
 	cudaFree(h->d_win);
 	cudaFree(h->d_db);
 	cudaFree(h->d_samples);
@@ -1103,6 +1107,20 @@ int rtlsdr_gpu_scan_init(const rtlsdr_gpu_scan_cfg_t *cfg, rtlsdr_gpu_scan_t **o
 				break;
 		}
 
+		if (cfg->bin_e > 4 && cfg->bin_e <= 12) {
+			/* compact table: stage s (4..L-1), group m at (1<<s)-16+m = tw[m << (L-1-s)] */
+			const int L = cfg->bin_e;
+			std::vector<int2> twc((size_t)N - 16);
+			for (int st = 4; st < L; st++)
+				for (int m = 0; m < (1 << st); m++)
+					twc[(size_t)(1 << st) - 16 + m] = h->tw_host[(size_t)m << (L - 1 - st)];
+			if (cudaMalloc(&h->d_twc, twc.size() * sizeof(int2)) != cudaSuccess) {
+				rc = RTLSDR_GPU_ERR_NOMEM;
+				break;
+			}
+			if (cudaMemcpy(h->d_twc, twc.data(), twc.size() * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess)
+				break;
+		}
 		if (h->path == PATH_LARGE) {
 			/* twb[se][plow][ilow] = tw[((ilow << 8) | plow) << (L-9-se)], se = 4 .. min(8, L-8)-1 */
 			const int L = cfg->bin_e, lb = std::min(8, L - 8);

@@ -267,6 +267,7 @@ struct SmallParams {
 	long long *samples;         /* [tune_count] tunes[i].samples (rtl_power.c:717) */
 	int samples_per_read;
 	const int2 *tw;             /* [N/2] halved twiddles (wr, wi) */
+	const int2 *twc;            /* [N-16] the same, per-stage compact: stage s >= 4, group m at (1<<s)-16+m */
 	const uint16_t *win;        /* [N] low 16 bits of window_coefs */
 	/* IN16 only: images of consecutive entries are contiguous, blocks_padded * N c16 each */
 	const int *dc_ave;          /* [entry - entry_base][2]: int16 averages remove_dc subtracts (I, Q) */
@@ -283,7 +284,7 @@ struct SmallSmem {
 	static constexpr int off_xch = 2 * kStageBytes;
 	static constexpr int off_tw = off_xch + 2 * kXchWords * 4; /* two transpose buffers */
 	static constexpr int tw_entries = N > 16 ? N - 16 : 1; /* stages 4..L-1, group m of stage s at (1<<s)-16+m */
-	static constexpr int off_win = off_tw + tw_entries * 8;
+	static constexpr int off_win = (off_tw + tw_entries * 8 + 15) & ~15; /* 16-byte aligned for cp.async */
 	static constexpr int off_red = (off_win + N * 2 + 15) & ~15;
 	static constexpr int off_dck = off_red + 16 * 8; /* after red[8 warps][2] */
 	static constexpr int bytes = off_dck + 16;
@@ -330,13 +331,19 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 	int *red = (int *)(smem + SM::off_red); /* [8 warps][2] */
 
 	const int t = threadIdx.x;
-	for (int i = t; i < N - 16; i += kThreads) {
-		/* entry i of the compact table: stage s with (1<<s)-16 <= i < (2<<s)-16 */
-		const int s = 31 - __clz(i + 16);
-		tws[i] = prm.tw[(i + 16 - (1 << s)) << (L - 1 - s)];
+	/* tables: asynchronous 16-byte copies (the host pre-arranges the per-stage compact
+	 * twiddle layout), overlapped with the first read's prefetch */
+	if constexpr (N > 16) {
+		for (int i = t; i < (N - 16) / 2; i += kThreads)
+			cp_async16((uint8_t *)tws + 16 * i, (const uint8_t *)prm.twc + 16 * i);
 	}
-	for (int i = t; i < N; i += kThreads)
-		wins[i] = prm.win[i];
+	if constexpr (N >= 8) {
+		for (int i = t; i < N / 8; i += kThreads)
+			cp_async16((uint8_t *)wins + 16 * i, (const uint8_t *)prm.win + 16 * i);
+	} else {
+		for (int i = t; i < N; i += kThreads)
+			wins[i] = prm.win[i];
+	}
 
 	TwSmall<L> tw;
 	tw.tws = tws;

@@ -12,6 +12,8 @@
 #include <barrier>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <memory>
@@ -38,7 +40,14 @@ inline std::vector<std::unique_ptr<std::barrier<>>> g_warp_bar;
 inline std::vector<uint64_t> g_shfl;
 
 inline unsigned char *dyn_smem() { return g_smem; }
-inline void copy16(void *d, const void *s) { memcpy(d, s, 16); }
+inline void copy16(void *d, const void *s)
+{
+	if (((uintptr_t)d & 15) || ((uintptr_t)s & 15)) {
+		fprintf(stderr, "cuda_emu: cp.async 16 with a misaligned address\n");
+		abort();
+	}
+	memcpy(d, s, 16);
+}
 inline unsigned linear_tid() { return t_threadIdx.x + g_blockDim.x * (t_threadIdx.y + g_blockDim.y * t_threadIdx.z); }
 
 template <class T>

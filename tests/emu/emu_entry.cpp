@@ -50,6 +50,15 @@ void run_small(int L, const SmallParams &prm, int peak, int in16)
 	}
 }
 
+std::vector<int2> compact_tw(const int2 *tw, int L)
+{
+	std::vector<int2> twc((size_t)(L > 4 ? (1 << L) - 16 : 1));
+	for (int st = 4; st < L; st++)
+		for (int m = 0; m < (1 << st); m++)
+			twc[(size_t)(1 << st) - 16 + m] = tw[(size_t)m << (L - 1 - st)];
+	return twc;
+}
+
 void fill_tw0(PassTw &tw0, const int2 *tw, int L)
 {
 	memset(&tw0, 0, sizeof(tw0));
@@ -80,6 +89,8 @@ void emu_small_u8(int L, int peak, const uint8_t *reads, int n_reads, const int 
 	p.samples = smp.data();
 	p.samples_per_read = 1;
 	p.tw = (const int2 *)tw;
+	std::vector<int2> twc = compact_tw(p.tw, L);
+	p.twc = twc.data();
 	p.win = win;
 	fill_tw0(p.tw0, p.tw, L);
 	run_small(L, p, peak, 0);
@@ -225,6 +236,8 @@ void emu_small_decim(int L, int peak, const uint8_t *reads, int n_reads, int buf
 	p.l_len = l_len;
 	p.n_blocks = n_blocks;
 	p.blocks_padded = blocks_padded;
+	std::vector<int2> twc = compact_tw(p.tw, L);
+	p.twc = twc.data();
 	fill_tw0(p.tw0, p.tw, L);
 	run_small(L, p, peak, 1);
 }
