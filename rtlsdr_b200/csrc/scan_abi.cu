@@ -75,6 +75,7 @@ struct rtlsdr_gpu_scan {
 
 	long long *d_avg = nullptr;     /* [tune_count * N] bins, then [tune_count] sample counters */
 	long long *d_smp64 = nullptr;   /* = d_avg + tune_count * N */
+	unsigned *d_done = nullptr;     /* [tune_count] epilogue tickets (fused read-and-zero) */
 	unsigned long long *d_level = nullptr; /* [tune_count][2] soft-AGC byte counts (optional) */
 	std::vector<uint64_t> level_bytes;
 	int2 *d_tw = nullptr;
@@ -805,6 +806,7 @@ void free_all(rtlsdr_gpu_scan *h)
 	cudaFree(h->d_avg);
 	cudaFree(h->d_tw);
 	cudaFree(h->d_level);
+	cudaFree(h->d_done);
 	cudaFree(h->d_twb);
 	cudaFree(h->d_twc);
 	cudaFree(h->d_win);
@@ -861,9 +863,13 @@ void free_all(rtlsdr_gpu_scan *h)
 
 /* dB rows (+ optional raw-bin / sample-count copies) of hops [hop0, hop0+nhops):
  * one kernel, outputs indexed from hop0 */
-int run_epilogue(rtlsdr_gpu_scan *h, int hop0, int nhops, double *db, long long *avg_out, int *samples_out)
+int run_epilogue(rtlsdr_gpu_scan *h, int hop0, int nhops, double *db, long long *avg_out, int *samples_out,
+		 bool zero_after = false)
 {
 	EpilogueParams p;
+	p.done = zero_after ? h->d_done : nullptr;
+	p.avg_rw = h->d_avg;
+	p.samples_rw = h->d_smp64;
 	p.avg = h->d_avg;
 	p.samples = h->d_smp64;
 	p.db = db;
@@ -1056,6 +1062,12 @@ int rtlsdr_gpu_scan_init(const rtlsdr_gpu_scan_cfg_t *cfg, rtlsdr_gpu_scan_t **o
 			break;
 		}
 		h->d_smp64 = h->d_avg + (size_t)cfg->tune_count * N;
+		if (cudaMalloc(&h->d_done, (size_t)cfg->tune_count * sizeof(unsigned)) != cudaSuccess) {
+			rc = RTLSDR_GPU_ERR_NOMEM;
+			break;
+		}
+		if (cudaMemsetAsync(h->d_done, 0, (size_t)cfg->tune_count * sizeof(unsigned), h->stream) != cudaSuccess)
+			break;
 		if (cudaMemsetAsync(h->d_avg, 0, avg_bytes, h->stream) != cudaSuccess)
 			break;
 		if (cfg->flags & RTLSDR_GPU_FLAG_LEVEL_STATS) {
@@ -1447,9 +1459,12 @@ int rtlsdr_gpu_scan_collect_device(rtlsdr_gpu_scan_t *h, void *dev_avg, void *de
 	const size_t N = (size_t)h->N, tc = (size_t)h->cfg.tune_count;
 	/* one kernel writes dB rows, raw bins and sample counts straight into the
 	 * caller's buffers (e.g. the NCCL send buffer), one memset clears the state */
-	if ((rc = run_epilogue(h, 0, (int)tc, (double *)dev_db, (long long *)dev_avg, (int *)dev_samples)))
+	/* up to 8192 bins the last epilogue block of a hop also zeroes it (no memset launch) */
+	const bool fused_zero = N <= 8192;
+	if ((rc = run_epilogue(h, 0, (int)tc, (double *)dev_db, (long long *)dev_avg, (int *)dev_samples, fused_zero)))
 		return rc;
-	CU(cudaMemsetAsync(h->d_avg, 0, (tc * N + tc) * sizeof(long long), h->stream));
+	if (!fused_zero)
+		CU(cudaMemsetAsync(h->d_avg, 0, (tc * N + tc) * sizeof(long long), h->stream));
 	if (h->d_level) {
 		CU(cudaMemsetAsync(h->d_level, 0, tc * 2 * sizeof(unsigned long long), h->stream));
 		std::fill(h->level_bytes.begin(), h->level_bytes.end(), 0);

@@ -1217,6 +1217,9 @@ struct EpilogueParams {
 	int i1, i2;               /* first / last printed bin of the swapped spectrum */
 	int rate;
 	int hop0;                 /* first hop to process */
+	unsigned *done;           /* optional [hops]: blocks finished per hop; the last one zeroes the hop */
+	long long *avg_rw;        /* same memory as avg when `done` is set */
+	long long *samples_rw;
 };
 
 /* one launch per report: dB row, raw-bin copy and sample count of every hop */
@@ -1232,8 +1235,7 @@ epilogue_kernel(const SCAN_GRID_CONSTANT EpilogueParams prm)
 		prm.avg_out[((long long)blockIdx.y << prm.bin_e) + k] = a[k];
 	if (prm.samples_out && k == 0)
 		prm.samples_out[blockIdx.y] = (int)prm.samples[hop];
-	if (k >= count || !prm.db)
-		return;
+	if (k < count && prm.db) {
 	const int i = (k < count - 1) ? prm.i1 + k : prm.i2;
 	long long v;
 	if (prm.bin_e > 0) {
@@ -1249,6 +1251,26 @@ epilogue_kernel(const SCAN_GRID_CONSTANT EpilogueParams prm)
 	else
 		d = __ddiv_rn((double)v, __dmul_rn(rate, smp));
 	prm.db[(long long)blockIdx.y * count + k] = 10 * log10(d);
+	}
+	/* read-and-zero (rtl_power.c:761-764): the last block of a hop to finish clears its
+	 * bins and sample counter, so no separate memset has to follow the report */
+	if (prm.done) {
+		__shared__ unsigned ticket;
+		__threadfence();
+		__syncthreads();
+		if (threadIdx.x == 0)
+			ticket = atomicAdd(prm.done + hop, 1u);
+		__syncthreads();
+		if (ticket == gridDim.x - 1) {
+			long long *z = prm.avg_rw + ((long long)hop << prm.bin_e);
+			for (int j = threadIdx.x; j < n; j += blockDim.x)
+				z[j] = 0;
+			if (threadIdx.x == 0) {
+				prm.samples_rw[hop] = 0;
+				prm.done[hop] = 0;
+			}
+		}
+	}
 }
 
 } // namespace rscan

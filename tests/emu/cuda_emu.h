@@ -176,3 +176,5 @@ static inline unsigned emu_vcmp4(unsigned a, unsigned b, F f)
 static inline unsigned __vcmpeq4(unsigned a, unsigned b) { return emu_vcmp4(a, b, [](unsigned x, unsigned y) { return x == y; }); }
 static inline unsigned __vcmpltu4(unsigned a, unsigned b) { return emu_vcmp4(a, b, [](unsigned x, unsigned y) { return x < y; }); }
 static inline unsigned __vcmpgtu4(unsigned a, unsigned b) { return emu_vcmp4(a, b, [](unsigned x, unsigned y) { return x > y; }); }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }

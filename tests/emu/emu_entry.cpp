@@ -278,6 +278,9 @@ void emu_epilogue(const long long *avg, const int *samples, double *db, int bin_
 	p.i2 = i2;
 	p.rate = rate;
 	p.hop0 = 0;
+	p.done = nullptr;
+	p.avg_rw = nullptr;
+	p.samples_rw = nullptr;
 	int count = i2 - i1 + 2;
 	int span = count > (1 << bin_e) ? count : (1 << bin_e);
 	cuda_emu::launch(dim3((span + 255) / 256, hops), dim3(256), 0, [&]() { epilogue_kernel(p); });

@@ -320,3 +320,32 @@ def test_cli_async_callback_mode_and_replay(scan_mod, port_oracle, tmp_path):
     r = subprocess.run([exe] + args + [str(out)], env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
     assert out.read_text() == outs["sync"]
+
+
+@pytest.mark.parametrize("bin_e", [0, 6, 12, 14])
+def test_collect_device_reports_and_zeroes(scan_mod, port_oracle, bin_e):
+    """collect_device: dB rows, raw bins and sample counts written into caller device buffers by the
+    epilogue kernel, accumulators cleared on the device (fused for N <= 8192, memset above)."""
+    import torch
+    n = 1 << bin_e
+    plan = plan_dict(bin_e, buf_len=max(16384, 2 * n), tune_count=4, crop=0.2 if bin_e else 0.0, rate=2000000)
+    w = port_oracle.window_coefs("hamming", n) if bin_e else None
+    reads, hops = make_reads(port_oracle.lib, plan, 3, SYNTH_BIASED, seed=bin_e, param=9)
+    want = expected(port_oracle, plan, w if w is not None else np.zeros(1, np.int32), reads, hops)
+    g = scan_mod.GpuScan.from_plan(plan, window_coefs=w)
+    try:
+        d_avg = torch.full((4, n), -1, dtype=torch.int64, device="cuda")
+        d_smp = torch.full((4,), -1, dtype=torch.int32, device="cuda")
+        d_db = torch.zeros((4, g.db_count), dtype=torch.float64, device="cuda")
+        for rep in range(2):   # second round: accumulators really were zeroed
+            for r, h in zip(reads, hops):
+                g.submit(int(h), r)
+            g.collect_device(d_avg.data_ptr(), d_smp.data_ptr(), d_db.data_ptr())
+            g.sync()
+            assert np.array_equal(d_avg.cpu().numpy(), want[0])
+            assert np.array_equal(d_smp.cpu().numpy(), want[1])
+            assert db_close(d_db.cpu().numpy(), want[2])
+        avg, smp, _ = g.collect_all(want_db=False)
+        assert not avg.any() and not smp.any()
+    finally:
+        g.close()
