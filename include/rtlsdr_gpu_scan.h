@@ -183,6 +183,9 @@ RTLSDR_GPU_API void rtlsdr_gpu_scan_host_free(void *p);
 /* Run the handle's work on a caller-owned CUDA stream (cudaStream_t passed as
  * void*); NULL restores the handle's own stream. */
 RTLSDR_GPU_API int rtlsdr_gpu_scan_set_stream(rtlsdr_gpu_scan_t *h, void *cuda_stream);
+/* The stream the handle currently launches on (cudaStream_t as void*), e.g. to record events on it
+ * or to make other streams wait for it. */
+RTLSDR_GPU_API void *rtlsdr_gpu_scan_get_stream(rtlsdr_gpu_scan_t *h);
 /* Host table builders using the reference's expressions: Sinewave
  * (rtl_power.c:247-261; out[(1<<bin_e)*3/4]) and window_coefs for a -w name
  * (rtl_power.c:329-408, 826-843, 985-988; out[n]).  window returns -1 for an
@@ -195,6 +198,9 @@ RTLSDR_GPU_API int rtlsdr_gpu_scan_stats(const rtlsdr_gpu_scan_t *h, uint64_t *k
 /* Device time in milliseconds of the main transform kernel(s) launched since
  * the previous call (CUDA events on the launching stream), and their count. */
 RTLSDR_GPU_API int rtlsdr_gpu_scan_kernel_time(rtlsdr_gpu_scan_t *h, double *ms, uint64_t *launches);
+/* Time only every `every`-th transform (0 = off).  Event records between two kernels keep the
+ * second from being launched programmatically dependent on the first, so long runs sample. */
+RTLSDR_GPU_API int rtlsdr_gpu_scan_set_timing(rtlsdr_gpu_scan_t *h, int every);
 RTLSDR_GPU_API const char *rtlsdr_gpu_scan_strerror(int err);
 /* Text of the last CUDA error seen by this handle ("" if none). */
 RTLSDR_GPU_API const char *rtlsdr_gpu_scan_last_cuda_error(const rtlsdr_gpu_scan_t *h);

@@ -129,11 +129,18 @@ struct rtlsdr_gpu_scan {
 	uint8_t *d_bulk = nullptr;
 	size_t bulk_bytes = 0;
 
+	/* true while the last operation this handle put on its OWN stream was the report epilogue:
+	 * only then may the next transform kernel be launched programmatically dependent (it reads
+	 * nothing the epilogue writes before its pdl_wait) */
+	bool last_was_epilogue = false;
 	uint64_t launches = 0, h2d = 0, d2h = 0;
 	/* timing of the transform kernels */
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
 	std::vector<cudaEvent_t> ev_pool;
 	bool timing = false;
+	int timing_every = 1;   /* bracket every k-th transform with events (events between kernels
+	                         * prevent programmatic dependent launch, so benchmarks sample) */
+	uint64_t timing_count = 0;
 
 	std::string last_error;
 };
@@ -244,8 +251,9 @@ struct TimedScope {
 	cudaEvent_t a = nullptr, b = nullptr;
 	explicit TimedScope(rtlsdr_gpu_scan *hh) : h(hh)
 	{
-		if (!h->timing)
+		if (!h->timing || (h->timing_count++ % (uint64_t)h->timing_every) != 0)
 			return;
+		h->last_was_epilogue = false;
 		a = get_event(h);
 		b = get_event(h);
 		if (a && b)
@@ -369,7 +377,22 @@ int launch_small_t(rtlsdr_gpu_scan *h, const SmallParams &prm)
 	const int smem = SmallSmem<L>::bytes;
 	CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 	const int grid = std::min(prm.n_segs, h->num_sms * 8);
-	kern<<<grid, kThreads, smem, h->stream>>>(prm);
+	if (!IN16 && h->last_was_epilogue && h->stream == h->own_stream) {
+		cudaLaunchConfig_t cfg = {};
+		cfg.gridDim = dim3(grid);
+		cfg.blockDim = dim3(kThreads);
+		cfg.dynamicSmemBytes = smem;
+		cfg.stream = h->stream;
+		cudaLaunchAttribute attr[1];
+		attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		attr[0].val.programmaticStreamSerializationAllowed = 1;
+		cfg.attrs = attr;
+		cfg.numAttrs = 1;
+		CU(cudaLaunchKernelEx(&cfg, kern, prm));
+	} else {
+		kern<<<grid, kThreads, smem, h->stream>>>(prm);
+	}
+	h->last_was_epilogue = false;
 	return check_launch(h, "scan_small_kernel");
 }
 
@@ -575,6 +598,8 @@ int launch_batch(rtlsdr_gpu_scan *h, const uint8_t *base, const uint8_t *d_desc,
 	const int4 *d_segs = (const int4 *)(d_desc + lay.off_segs);
 	const int *d_hops = (const int *)(d_desc + lay.off_hops);
 	int rc = 0;
+	if (h->path != PATH_SMALL_U8 || h->d_level)
+		h->last_was_epilogue = false;
 
 	if (h->d_level) {
 		LevelParams lp;
@@ -738,6 +763,7 @@ int process_batch(rtlsdr_gpu_scan *h, const uint8_t *base, const std::vector<lon
 	memcpy(hp + lay.off_reads, s_offs.data(), (size_t)n * 8);
 	memcpy(hp + lay.off_segs, segs.data(), (size_t)n_segs * 16);
 	memcpy(hp + lay.off_hops, s_hops.data(), (size_t)n * 4);
+	h->last_was_epilogue = false;
 	CU(cudaMemcpyAsync(slot->d, slot->h, lay.bytes, cudaMemcpyHostToDevice, h->stream));
 	rc = launch_batch(h, base, (const uint8_t *)slot->d, n, n_segs, &segs);
 	CU(cudaEventRecord(slot->done, h->stream));
@@ -759,6 +785,7 @@ int flush_ring(rtlsdr_gpu_scan *h)
 	if (n == 0)
 		return 0;
 	const size_t B = (size_t)h->cfg.buf_len;
+	h->last_was_epilogue = false;
 	CU(cudaMemcpyAsync(h->d_ring[half], h->h_ring[half], (size_t)n * B, cudaMemcpyHostToDevice, h->stream));
 	h->h2d += (uint64_t)n * B;
 	std::vector<long long> offs(n);
@@ -883,6 +910,7 @@ int run_epilogue(rtlsdr_gpu_scan *h, int hop0, int nhops, double *db, long long 
 	const int span = std::max(h->db_count, avg_out ? h->N : 0);
 	dim3 grid((span + 255) / 256, nhops);
 	epilogue_kernel<<<grid, 256, 0, h->stream>>>(p);
+	h->last_was_epilogue = zero_after; /* nothing else follows it on the stream in the fused-zero case */
 	return check_launch(h, "epilogue_kernel");
 }
 
@@ -1184,6 +1212,11 @@ void rtlsdr_gpu_scan_close(rtlsdr_gpu_scan_t *h)
 	free_all(h);
 }
 
+void *rtlsdr_gpu_scan_get_stream(rtlsdr_gpu_scan_t *h)
+{
+	return h ? (void *)h->stream : nullptr;
+}
+
 int rtlsdr_gpu_scan_set_stream(rtlsdr_gpu_scan_t *h, void *cuda_stream)
 {
 	if (!h)
@@ -1191,6 +1224,7 @@ int rtlsdr_gpu_scan_set_stream(rtlsdr_gpu_scan_t *h, void *cuda_stream)
 	CU(cudaSetDevice(h->cfg.device));
 	CU(cudaStreamSynchronize(h->stream));
 	h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+	h->last_was_epilogue = false;
 	return 0;
 }
 
@@ -1285,6 +1319,7 @@ static int submit_regular(rtlsdr_gpu_scan_t *h, int hop_first, int hop_count, in
 		memcpy(hp + lay.off_reads, s_offs.data(), (size_t)n * 8);
 		memcpy(hp + lay.off_segs, hit->segs.data(), (size_t)n_segs * 16);
 		memcpy(hp + lay.off_hops, s_hops.data(), (size_t)n * 4);
+		h->last_was_epilogue = false;
 		CU(cudaMemcpyAsync(hit->d_desc, slot->h, lay.bytes, cudaMemcpyHostToDevice, h->stream));
 		CU(cudaEventRecord(slot->done, h->stream));
 		slot->used = true;
@@ -1378,6 +1413,7 @@ int rtlsdr_gpu_scan_submit_batch(rtlsdr_gpu_scan_t *h, int hop_first, int hop_co
 	}
 	for (int c = 0; c < chunks; c++) {
 		const int p0 = (int)((long long)passes * c / chunks), p1 = (int)((long long)passes * (c + 1) / chunks);
+		h->last_was_epilogue = false;
 		CU(cudaStreamWaitEvent(h->stream, h->chunk_ready[c], 0));
 		rc = submit_regular(h, hop_first, hop_count, p1 - p0, h->d_bulk + (size_t)p0 * (size_t)pass_stride,
 				    pass_stride, hop_stride);
@@ -1413,6 +1449,7 @@ static int collect_range(rtlsdr_gpu_scan_t *h, int hop0, int nhops, int64_t *avg
 		h->d2h += (uint64_t)nhops * N * sizeof(long long);
 	}
 	/* read-and-zero, like csv_dbm (rtl_power.c:761-764) */
+	h->last_was_epilogue = false;
 	if (nhops == h->cfg.tune_count) {
 		CU(cudaMemsetAsync(h->d_avg, 0, ((size_t)nhops * N + (size_t)nhops) * sizeof(long long), h->stream));
 	} else {
@@ -1463,9 +1500,12 @@ int rtlsdr_gpu_scan_collect_device(rtlsdr_gpu_scan_t *h, void *dev_avg, void *de
 	const bool fused_zero = N <= 8192;
 	if ((rc = run_epilogue(h, 0, (int)tc, (double *)dev_db, (long long *)dev_avg, (int *)dev_samples, fused_zero)))
 		return rc;
-	if (!fused_zero)
+	if (!fused_zero) {
+		h->last_was_epilogue = false;
 		CU(cudaMemsetAsync(h->d_avg, 0, (tc * N + tc) * sizeof(long long), h->stream));
+	}
 	if (h->d_level) {
+		h->last_was_epilogue = false;
 		CU(cudaMemsetAsync(h->d_level, 0, tc * 2 * sizeof(unsigned long long), h->stream));
 		std::fill(h->level_bytes.begin(), h->level_bytes.end(), 0);
 	}
@@ -1486,6 +1526,7 @@ int rtlsdr_gpu_scan_level_stats(rtlsdr_gpu_scan_t *h, int hop, uint64_t *overloa
 	if (rc)
 		return rc;
 	unsigned long long v[2] = { 0, 0 };
+	h->last_was_epilogue = false;
 	CU(cudaMemcpyAsync(v, h->d_level + 2 * (size_t)hop, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
 	CU(cudaStreamSynchronize(h->stream));
 	if (overload)
@@ -1507,6 +1548,16 @@ int rtlsdr_gpu_scan_stats(const rtlsdr_gpu_scan_t *h, uint64_t *kernel_launches,
 		*h2d_bytes = h->h2d;
 	if (d2h_bytes)
 		*d2h_bytes = h->d2h;
+	return 0;
+}
+
+int rtlsdr_gpu_scan_set_timing(rtlsdr_gpu_scan_t *h, int every)
+{
+	if (!h)
+		return RTLSDR_GPU_ERR_NULL;
+	h->timing = every > 0;
+	h->timing_every = every > 0 ? every : 1;
+	h->timing_count = 0;
 	return 0;
 }
 

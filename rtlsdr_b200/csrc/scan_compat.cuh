@@ -49,4 +49,25 @@ SCAN_DEV void cp_async_wait_all()
 #endif
 }
 
+/*
+ * Programmatic dependent launch (sm_90+): a kernel launched with the
+ * programmatic-stream-serialization attribute may start while the previous
+ * kernel in the stream is still running; pdl_wait() blocks until that kernel
+ * has completed and its writes are visible, pdl_launch_dependents() lets the
+ * next kernel start early.  Both are no-ops for ordinary launches.
+ */
+SCAN_DEV void pdl_wait()
+{
+#ifndef SCAN_EMU
+	asm volatile("griddepcontrol.wait;\n" ::: "memory");
+#endif
+}
+
+SCAN_DEV void pdl_launch_dependents()
+{
+#ifndef SCAN_EMU
+	asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+#endif
+}
+
 } // namespace rscan

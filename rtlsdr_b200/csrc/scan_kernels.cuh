@@ -524,6 +524,9 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 			}
 		}
 
+		/* everything above only read this launch's inputs; the accumulators may still be in use
+		 * by the report epilogue of the previous interval (programmatic dependent launch) */
+		pdl_wait();
 		if (t == 0)
 			atomicAdd((unsigned long long *)(prm.samples + hop), (unsigned long long)((long long)sg.z * prm.samples_per_read));
 
@@ -1226,6 +1229,7 @@ struct EpilogueParams {
 __global__ void __launch_bounds__(256)
 epilogue_kernel(const SCAN_GRID_CONSTANT EpilogueParams prm)
 {
+	pdl_launch_dependents(); /* the next interval's transform may start; it waits before its flush */
 	const int hop = prm.hop0 + blockIdx.y;
 	const int n = 1 << prm.bin_e;
 	const int count = prm.i2 - prm.i1 + 2;

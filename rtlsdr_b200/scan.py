@@ -57,12 +57,15 @@ def load_library():
     L.rtlsdr_gpu_scan_host_free.argtypes = [vp]
     L.rtlsdr_gpu_scan_host_free.restype = None
     L.rtlsdr_gpu_scan_set_stream.argtypes = [vp, vp]
+    L.rtlsdr_gpu_scan_get_stream.argtypes = [vp]
+    L.rtlsdr_gpu_scan_get_stream.restype = vp
     L.rtlsdr_gpu_scan_sine_table.argtypes = [i, vp]
     L.rtlsdr_gpu_scan_sine_table.restype = None
     L.rtlsdr_gpu_scan_window.argtypes = [ctypes.c_char_p, i, vp]
     L.rtlsdr_gpu_scan_stats.argtypes = [vp, vp, vp, vp]
     L.rtlsdr_gpu_scan_level_stats.argtypes = [vp, i, vp, vp, vp]
     L.rtlsdr_gpu_scan_kernel_time.argtypes = [vp, vp, vp]
+    L.rtlsdr_gpu_scan_set_timing.argtypes = [vp, i]
     L.rtlsdr_gpu_scan_strerror.argtypes = [i]
     L.rtlsdr_gpu_scan_strerror.restype = ctypes.c_char_p
     L.rtlsdr_gpu_scan_last_cuda_error.argtypes = [vp]
@@ -215,10 +218,18 @@ class GpuScan:
                                                          ctypes.byref(c)), "level_stats")
         return a.value, b.value, c.value
 
+    def get_stream(self):
+        """raw cudaStream_t of the handle (wrap with torch.cuda.ExternalStream to record events on it)"""
+        return self.lib.rtlsdr_gpu_scan_get_stream(self.h)
+
     def stats(self):
         k, a, b = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
         self.lib.rtlsdr_gpu_scan_stats(self.h, ctypes.byref(k), ctypes.byref(a), ctypes.byref(b))
         return dict(kernel_launches=k.value, h2d_bytes=a.value, d2h_bytes=b.value)
+
+    def set_timing(self, every):
+        """bracket every `every`-th transform kernel with CUDA events (0 = off)"""
+        self._check(self.lib.rtlsdr_gpu_scan_set_timing(self.h, every), "set_timing")
 
     def kernel_time(self):
         """(ms, launches) of the transform kernels since the previous call; the first call arms timing."""

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--sets", type=int, default=0, help="distinct input sets (0 = enough to exceed 2x L2)")
+    ap.add_argument("--no-kernel-time", action="store_true", help="do not bracket the transform kernels with events")
     args = ap.parse_args()
 
     import torch
@@ -37,8 +38,7 @@ def main():
     pd["peak_hold"] = 1 if args.peak else 0
     tc, b, n = pd["tune_count"], pd["buf_len"], 1 << pd["bin_e"]
     g = rs.GpuScan.from_plan(pd, window_coefs=rs.window_coefs(args.window, n) if pd["bin_e"] else None)
-    stream = torch.cuda.Stream()
-    g.set_stream(stream.cuda_stream)
+    stream = torch.cuda.ExternalStream(g.get_stream())
     step_bytes = args.passes * tc * b
     n_sets = args.sets or max(1, -(-(256 << 20) // step_bytes))
     dev_in = torch.randint(0, 256, (n_sets, args.passes, tc, b), dtype=torch.uint8, device="cuda")
@@ -54,7 +54,8 @@ def main():
     for i in range(args.warmup):
         step(i)
     torch.cuda.synchronize()
-    g.kernel_time()
+    if not args.no_kernel_time:
+        g.kernel_time()
     s0 = g.stats()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -63,7 +64,7 @@ def main():
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
-    k_ms, k_n = g.kernel_time()
+    k_ms, k_n = (0.0, 0) if args.no_kernel_time else g.kernel_time()
     s1 = g.stats()
     samples = step_bytes // 2
     print(json.dumps({
