@@ -78,3 +78,30 @@ def test_host_table_helpers_match_oracle(lib, port_oracle):
     out = np.zeros(8, dtype=np.int32)
     assert lib.rtlsdr_gpu_scan_window(b"nonsense", 8, out.ctypes.data_as(ctypes.c_void_p)) == -1
     assert (out == 256).all()  # unknown names silently stay rectangle (rtl_power.c:826-843)
+
+
+def test_config_validation_happens_before_any_device_work(lib):
+    """malformed configurations are rejected with RTLSDR_GPU_ERR_CONFIG (-2) even without a GPU"""
+    import rtlsdr_b200.scan as rs
+
+    def init(**kw):
+        cfg = rs._Cfg()
+        cfg.struct_size = ctypes.sizeof(rs._Cfg)
+        base = dict(device=0, tune_count=1, bin_e=10, buf_len=16384, downsample=1, downsample_passes=0,
+                    boxcar=1, comp_fir_size=0, peak_hold=0, rate=2400000, crop=0.0)
+        base.update(kw)
+        for k, v in base.items():
+            setattr(cfg, k, v)
+        h = ctypes.c_void_p()
+        return lib.rtlsdr_gpu_scan_init(ctypes.byref(cfg), ctypes.byref(h))
+
+    assert init(struct_size=8) == -2                 # ABI version mismatch
+    assert init(tune_count=0) == -2
+    assert init(tune_count=3001) == -2               # MAX_TUNES, rtl_power.c:113
+    assert init(bin_e=22) == -2                      # planner stops at 21, rtl_power.c:483
+    assert init(buf_len=1000) == -2                  # not a multiple of 16
+    assert init(rate=0) == -2
+    assert init(crop=1.5) == -2
+    assert init(downsample=0) == -2
+    assert init(boxcar=0, downsample=8, downsample_passes=2) == -2   # ds must be 2^passes with -F
+    assert init(boxcar=0, downsample=3, downsample_passes=0) == -2   # ds > 1 without a decimator

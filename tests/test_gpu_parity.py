@@ -349,3 +349,29 @@ def test_collect_device_reports_and_zeroes(scan_mod, port_oracle, bin_e):
         assert not avg.any() and not smp.any()
     finally:
         g.close()
+
+
+def test_argument_errors_on_device_paths(scan_mod):
+    import torch
+    g = scan_mod.GpuScan(4, 10, 16384)
+    try:
+        dev = torch.zeros(4 * 16384 + 64, dtype=torch.uint8, device="cuda")
+        for args, code in (((0, 4, 1, dev.data_ptr() + 1, 4 * 16384, 16384), -8),     # misaligned base
+                           ((0, 4, 1, dev.data_ptr(), 4 * 16384 + 8, 16384), -8),     # misaligned stride
+                           ((2, 3, 1, dev.data_ptr(), 4 * 16384, 16384), -3),         # hops 2..4 of 4
+                           ((0, 4, 0, dev.data_ptr(), 4 * 16384, 16384), -2)):        # no passes
+            with pytest.raises(scan_mod.ScanError) as e:
+                g.submit_device(*args)
+            assert e.value.code == code, args
+        with pytest.raises(scan_mod.ScanError) as e:
+            g.collect(4)
+        assert e.value.code == -3
+        # an untouched handle reports zeros and "-inf"-free rows are the caller's business
+        avg, smp, db = g.collect_all()
+        assert not avg.any() and not smp.any()
+    finally:
+        g.close()
+    # u8 fast path needs the planner's buffer length (16384 whenever 2N <= 16384, rtl_power.c:501-504)
+    with pytest.raises(scan_mod.ScanError) as e:
+        scan_mod.GpuScan(1, 10, 32768)
+    assert e.value.code == -2
