@@ -375,3 +375,28 @@ def test_argument_errors_on_device_paths(scan_mod):
     with pytest.raises(scan_mod.ScanError) as e:
         scan_mod.GpuScan(1, 10, 32768)
     assert e.value.code == -2
+
+
+def test_sweep_main_single_rank_rows(scan_mod, port_oracle, tmp_path):
+    """rtlsdr_b200.sweep_main (the hop-sharded driver) at world size 1: rows equal the oracle's"""
+    import os
+    import subprocess
+    import sys
+    from rtlsdr_b200.planner import plan_scan
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "sweep.csv"
+    r = subprocess.run([sys.executable, "-m", "rtlsdr_b200.sweep_main", "-f", "88M:108M:25k", "-c", "20%", "-w",
+                        "hamming", "--sweeps", "3", "--intervals", "2", "--synth", "biased", "--seed", "4",
+                        "--param", "17", "-o", str(out)], cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    plan = plan_scan("88M:108M:25k", 0.2)
+    pd = plan.as_dict()
+    pd["peak_hold"] = 0
+    w = port_oracle.window_coefs("hamming", 1 << pd["bin_e"])
+    reads, hops = make_reads(port_oracle.lib, pd, 6, SYNTH_BIASED, seed=4, param=17)
+    per = 3 * pd["tune_count"]
+    want = ""
+    for i in range(2):
+        avg, smp, db = expected(port_oracle, pd, w, reads[i * per:(i + 1) * per], hops[i * per:(i + 1) * per])
+        want += "".join("2026-01-01, 00:00:00, " + plan.csv_row(h, int(smp[h]), db[h]) for h in range(pd["tune_count"]))
+    assert out.read_text() == want
