@@ -343,9 +343,20 @@ def run_gpu(args):
         e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     s1 = g.stats()
     k_ms, k_n = g.kernel_time()
+    g.set_timing(0)
+    if rank == 0 and world == 1:
+        # a short timed region (small --steps) may end before nvidia-smi's first 50 ms tick: keep the
+        # same load running, untimed, until a few clock samples exist
+        t_end = time.perf_counter() + 1.0
+        i = args.warmup + args.steps
+        while len(sampler.rows) < 4 and time.perf_counter() < t_end:
+            for _ in range(50):
+                step_device(i)
+                i += 1
+            torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
     launches = s1["kernel_launches"] - s0["kernel_launches"]
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
