@@ -374,7 +374,9 @@ template <int L, bool PEAK, bool IN16>
 int launch_small_t(rtlsdr_gpu_scan *h, const SmallParams &prm)
 {
 	auto kern = scan_small_kernel<L, PEAK, IN16>;
-	const int smem = SmallSmem<L>::bytes;
+	/* RTLSDR_GPU_DEBUG_SMEM_PAD: occupancy experiments only (extra bytes -> fewer CTAs per SM) */
+	static const int pad = getenv("RTLSDR_GPU_DEBUG_SMEM_PAD") ? atoi(getenv("RTLSDR_GPU_DEBUG_SMEM_PAD")) : 0;
+	const int smem = SmallSmem<L>::bytes + pad;
 	CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 	const int grid = std::min(prm.n_segs, h->num_sms * 8);
 	if (!IN16 && h->last_was_epilogue && h->stream == h->own_stream) {

@@ -400,3 +400,70 @@ def test_sweep_main_single_rank_rows(scan_mod, port_oracle, tmp_path):
         avg, smp, db = expected(port_oracle, pd, w, reads[i * per:(i + 1) * per], hops[i * per:(i + 1) * per])
         want += "".join("2026-01-01, 00:00:00, " + plan.csv_row(h, int(smp[h]), db[h]) for h in range(pd["tune_count"]))
     assert out.read_text() == want
+
+
+@pytest.mark.parametrize("peak", [0, 1])
+def test_mixed_submission_paths_stress(scan_mod, port_oracle, peak):
+    """random interleaving of submit (ring), submit_batch (pinned), submit_device, flush, per-hop
+    collect and a caller-owned stream; every hop's report must equal the oracle over exactly the
+    reads submitted since its previous collect"""
+    import torch
+    rng = np.random.default_rng(99 + peak)
+    bin_e, tc, b = 8, 5, 16384
+    n = 1 << bin_e
+    plan = plan_dict(bin_e, tune_count=tc, peak_hold=peak, crop=0.1, rate=2500000)
+    w = port_oracle.window_coefs("blackman-harris", n)
+    g = scan_mod.GpuScan.from_plan(plan, window_coefs=w, ring_bytes=8 * b)   # tiny ring: many flushes
+    pinned = scan_mod.PinnedBuffer(6 * tc * b)
+    pending = {h: [] for h in range(tc)}
+
+    def check(h):
+        avg, smp, db = g.collect(h)
+        reads = np.array(pending[h], dtype=np.uint8).reshape(-1, b) if pending[h] else np.zeros((0, b), np.uint8)
+        one = dict(plan, tune_count=1)
+        want = expected(port_oracle, one, w, reads, np.zeros(len(reads), np.int32))
+        assert np.array_equal(avg, want[0][0]), h
+        assert smp == want[1][0]
+        if len(reads):
+            assert db_close(db, want[2][0])
+        pending[h] = []
+
+    try:
+        user_stream = torch.cuda.Stream()
+        for step in range(60):
+            op = rng.integers(0, 6)
+            if op == 0:      # single reads through the ring
+                for _ in range(rng.integers(1, 12)):
+                    h = int(rng.integers(0, tc))
+                    r = rng.integers(0, 256, b, dtype=np.uint8)
+                    g.submit(h, r)
+                    pending[h].append(r)
+            elif op == 1:    # pinned strided batch over a hop range
+                h0 = int(rng.integers(0, tc)); hc = int(rng.integers(1, tc - h0 + 1)); p = int(rng.integers(1, 7))
+                cube = pinned.view(np.uint8, (p, hc, b))
+                cube[:] = rng.integers(0, 256, (p, hc, b), dtype=np.uint8)
+                g.submit_batch(h0, hc, p, pinned.ptr, hc * b, b)
+                g.sync()     # the pinned block is reused by the next batch
+                for pi in range(p):
+                    for k in range(hc):
+                        pending[h0 + k].append(cube[pi, k].copy())
+            elif op == 2:    # device-resident batch
+                h0 = int(rng.integers(0, tc)); hc = int(rng.integers(1, tc - h0 + 1)); p = int(rng.integers(1, 5))
+                host = rng.integers(0, 256, (p, hc, b), dtype=np.uint8)
+                dev = torch.from_numpy(host).cuda()
+                torch.cuda.synchronize()
+                g.submit_device(h0, hc, p, dev.data_ptr(), hc * b, b)
+                g.sync()
+                for pi in range(p):
+                    for k in range(hc):
+                        pending[h0 + k].append(host[pi, k])
+            elif op == 3:
+                g.flush()
+            elif op == 4:
+                check(int(rng.integers(0, tc)))
+            else:            # move the handle to a caller stream and back
+                g.set_stream(user_stream.cuda_stream if step % 2 else None)
+        for h in range(tc):
+            check(h)
+    finally:
+        g.close()
