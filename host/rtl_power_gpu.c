@@ -24,6 +24,7 @@
  *   RTL_POWER_ASYNC     1 = fetch every hop visit through rtlsdr_read_async + callback
  *   RTL_POWER_PASSES    report after this many sweeps instead of by wall clock
  *   RTL_POWER_TIMESTAMP fixed "date, time" prefix (byte-reproducible output)
+ *   RTL_POWER_REPORTS   exit after this many reports (with RTL_POWER_PASSES: a fixed amount of work)
  *   RTLSDR_GPU_DEVICE   CUDA device ordinal
  */
 #include <math.h>
@@ -162,6 +163,7 @@ int main(int argc, char **argv)
 	const char *fixed_stamp = getenv("RTL_POWER_TIMESTAMP");
 	int opt, interval = 10, single = 0, peak_hold = 0, boxcar = 1, comp_fir_size = 0;
 	int passes_per_report = env_int("RTL_POWER_PASSES", 0), passes = 0, rc = 0, hop;
+	int max_reports = env_int("RTL_POWER_REPORTS", 0), reports = 0;
 	long exit_after = 0;
 	double crop = 0.0;
 	time_t next_tick, exit_time = 0, now;
@@ -321,7 +323,7 @@ int main(int argc, char **argv)
 			break;
 		while (time(NULL) >= next_tick)
 			next_tick += interval;
-		if (single)
+		if (single || (max_reports && ++reports >= max_reports))
 			break;
 		if (exit_time && time(NULL) >= exit_time)
 			break;

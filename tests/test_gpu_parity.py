@@ -467,3 +467,48 @@ def test_mixed_submission_paths_stress(scan_mod, port_oracle, peak):
             check(h)
     finally:
         g.close()
+
+
+@pytest.mark.parametrize("seed", list(range(24)))
+def test_random_configurations_fuzz(scan_mod, port_oracle, seed):
+    """random (bin_e, decimator, window, peak, crop, hop count, submission order) against the oracle"""
+    rng = np.random.default_rng(1000 + seed)
+    kind = rng.choice(["plain", "boxcar", "halfband", "rms", "large"], p=[0.35, 0.25, 0.2, 0.05, 0.15])
+    peak = int(rng.integers(0, 2))
+    tc = int(rng.integers(1, 6))
+    crop = float(rng.choice([0.0, 0.1, 0.33, 0.5]))
+    rate = int(rng.integers(900001, 2800000))
+    window = str(rng.choice(WINDOWS))
+    if kind == "plain":
+        bin_e = int(rng.integers(1, 13))
+        plan = plan_dict(bin_e, peak_hold=peak, tune_count=tc, crop=crop, rate=rate)
+    elif kind == "boxcar":
+        bin_e = int(rng.integers(1, 12))
+        ds = int(rng.integers(2, 200))
+        plan = plan_dict(bin_e, buf_len=max(16384, 2 * (1 << bin_e) * ds), downsample=ds, peak_hold=peak,
+                         tune_count=tc, crop=crop, rate=rate)
+    elif kind == "halfband":
+        bin_e = int(rng.integers(2, 11))
+        p = int(rng.integers(1, 10))
+        plan = plan_dict(bin_e, buf_len=max(16384, 2 * (1 << bin_e) << p), downsample=1 << p, downsample_passes=p,
+                         boxcar=0, comp_fir_size=int(rng.choice([0, 9])), peak_hold=peak, tune_count=tc, crop=crop,
+                         rate=rate)
+    elif kind == "rms":
+        bin_e = 0
+        plan = plan_dict(0, peak_hold=peak, tune_count=tc, crop=0.0, rate=rate)
+    else:
+        bin_e = int(rng.integers(13, 17))
+        plan = plan_dict(bin_e, buf_len=2 << bin_e, peak_hold=peak, tune_count=min(tc, 2), crop=crop, rate=rate)
+    n = 1 << plan["bin_e"]
+    w = port_oracle.window_coefs(window, n) if plan["bin_e"] else np.zeros(1, np.int32)
+    passes = int(rng.integers(1, 5))
+    mode, param = [(SYNTH_XORSHIFT, 0), (SYNTH_BIASED, int(rng.integers(-60, 60))), (SYNTH_TONE, int(rng.integers(20, 200))),
+                   (SYNTH_COUNTER, 0)][int(rng.integers(0, 4))]
+    reads, hops = make_reads(port_oracle.lib, plan, passes, mode, seed=seed, param=param)
+    order = rng.permutation(len(reads))            # hops arrive in any order
+    reads, hops = reads[order], hops[order]
+    want = expected(port_oracle, plan, w, reads, hops)
+    got = run_gpu(scan_mod, plan, w if plan["bin_e"] else None, reads, hops)
+    assert np.array_equal(got[0], want[0]), (kind, plan)
+    assert np.array_equal(got[1], want[1]), (kind, plan)
+    assert db_close(got[2], want[2]), (kind, plan)
