@@ -426,6 +426,55 @@ int launch_small(rtlsdr_gpu_scan *h, const SmallParams &prm, bool in16)
 	return RTLSDR_GPU_ERR_CONFIG;
 }
 
+template <int L, bool PEAK, int NS>
+int launch_fused_boxcar_t(rtlsdr_gpu_scan *h, const FusedBoxcarParams &prm)
+{
+	auto k = scan_boxcar_fused_kernel<L, PEAK, NS>;
+	const int smem = FusedSmem<L>::bytes(prm.ds, NS);
+	const int grid = std::min(prm.n_segs, h->num_sms * 8);
+	CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+	k<<<grid, kThreads, smem, h->stream>>>(prm);
+	h->last_was_epilogue = false;
+	return check_launch(h, "scan_boxcar_fused_kernel");
+}
+
+template <int L>
+int launch_fused_boxcar_l(rtlsdr_gpu_scan *h, const FusedBoxcarParams &prm_in)
+{
+	FusedBoxcarParams prm = prm_in;
+	/* deepest staging ring that still lets two CTAs share an SM (227 KiB, 1 KiB reserved per CTA) */
+	int slots = 4;
+	while (slots > 2 && 2 * (FusedSmem<L>::bytes(prm.ds, slots) + 1024) > 227 * 1024)
+		slots--;
+	prm.slots = slots;
+	const bool pk = h->cfg.peak_hold != 0;
+	switch (slots) {
+	case 4: return pk ? launch_fused_boxcar_t<L, true, 4>(h, prm) : launch_fused_boxcar_t<L, false, 4>(h, prm);
+	case 3: return pk ? launch_fused_boxcar_t<L, true, 3>(h, prm) : launch_fused_boxcar_t<L, false, 3>(h, prm);
+	default: return pk ? launch_fused_boxcar_t<L, true, 2>(h, prm) : launch_fused_boxcar_t<L, false, 2>(h, prm);
+	}
+}
+
+int launch_fused_boxcar(rtlsdr_gpu_scan *h, const FusedBoxcarParams &prm)
+{
+	switch (h->cfg.bin_e) {
+	case 8: return launch_fused_boxcar_l<8>(h, prm);
+	case 9: return launch_fused_boxcar_l<9>(h, prm);
+	case 10: return launch_fused_boxcar_l<10>(h, prm);
+	case 11: return launch_fused_boxcar_l<11>(h, prm);
+	case 12: return launch_fused_boxcar_l<12>(h, prm);
+	default: return RTLSDR_GPU_ERR_CONFIG;
+	}
+}
+
+/* narrow boxcar scans whose every read is exactly one FFT block: one fused kernel */
+bool fused_boxcar_ok(const rtlsdr_gpu_scan *h)
+{
+	const int ds = h->cfg.downsample;
+	return h->cfg.boxcar && ds >= 2 && ds <= 64 && h->cfg.bin_e >= 8 && h->cfg.bin_e <= 12 && h->n_blocks == 1 &&
+	       h->cfg.buf_len == 2 * h->N * ds && !getenv("RTLSDR_GPU_NO_FUSED_BOXCAR");
+}
+
 /*
  * Decimate entries [e0, e0+n) (u8 reads at base + d_offs[e]) into c16 images in
  * scratch and compute their DC sums.  Scratch layout for n entries:
@@ -649,6 +698,23 @@ int launch_batch(rtlsdr_gpu_scan *h, const uint8_t *base, const uint8_t *d_desc,
 		p.tw0 = h->tw0;
 		TimedScope ts(h);
 		return launch_small(h, p, false);
+	}
+
+	if (h->path == PATH_SMALL_DECIM && fused_boxcar_ok(h)) {
+		FusedBoxcarParams p;
+		memset(&p, 0, sizeof(p));
+		p.base = base;
+		p.read_off = d_offs;
+		p.segs = d_segs;
+		p.n_segs = n_segs;
+		p.ds = h->cfg.downsample;
+		p.avg = h->d_avg;
+		p.samples = h->d_smp64;
+		p.twc = h->d_twc;
+		p.win = h->d_win;
+		p.tw0 = h->tw0;
+		TimedScope ts(h);
+		return launch_fused_boxcar(h, p);
 	}
 
 	if (h->path == PATH_SMALL_DECIM) {

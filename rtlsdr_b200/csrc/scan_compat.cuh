@@ -49,6 +49,21 @@ SCAN_DEV void cp_async_wait_all()
 #endif
 }
 
+/* wait until at most `pending` of the most recently committed copy groups are still in flight */
+SCAN_DEV void cp_async_wait_pending(int pending)
+{
+#ifndef SCAN_EMU
+	switch (pending) {
+	case 0: asm volatile("cp.async.wait_group 0;\n" ::: "memory"); break;
+	case 1: asm volatile("cp.async.wait_group 1;\n" ::: "memory"); break;
+	case 2: asm volatile("cp.async.wait_group 2;\n" ::: "memory"); break;
+	default: asm volatile("cp.async.wait_group 3;\n" ::: "memory"); break;
+	}
+#else
+	(void)pending;
+#endif
+}
+
 /*
  * Programmatic dependent launch (sm_90+): a kernel launched with the
  * programmatic-stream-serialization attribute may start while the previous

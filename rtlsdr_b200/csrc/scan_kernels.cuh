@@ -1100,6 +1100,243 @@ dc_finalize_kernel(const SCAN_GRID_CONSTANT DcFinalizeParams prm)
 }
 
 /* ======================================================================== *
+ *  Narrow scans, fused: boxcar decimation + DC + window + FFT + |X|^2 in one *
+ *  kernel (the HBM-bound regime: 2*ds input bytes per transformed sample)    *
+ * ======================================================================== */
+
+struct FusedBoxcarParams {
+	const uint8_t *base;        /* u8 reads of 2 * N * ds bytes (one FFT block per read) */
+	const long long *read_off;
+	const int4 *segs;           /* (hop, first entry, entry count, -) */
+	int n_segs;
+	int ds;
+	int slots;                  /* staging ring depth, 2..4 chunks of 512 * ds bytes */
+	long long *avg;
+	long long *samples;
+	const int2 *twc;
+	const uint16_t *win;
+	PassTw tw0;
+};
+
+template <int L>
+struct FusedSmem {
+	static constexpr int N = 1 << L;
+	static constexpr int off_image = 0;                          /* 4096 c16 decimated samples */
+	static constexpr int off_xch = kWS * 4;                      /* two transpose buffers */
+	static constexpr int off_tw = off_xch + 2 * kXchWords * 4;
+	static constexpr int off_win = off_tw + (N - 16) * 8;
+	static constexpr int off_red = (off_win + N * 2 + 15) & ~15; /* [8 warps][2] long long */
+	static constexpr int off_stage = off_red + 128;              /* `slots` chunks of 512 * ds bytes */
+	static int bytes(int ds, int slots) { return off_stage + slots * 512 * ds; }
+};
+
+/*
+ * Requirements (checked by the host): boxcar, 2 <= ds <= 64, buf_len = 2 * N * ds (so every
+ * read is exactly one FFT block and remove_dc covers all of it), 256 <= N <= 4096.
+ * A CTA walks a segment of reads of one hop.  The input is streamed through two 512*ds-byte
+ * shared-memory slots with 16-byte cp.async copies (the next slot is in flight while the
+ * current one is summed); 256 slots of a chunk are summed per thread with IDP.4A (rtl_power.c
+ * :671-681 in closed form); 4096 / N reads fill the working set, each with its own DC average
+ * (rtl_power.c:581-596, 692-693); then the same register-blocked transform as scan_small_kernel.
+ */
+template <int L, bool PEAK, int NS>
+__global__ void __launch_bounds__(kThreads, 2)
+scan_boxcar_fused_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
+{
+	SCAN_DYN_SMEM(smem);
+	typedef FusedSmem<L> SM;
+	constexpr int N = 1 << L;
+	constexpr int RPW = kWS / N;      /* reads per working set */
+	constexpr int CPR = N / kThreads; /* 256-slot chunks per read */
+	c16 *image = (c16 *)(smem + SM::off_image);
+	c16 *xch = (c16 *)(smem + SM::off_xch);
+	int2 *tws = (int2 *)(smem + SM::off_tw);
+	uint16_t *wins = (uint16_t *)(smem + SM::off_win);
+	long long *red = (long long *)(smem + SM::off_red);
+	uint8_t *stage = smem + SM::off_stage;
+
+	const int t = threadIdx.x, ds = prm.ds;
+	const int chunk_bytes = 512 * ds;
+	for (int i = t; i < (N - 16) / 2; i += kThreads)
+		cp_async16((uint8_t *)tws + 16 * i, (const uint8_t *)prm.twc + 16 * i);
+	for (int i = t; i < N / 8; i += kThreads)
+		cp_async16((uint8_t *)wins + 16 * i, (const uint8_t *)prm.win + 16 * i);
+
+	TwSmall<L> tw;
+	tw.tws = tws;
+	tw.tw0 = &prm.tw0;
+	const int trev = brev_bits((unsigned)(t & ((1 << (L - 4)) - 1)), L - 4);
+	const int myblk = t >> (L - 4);
+	const int blkbase = myblk << L;
+	int flip = 0;
+
+	for (int seg = blockIdx.x; seg < prm.n_segs; seg += gridDim.x) {
+		const int4 sg = prm.segs[seg];
+		const int hop = sg.x, first = sg.y, count = sg.z;
+		const int total_chunks = count * CPR;
+		unsigned long long acc[kPts];
+#pragma unroll
+		for (int r = 0; r < kPts; ++r)
+			acc[r] = 0ull;
+
+		/* chunk q of the segment = chunk (q % CPR) of read first + q / CPR; a ring of `slots`
+		 * staging slots keeps slots-1 chunks in flight (one copy group per chunk, possibly empty) */
+		constexpr int ns = NS; /* compile time: slot index and wait depth cost no division / branch */
+#pragma unroll
+		for (int q0 = 0; q0 < ns - 1; ++q0) {
+			if (q0 < total_chunks) {
+				const uint8_t *src = prm.base + prm.read_off[first + q0 / CPR] + (long long)(q0 % CPR) * chunk_bytes;
+				uint8_t *dst = stage + (q0 % ns) * chunk_bytes;
+				for (int o = t * 16; o < chunk_bytes; o += kThreads * 16)
+					cp_async16(dst + o, src + o);
+			}
+			cp_async_commit();
+		}
+		int kI = 0, kQ = 0;
+		long long dI = 0, dQ = 0;
+		for (int q = 0; q < total_chunks; ++q) {
+			cp_async_wait_pending(NS - 2);
+			__syncthreads(); /* chunk q landed; the slot of chunk q-1 is free */
+			{
+				const int qn = q + ns - 1;
+				if (qn < total_chunks) {
+					const uint8_t *src = prm.base + prm.read_off[first + qn / CPR] + (long long)(qn % CPR) * chunk_bytes;
+					uint8_t *dst = stage + (qn % ns) * chunk_bytes;
+					for (int o = t * 16; o < chunk_bytes; o += kThreads * 16)
+						cp_async16(dst + o, src + o);
+				}
+				cp_async_commit();
+			}
+			const int rd = q / CPR;          /* read within the segment */
+			const int rw = rd % RPW;         /* read within the working set */
+			const int c = q % CPR;
+			/* ---- boxcar: slot = sum of ds samples, minus 127 each (rtl_power.c:666-681) ---- */
+			{
+				const uint8_t *p = stage + (q % ns) * chunk_bytes + t * 2 * ds;
+				unsigned ui = 0, uq = 0;
+				if ((ds & 1) == 0) {
+					int o = 0;
+					for (; o + 16 <= 2 * ds; o += 16) {
+						const unsigned w0 = *(const unsigned *)(p + o), w1 = *(const unsigned *)(p + o + 4),
+							       w2 = *(const unsigned *)(p + o + 8), w3 = *(const unsigned *)(p + o + 12);
+						ui = __dp4a(w0, 0x00010001u, ui); uq = __dp4a(w0, 0x01000100u, uq);
+						ui = __dp4a(w1, 0x00010001u, ui); uq = __dp4a(w1, 0x01000100u, uq);
+						ui = __dp4a(w2, 0x00010001u, ui); uq = __dp4a(w2, 0x01000100u, uq);
+						ui = __dp4a(w3, 0x00010001u, ui); uq = __dp4a(w3, 0x01000100u, uq);
+					}
+					for (; o < 2 * ds; o += 4) {
+						const unsigned w4 = *(const unsigned *)(p + o);
+						ui = __dp4a(w4, 0x00010001u, ui);
+						uq = __dp4a(w4, 0x01000100u, uq);
+					}
+				} else {
+					for (int o = 0; o < 2 * ds; o += 2) {
+						const unsigned raw = *(const uint16_t *)(p + o);
+						ui += raw & 0xFFu;
+						uq += raw >> 8;
+					}
+				}
+				const c16 v = c16_pack((int)ui - 127 * ds, (int)uq - 127 * ds);
+				image[rw * N + c * kThreads + t] = v;
+				dI += c16_re(v); /* remove_dc sums the wrapped int16 values */
+				dQ += c16_im(v);
+			}
+			if (c == CPR - 1) {
+				/* ---- the read is complete: its DC averages (divisors 2N and 2N-1) ---- */
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) {
+					dI += __shfl_xor_sync(0xffffffffu, dI, o);
+					dQ += __shfl_xor_sync(0xffffffffu, dQ, o);
+				}
+				long long *rr = red; /* the two barriers below order its reuse */
+				if ((t & 31) == 0) {
+					rr[(t >> 5) * 2] = dI;
+					rr[(t >> 5) * 2 + 1] = dQ;
+				}
+				__syncthreads();
+				if (myblk == rw) {
+					long long sI = 0, sQ = 0;
+#pragma unroll
+					for (int w = 0; w < kThreads / 32; ++w) {
+						sI += rr[2 * w];
+						sQ += rr[2 * w + 1];
+					}
+					kI = dc_average(sI, 2 * N);
+					kQ = dc_average(sQ, 2 * N - 1);
+				}
+				dI = dQ = 0;
+				__syncthreads(); /* red may be rewritten by the next read */
+			}
+			const bool ws_done = (c == CPR - 1) && (rw == RPW - 1 || rd == count - 1);
+			if (!ws_done)
+				continue;
+			const int nvalid = rw + 1;
+
+			/* ---- DC, window, bit-reversed placement, transform, |X|^2 ---- */
+			X2 x[kPts];
+#pragma unroll
+			for (int r = 0; r < kPts; ++r) {
+				const int nblk = (brev4(r) << (L - 4)) + trev;
+				const c16 raw = image[blkbase + nblk];
+				const int wv = wins[nblk];
+				x[r].re = ((c16_re(raw) - kI) * wv) << 16;
+				x[r].im = ((c16_im(raw) - kQ) * wv) << 16;
+			}
+			engine_fft_db<L>(x, xch, flip, t, tw);
+#pragma unroll
+			for (int r = 0; r < kPts; ++r) {
+				const int re = x[r].re >> 16, im = x[r].im >> 16;
+				const unsigned pw = (unsigned)(re * re) + (unsigned)(im * im);
+				if ((last_pos<L>(t, r) >> L) < nvalid) {
+					if constexpr (PEAK)
+						acc[r] = acc[r] > pw ? acc[r] : (unsigned long long)pw;
+					else
+						acc[r] += pw;
+				}
+			}
+			__syncthreads(); /* the image is rewritten by the next working set */
+		}
+
+		pdl_wait();
+		if (t == 0)
+			atomicAdd((unsigned long long *)(prm.samples + hop), (unsigned long long)((long long)count * ds));
+		long long *out = prm.avg + ((long long)hop << L);
+		if constexpr (L == 12) {
+#pragma unroll
+			for (int r = 0; r < kPts; ++r) {
+				const int bin = last_pos<L>(t, r) & (N - 1);
+				if constexpr (PEAK)
+					atomicMax(out + bin, (long long)acc[r]);
+				else
+					atomicAdd((unsigned long long *)(out + bin), acc[r]);
+			}
+		} else {
+			unsigned long long *bins = (unsigned long long *)xch; /* 2 * kXchWords * 4 >= N * 8 */
+			__syncthreads();
+			for (int i = t; i < N; i += kThreads)
+				bins[i] = 0ull;
+			__syncthreads();
+#pragma unroll
+			for (int r = 0; r < kPts; ++r) {
+				const int bin = last_pos<L>(t, r) & (N - 1);
+				if constexpr (PEAK)
+					atomicMax(bins + bin, acc[r]);
+				else
+					atomicAdd(bins + bin, acc[r]);
+			}
+			__syncthreads();
+			for (int i = t; i < N; i += kThreads) {
+				if constexpr (PEAK)
+					atomicMax(out + i, (long long)bins[i]);
+				else
+					atomicAdd((unsigned long long *)(out + i), bins[i]);
+			}
+			__syncthreads();
+		}
+	}
+}
+
+/* ======================================================================== *
  *  rms_power: 1-bin hops (rtl_power.c:410-436)                              *
  * ======================================================================== */
 

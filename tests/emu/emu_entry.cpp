@@ -307,6 +307,50 @@ void emu_level_stats(const uint8_t *reads, int n_reads, int buf_len, const int *
 	cuda_emu::launch(dim3(2), dim3(256), 0, [&]() { level_stats_kernel(p); });
 }
 
+/* fused boxcar + transform kernel: reads [n_reads][2*N*ds] */
+void emu_fused_boxcar(int L, int peak, const uint8_t *reads, int n_reads, int ds, int slots, const int *segs,
+		      int n_segs, const int *tw, const uint16_t *win, long long *avg, long long *samples)
+{
+	const int N = 1 << L;
+	std::vector<long long> offs(n_reads);
+	for (int i = 0; i < n_reads; i++)
+		offs[i] = (long long)i * 2 * N * ds;
+	FusedBoxcarParams p;
+	memset(&p, 0, sizeof(p));
+	p.base = reads;
+	p.read_off = offs.data();
+	p.segs = (const int4 *)segs;
+	p.n_segs = n_segs;
+	p.ds = ds;
+	p.slots = slots;
+	p.avg = avg;
+	p.samples = samples;
+	std::vector<int2> twc = compact_tw((const int2 *)tw, L);
+	p.twc = twc.data();
+	p.win = win;
+	fill_tw0(p.tw0, (const int2 *)tw, L);
+#define FBS(LV, PK, NSV)                                                                              \
+	cuda_emu::launch(dim3(n_segs), dim3(kThreads), FusedSmem<LV>::bytes(ds, NSV),                 \
+			 [&]() { scan_boxcar_fused_kernel<LV, PK, NSV>(p); })
+#define FB(LV)                                                                                        \
+	do {                                                                                          \
+		if (peak) {                                                                           \
+			if (slots == 4) FBS(LV, true, 4); else if (slots == 3) FBS(LV, true, 3); else FBS(LV, true, 2); \
+		} else {                                                                              \
+			if (slots == 4) FBS(LV, false, 4); else if (slots == 3) FBS(LV, false, 3); else FBS(LV, false, 2); \
+		}                                                                                     \
+	} while (0)
+	switch (L) {
+	case 8: FB(8); break;
+	case 9: FB(9); break;
+	case 10: FB(10); break;
+	case 11: FB(11); break;
+	case 12: FB(12); break;
+	}
+#undef FBS
+#undef FB
+}
+
 #include "emu_large.inl"
 
 } /* extern "C" */

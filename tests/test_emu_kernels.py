@@ -205,3 +205,26 @@ def test_level_stats_kernel(emu):
         b = reads[hop_of == h]
         assert level[h, 0] == np.count_nonzero((b == 0) | (b == 255))     # librtlsdr.c:3302
         assert level[h, 1] == np.count_nonzero((b < 64) | (b > 191))      # librtlsdr.c:3304
+
+
+@pytest.mark.parametrize("bin_e,ds,slots", [(8, 2, 2), (8, 13, 3), (9, 28, 4), (10, 28, 3), (10, 64, 2), (11, 5, 4), (12, 3, 3)])
+def test_fused_boxcar_kernel(emu, port_oracle, bin_e, ds, slots):
+    """boxcar + DC + window + FFT + |X|^2 in one kernel (narrow scans, one FFT block per read)"""
+    n = 1 << bin_e
+    buf_len = 2 * n * ds
+    for peak in (0, 1):
+        plan = plan_dict(bin_e, buf_len=buf_len, downsample=ds, tune_count=2, peak_hold=peak)
+        win = port_oracle.window_coefs("blackman", n)
+        reads, hops = make_reads(port_oracle.lib, plan, 5, SYNTH_BIASED, seed=bin_e + ds, param=35)
+        reads, hops = reads[:9], hops[:9]
+        reads[3, :] = 255
+        want, want_smp, _ = expected(port_oracle, plan, win, reads, hops)
+        sreads, _, segs = sort_by_hop(reads, hops, 2, split=2)
+        tw = twiddles(port_oracle.sine_table(bin_e), bin_e)
+        w16 = (win & 0xFFFF).astype(np.uint16)
+        avg = np.zeros((2, n), dtype=np.int64)
+        smp = np.zeros(2, dtype=np.int64)
+        emu.emu_fused_boxcar(bin_e, peak, vp(sreads), len(sreads), ds, slots, vp(segs), len(segs), vp(tw), vp(w16),
+                             vp(avg), vp(smp))
+        assert np.array_equal(avg, want), (bin_e, ds, peak)
+        assert np.array_equal(smp, want_smp)

@@ -512,3 +512,20 @@ def test_random_configurations_fuzz(scan_mod, port_oracle, seed):
     assert np.array_equal(got[0], want[0]), (kind, plan)
     assert np.array_equal(got[1], want[1]), (kind, plan)
     assert db_close(got[2], want[2]), (kind, plan)
+
+
+@pytest.mark.parametrize("bin_e,ds", [(8, 2), (8, 13), (9, 28), (10, 28), (10, 64), (11, 5), (12, 3), (12, 9)])
+@pytest.mark.parametrize("peak", [0, 1])
+def test_fused_boxcar_path(scan_mod, port_oracle, bin_e, ds, peak):
+    """narrow boxcar scans with one FFT block per read go through the single fused kernel"""
+    n = 1 << bin_e
+    plan = plan_dict(bin_e, buf_len=2 * n * ds, downsample=ds, tune_count=3, peak_hold=peak, crop=0.2)
+    w = port_oracle.window_coefs("hamming", n)
+    reads, hops = make_reads(port_oracle.lib, plan, 6, SYNTH_BIASED, seed=bin_e * 100 + ds, param=-25)
+    reads[4, :] = 255
+    reads[7, ::2] = 0
+    want = expected(port_oracle, plan, w, reads, hops)
+    got = run_gpu(scan_mod, plan, w, reads, hops)
+    assert np.array_equal(got[0], want[0])
+    assert np.array_equal(got[1], want[1])
+    assert db_close(got[2], want[2])
