@@ -442,17 +442,37 @@ template <int L>
 int launch_fused_boxcar_l(rtlsdr_gpu_scan *h, const FusedBoxcarParams &prm_in)
 {
 	FusedBoxcarParams prm = prm_in;
-	/* deepest staging ring that still lets two CTAs share an SM (227 KiB, 1 KiB reserved per CTA) */
-	int slots = 4;
-	while (slots > 2 && 2 * (FusedSmem<L>::bytes(prm.ds, slots) + 1024) > 227 * 1024)
-		slots--;
+	/*
+	 * Staging ring depth.  Two CTAs per SM (one streams while the other transforms) with 4 or
+	 * 3 slots each is the measured best; only when not even 3 slots fit twice (ds > ~40) one
+	 * CTA per SM with as many slots as fit takes over (measured at ds = 56: 274 -> 250 us;
+	 * at ds = 28 one CTA with 8 slots was slower than two with 3: 197 vs 130 us).
+	 */
+	const int limit = 227 * 1024 - 1024;
+	int slots;
+	if (2 * (FusedSmem<L>::bytes(prm.ds, 4) + 1024) <= 227 * 1024) {
+		slots = 4;
+	} else if (2 * (FusedSmem<L>::bytes(prm.ds, 3) + 1024) <= 227 * 1024) {
+		slots = 3;
+	} else {
+		const int fit = (limit - FusedSmem<L>::off_stage) / (512 * prm.ds);
+		slots = fit >= 12 ? 12 : fit >= 8 ? 8 : fit >= 6 ? 6 : fit >= 4 ? 4 : fit >= 3 ? 3 : 2;
+	}
 	prm.slots = slots;
 	const bool pk = h->cfg.peak_hold != 0;
+#define FUSED_CASE(NSV)                                                                               \
+	case NSV:                                                                                     \
+		return pk ? launch_fused_boxcar_t<L, true, NSV>(h, prm) : launch_fused_boxcar_t<L, false, NSV>(h, prm)
 	switch (slots) {
-	case 4: return pk ? launch_fused_boxcar_t<L, true, 4>(h, prm) : launch_fused_boxcar_t<L, false, 4>(h, prm);
-	case 3: return pk ? launch_fused_boxcar_t<L, true, 3>(h, prm) : launch_fused_boxcar_t<L, false, 3>(h, prm);
-	default: return pk ? launch_fused_boxcar_t<L, true, 2>(h, prm) : launch_fused_boxcar_t<L, false, 2>(h, prm);
+		FUSED_CASE(12);
+		FUSED_CASE(8);
+		FUSED_CASE(6);
+		FUSED_CASE(4);
+		FUSED_CASE(3);
+	default:
+		return pk ? launch_fused_boxcar_t<L, true, 2>(h, prm) : launch_fused_boxcar_t<L, false, 2>(h, prm);
 	}
+#undef FUSED_CASE
 }
 
 int launch_fused_boxcar(rtlsdr_gpu_scan *h, const FusedBoxcarParams &prm)

@@ -64,6 +64,14 @@ SCAN_DEV void cp_async_wait_pending(int pending)
 #endif
 }
 
+template <int PENDING>
+SCAN_DEV void cp_async_wait_group()
+{
+#ifndef SCAN_EMU
+	asm volatile("cp.async.wait_group %0;\n" ::"n"(PENDING) : "memory");
+#endif
+}
+
 /*
  * Programmatic dependent launch (sm_90+): a kernel launched with the
  * programmatic-stream-serialization attribute may start while the previous

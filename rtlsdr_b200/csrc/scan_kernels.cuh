@@ -1195,7 +1195,7 @@ scan_boxcar_fused_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
 		int kI = 0, kQ = 0;
 		long long dI = 0, dQ = 0;
 		for (int q = 0; q < total_chunks; ++q) {
-			cp_async_wait_pending(NS - 2);
+			cp_async_wait_group<NS - 2>();
 			__syncthreads(); /* chunk q landed; the slot of chunk q-1 is free */
 			{
 				const int qn = q + ns - 1;

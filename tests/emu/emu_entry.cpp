@@ -335,9 +335,9 @@ void emu_fused_boxcar(int L, int peak, const uint8_t *reads, int n_reads, int ds
 #define FB(LV)                                                                                        \
 	do {                                                                                          \
 		if (peak) {                                                                           \
-			if (slots == 4) FBS(LV, true, 4); else if (slots == 3) FBS(LV, true, 3); else FBS(LV, true, 2); \
+			if (slots == 12) FBS(LV, true, 12); else if (slots == 6) FBS(LV, true, 6); else if (slots == 4) FBS(LV, true, 4); else if (slots == 3) FBS(LV, true, 3); else FBS(LV, true, 2); \
 		} else {                                                                              \
-			if (slots == 4) FBS(LV, false, 4); else if (slots == 3) FBS(LV, false, 3); else FBS(LV, false, 2); \
+			if (slots == 12) FBS(LV, false, 12); else if (slots == 6) FBS(LV, false, 6); else if (slots == 4) FBS(LV, false, 4); else if (slots == 3) FBS(LV, false, 3); else FBS(LV, false, 2); \
 		}                                                                                     \
 	} while (0)
 	switch (L) {

@@ -207,7 +207,7 @@ def test_level_stats_kernel(emu):
         assert level[h, 1] == np.count_nonzero((b < 64) | (b > 191))      # librtlsdr.c:3304
 
 
-@pytest.mark.parametrize("bin_e,ds,slots", [(8, 2, 2), (8, 13, 3), (9, 28, 4), (10, 28, 3), (10, 64, 2), (11, 5, 4), (12, 3, 3)])
+@pytest.mark.parametrize("bin_e,ds,slots", [(8, 2, 2), (8, 13, 3), (9, 28, 12), (10, 28, 6), (10, 64, 2), (11, 5, 4), (12, 3, 3)])
 def test_fused_boxcar_kernel(emu, port_oracle, bin_e, ds, slots):
     """boxcar + DC + window + FFT + |X|^2 in one kernel (narrow scans, one FFT block per read)"""
     n = 1 << bin_e
