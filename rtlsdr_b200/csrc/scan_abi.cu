@@ -475,8 +475,70 @@ int launch_fused_boxcar_l(rtlsdr_gpu_scan *h, const FusedBoxcarParams &prm_in)
 #undef FUSED_CASE
 }
 
+/*
+ * Warp-specialised variant (producer / boxcar / transform roles, one CTA per SM).  Taken when
+ * the streaming side dominates: the single-role kernel's time is the SUM of its streaming and
+ * transform phases, this one's is their maximum.  Below ds ~ 12 the transform dominates and two
+ * single-role CTAs per SM (16 transform warps instead of 8) are faster.
+ * RTLSDR_GPU_BOXCAR_STREAM=0 / 1 forces the choice (A/B measurements, tests).
+ */
+constexpr int kStreamMinDs = 12;
+
+template <int L>
+int stream_boxcar_slots(int ds)
+{
+	const int fit = (227 * 1024 - StreamSmem<L>::off_stage) / (512 * ds);
+	return std::min(fit, kStreamMaxSlots);
+}
+
+template <int L>
+int launch_stream_boxcar_l(rtlsdr_gpu_scan *h, const FusedBoxcarParams &prm_in)
+{
+	FusedBoxcarParams prm = prm_in;
+	prm.slots = stream_boxcar_slots<L>(prm.ds);
+	const int smem = StreamSmem<L>::bytes(prm.ds, prm.slots);
+	const int grid = std::min(prm.n_segs, h->num_sms);
+	if (h->cfg.peak_hold) {
+		auto k = scan_boxcar_stream_kernel<L, true>;
+		CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		k<<<grid, kStreamThreads, smem, h->stream>>>(prm);
+	} else {
+		auto k = scan_boxcar_stream_kernel<L, false>;
+		CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		k<<<grid, kStreamThreads, smem, h->stream>>>(prm);
+	}
+	h->last_was_epilogue = false;
+	return check_launch(h, "scan_boxcar_stream_kernel");
+}
+
+template <int L>
+bool stream_boxcar_wanted(const rtlsdr_gpu_scan *h)
+{
+	const char *force = getenv("RTLSDR_GPU_BOXCAR_STREAM");
+	const int ds = h->cfg.downsample;
+	if (stream_boxcar_slots<L>(ds) < 3)
+		return false;
+	if (force)
+		return atoi(force) != 0;
+	return ds >= kStreamMinDs;
+}
+
 int launch_fused_boxcar(rtlsdr_gpu_scan *h, const FusedBoxcarParams &prm)
 {
+#define STREAM_CASE(LV)                                                                               \
+	case LV:                                                                                      \
+		if (stream_boxcar_wanted<LV>(h))                                                      \
+			return launch_stream_boxcar_l<LV>(h, prm);                                    \
+		break
+	switch (h->cfg.bin_e) {
+		STREAM_CASE(8);
+		STREAM_CASE(9);
+		STREAM_CASE(10);
+		STREAM_CASE(11);
+		STREAM_CASE(12);
+	default: break;
+	}
+#undef STREAM_CASE
 	switch (h->cfg.bin_e) {
 	case 8: return launch_fused_boxcar_l<8>(h, prm);
 	case 9: return launch_fused_boxcar_l<9>(h, prm);

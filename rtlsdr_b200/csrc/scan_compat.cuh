@@ -93,4 +93,104 @@ SCAN_DEV void pdl_launch_dependents()
 #endif
 }
 
+/*
+ * Transaction barriers (mbarrier), bulk asynchronous copies (the 1-D form of the
+ * TMA engine) and named barriers: the producer / consumer plumbing of the
+ * warp-specialised streaming kernel.  A wait on parity p returns once the phase
+ * with that parity has completed; waiting for parity 1 on a freshly initialised
+ * barrier returns at once (the "previous" phase counts as complete).
+ */
+SCAN_DEV void mbar_init(uint64_t *bar, int count)
+{
+#ifdef SCAN_EMU
+	::cuda_emu::mbar_init(bar, count);
+#else
+	unsigned s = (unsigned)__cvta_generic_to_shared(bar);
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(s), "r"(count) : "memory");
+#endif
+}
+
+/* make the initialised barriers visible to the async proxy (bulk copies) */
+SCAN_DEV void mbar_fence_init()
+{
+#ifndef SCAN_EMU
+	asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+	asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+#endif
+}
+
+SCAN_DEV void mbar_arrive(uint64_t *bar)
+{
+#ifdef SCAN_EMU
+	::cuda_emu::mbar_arrive(bar, 0);
+#else
+	unsigned s = (unsigned)__cvta_generic_to_shared(bar);
+	asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(s) : "memory");
+#endif
+}
+
+SCAN_DEV void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes)
+{
+#ifdef SCAN_EMU
+	::cuda_emu::mbar_arrive(bar, bytes);
+#else
+	unsigned s = (unsigned)__cvta_generic_to_shared(bar);
+	asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(s), "r"(bytes)
+		     : "memory");
+#endif
+}
+
+SCAN_DEV void mbar_wait(uint64_t *bar, unsigned parity)
+{
+#ifdef SCAN_EMU
+	::cuda_emu::mbar_wait(bar, parity);
+#else
+	unsigned s = (unsigned)__cvta_generic_to_shared(bar);
+	asm volatile("{\n"
+		     ".reg .pred p;\n"
+		     "MBAR_WAIT:\n"
+		     "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		     "@p bra MBAR_DONE;\n"
+		     "bra MBAR_WAIT;\n"
+		     "MBAR_DONE:\n"
+		     "}\n" ::"r"(s),
+		     "r"(parity)
+		     : "memory");
+#endif
+}
+
+/* global -> shared bulk copy (16-byte aligned, size a multiple of 16); completion is
+ * counted on `bar` as `bytes` transaction bytes */
+SCAN_DEV void bulk_copy_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar)
+{
+#ifdef SCAN_EMU
+	::cuda_emu::bulk_copy(smem_dst, gmem_src, bytes, bar);
+#else
+	unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+	unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(d),
+		     "l"(gmem_src), "r"(bytes), "r"(b)
+		     : "memory");
+#endif
+}
+
+/* barrier `id` (1..15) over `count` threads of the CTA (a multiple of 32) */
+SCAN_DEV void named_bar_sync(int id, int count)
+{
+#ifdef SCAN_EMU
+	::cuda_emu::named_bar_sync(id, count);
+#else
+	asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory");
+#endif
+}
+
+SCAN_DEV void warp_sync()
+{
+#ifdef SCAN_EMU
+	::cuda_emu::warp_sync();
+#else
+	__syncwarp();
+#endif
+}
+
 } // namespace rscan

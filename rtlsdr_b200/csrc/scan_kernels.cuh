@@ -194,15 +194,23 @@ SCAN_DEV void run_pass(X2 (&x)[kPts], int t, const TW &tw)
  * a buffer is rewritten only two exchanges later and the barrier of the
  * exchange in between already orders those accesses, so one barrier suffices.
  */
-template <int KA, int KB, bool LEAD>
+struct BlockBar { /* the 256 transform threads are the whole CTA */
+	static SCAN_DEV void sync() { __syncthreads(); }
+};
+template <int ID, int COUNT>
+struct GroupBar { /* the transform threads are one role of a warp-specialised CTA */
+	static SCAN_DEV void sync() { named_bar_sync(ID, COUNT); }
+};
+
+template <int KA, int KB, bool LEAD, class BAR = BlockBar>
 SCAN_DEV void exchange(X2 (&x)[kPts], c16 *xch, int t)
 {
 	if (LEAD)
-		__syncthreads();
+		BAR::sync();
 #pragma unroll
 	for (int r = 0; r < kPts; ++r)
 		xch[xch_idx(pos<KA>(t, r))] = x_pack(x[r]);
-	__syncthreads();
+	BAR::sync();
 #pragma unroll
 	for (int r = 0; r < kPts; ++r)
 		x[r] = x_unpack(xch[xch_idx(pos<KB>(t, r))]);
@@ -226,17 +234,17 @@ SCAN_DEV void engine_fft(X2 (&x)[kPts], c16 *xch, int t, const TW &tw)
 
 /* Same, with two transpose buffers of kXchWords each; `flip` is the running
  * exchange parity (uniform across the CTA, carried across working sets). */
-template <int LE, class TW>
+template <int LE, class TW, class BAR = BlockBar>
 SCAN_DEV void engine_fft_db(X2 (&x)[kPts], c16 *xch2, int &flip, int t, const TW &tw)
 {
 	run_pass<0, LE>(x, t, tw);
 	if constexpr (LE > 4) {
-		exchange<0, 1, false>(x, xch2 + flip * kXchWords, t);
+		exchange<0, 1, false, BAR>(x, xch2 + flip * kXchWords, t);
 		flip ^= 1;
 		run_pass<1, LE>(x, t, tw);
 	}
 	if constexpr (LE > 8) {
-		exchange<1, 2, false>(x, xch2 + flip * kXchWords, t);
+		exchange<1, 2, false, BAR>(x, xch2 + flip * kXchWords, t);
 		flip ^= 1;
 		run_pass<2, LE>(x, t, tw);
 	}
@@ -1332,6 +1340,336 @@ scan_boxcar_fused_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
 					atomicAdd((unsigned long long *)(out + i), bins[i]);
 			}
 			__syncthreads();
+		}
+	}
+}
+
+/*
+ * The same narrow-scan pipeline, warp specialised (one CTA per SM, three roles):
+ *   - warp 12, one lane: the producer.  It walks the CTA's segments and issues one
+ *     bulk asynchronous copy (cp.async.bulk, the TMA engine's 1-D form) per 512*ds-byte
+ *     chunk into a ring of `slots` shared-memory slots; full[]/empty[] transaction
+ *     barriers hand the slots back and forth.  The copies never stop while the other
+ *     roles compute, which the single-role kernel above cannot do (its CTAs alternate
+ *     between a streaming phase and a transform phase: measured time = sum of both).
+ *   - warps 8..11: the boxcar role.  256 output slots per chunk, two per thread, summed
+ *     from shared memory with IDP.4A (rtl_power.c:666-681 in closed form) into one of
+ *     TWO 4096-sample images; per read the DC averages (rtl_power.c:581-596, 692-693).
+ *   - warps 0..7: the transform role.  It waits for a complete image, applies DC and
+ *     window, hands the image back at once (img_empty) and runs the register-blocked
+ *     fix_fft + |X|^2 with its own named barrier while the other image fills.
+ * Same requirements as scan_boxcar_fused_kernel; the host picks this kernel when the
+ * streaming side dominates (large ds) and the ring fits.
+ */
+constexpr int kStreamFftThreads = kThreads;  /* 8 warps */
+constexpr int kStreamBoxThreads = 128;       /* 4 warps */
+constexpr int kStreamThreads = kStreamFftThreads + kStreamBoxThreads + 32;
+constexpr int kStreamMaxSlots = 16;
+
+template <int L>
+struct StreamSmem {
+	static constexpr int N = 1 << L;
+	static constexpr int off_image = 0;                          /* 2 x 4096 c16 */
+	static constexpr int off_xch = 2 * kWS * 4;                  /* two transpose buffers */
+	static constexpr int off_tw = off_xch + 2 * kXchWords * 4;
+	static constexpr int off_win = off_tw + (N - 16) * 8;
+	static constexpr int off_dc = (off_win + N * 2 + 15) & ~15;  /* [2 images][16 reads][2] int */
+	static constexpr int off_red = off_dc + 2 * 16 * 2 * 4;      /* [2][4 warps][2] int */
+	static constexpr int off_bar = off_red + 2 * 4 * 2 * 4;      /* full[16] empty[16] img_full[2] img_empty[2] */
+	static constexpr int off_stage = (off_bar + (2 * kStreamMaxSlots + 4) * 8 + 127) & ~127;
+	static int bytes(int ds, int slots) { return off_stage + slots * 512 * ds; }
+};
+
+/*
+ * Byte sums of two boxcar slots at once: I = bytes at even addresses, Q = bytes at odd
+ * addresses of [p0, p0 + nbytes) and [p1, p1 + nbytes); both pointers aligned to ALIGN,
+ * nbytes a multiple of ALIGN.  Eight independent IDP.4A chains and all loads of an
+ * iteration issued before they are consumed: the boxcar role is four warps only.
+ */
+template <int ALIGN>
+SCAN_DEV void boxcar_two_slot_sums(const uint8_t *p0, const uint8_t *p1, int nbytes, unsigned &i0, unsigned &q0,
+				   unsigned &i1, unsigned &q1)
+{
+	unsigned a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0, d0 = 0, d1 = 0;
+	if constexpr (ALIGN == 16) {
+#pragma unroll 2
+		for (int o = 0; o < nbytes; o += 16) {
+			const uint4 q = *(const uint4 *)(p0 + o), r = *(const uint4 *)(p1 + o);
+			a0 = __dp4a(q.x, 0x00010001u, a0); b0 = __dp4a(q.x, 0x01000100u, b0);
+			c0 = __dp4a(r.x, 0x00010001u, c0); d0 = __dp4a(r.x, 0x01000100u, d0);
+			a1 = __dp4a(q.y, 0x00010001u, a1); b1 = __dp4a(q.y, 0x01000100u, b1);
+			c1 = __dp4a(r.y, 0x00010001u, c1); d1 = __dp4a(r.y, 0x01000100u, d1);
+			a0 = __dp4a(q.z, 0x00010001u, a0); b0 = __dp4a(q.z, 0x01000100u, b0);
+			c0 = __dp4a(r.z, 0x00010001u, c0); d0 = __dp4a(r.z, 0x01000100u, d0);
+			a1 = __dp4a(q.w, 0x00010001u, a1); b1 = __dp4a(q.w, 0x01000100u, b1);
+			c1 = __dp4a(r.w, 0x00010001u, c1); d1 = __dp4a(r.w, 0x01000100u, d1);
+		}
+	} else if constexpr (ALIGN == 8) {
+#pragma unroll 4
+		for (int o = 0; o < nbytes; o += 8) {
+			const uint2 q = *(const uint2 *)(p0 + o), r = *(const uint2 *)(p1 + o);
+			a0 = __dp4a(q.x, 0x00010001u, a0); b0 = __dp4a(q.x, 0x01000100u, b0);
+			c0 = __dp4a(r.x, 0x00010001u, c0); d0 = __dp4a(r.x, 0x01000100u, d0);
+			a1 = __dp4a(q.y, 0x00010001u, a1); b1 = __dp4a(q.y, 0x01000100u, b1);
+			c1 = __dp4a(r.y, 0x00010001u, c1); d1 = __dp4a(r.y, 0x01000100u, d1);
+		}
+	} else if constexpr (ALIGN == 4) {
+#pragma unroll 4
+		for (int o = 0; o < nbytes; o += 4) {
+			const unsigned q = *(const unsigned *)(p0 + o), r = *(const unsigned *)(p1 + o);
+			a0 = __dp4a(q, 0x00010001u, a0); b0 = __dp4a(q, 0x01000100u, b0);
+			c0 = __dp4a(r, 0x00010001u, c0); d0 = __dp4a(r, 0x01000100u, d0);
+		}
+	} else {
+#pragma unroll 4
+		for (int o = 0; o < nbytes; o += 2) {
+			const unsigned q = *(const uint16_t *)(p0 + o), r = *(const uint16_t *)(p1 + o);
+			a0 += q & 0xFFu; b0 += q >> 8;
+			c0 += r & 0xFFu; d0 += r >> 8;
+		}
+	}
+	i0 = a0 + a1;
+	q0 = b0 + b1;
+	i1 = c0 + c1;
+	q1 = d0 + d1;
+}
+
+template <int L, bool PEAK>
+__global__ void __launch_bounds__(kStreamThreads, 1)
+scan_boxcar_stream_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
+{
+	SCAN_DYN_SMEM(smem);
+	typedef StreamSmem<L> SM;
+	constexpr int N = 1 << L;
+	constexpr int RPW = kWS / N;      /* reads per working set */
+	constexpr int CPR = N / kThreads; /* 256-slot chunks per read */
+	typedef GroupBar<1, kStreamFftThreads> FftBar;
+	c16 *image = (c16 *)(smem + SM::off_image);
+	c16 *xch = (c16 *)(smem + SM::off_xch);
+	int2 *tws = (int2 *)(smem + SM::off_tw);
+	uint16_t *wins = (uint16_t *)(smem + SM::off_win);
+	int *dc = (int *)(smem + SM::off_dc);
+	int *red = (int *)(smem + SM::off_red);
+	uint64_t *full = (uint64_t *)(smem + SM::off_bar);
+	uint64_t *empty = full + kStreamMaxSlots;
+	uint64_t *img_full = empty + kStreamMaxSlots;
+	uint64_t *img_empty = img_full + 2;
+	uint8_t *stage = smem + SM::off_stage;
+
+	const int t = threadIdx.x, ds = prm.ds, nslots = prm.slots;
+	const int chunk_bytes = 512 * ds;
+	if (t == 0) {
+		for (int s = 0; s < nslots; ++s) {
+			mbar_init(full + s, 1);
+			mbar_init(empty + s, kStreamBoxThreads / 32);
+		}
+		for (int b = 0; b < 2; ++b) {
+			mbar_init(img_full + b, kStreamBoxThreads);
+			mbar_init(img_empty + b, kStreamFftThreads);
+		}
+		mbar_fence_init();
+	}
+	__syncthreads();
+
+	if (t >= kStreamFftThreads + kStreamBoxThreads) {
+		/* ================= producer ================= */
+		if (t != kStreamFftThreads + kStreamBoxThreads)
+			return;
+		int slot = 0;
+		unsigned ph = 0;
+		for (int seg = blockIdx.x; seg < prm.n_segs; seg += gridDim.x) {
+			const int4 sg = prm.segs[seg];
+			long long off = prm.read_off[sg.y];
+			for (int rd = 0; rd < sg.z; ++rd) {
+				const uint8_t *src = prm.base + off;
+				if (rd + 1 < sg.z)
+					off = prm.read_off[sg.y + rd + 1]; /* in flight while this read's copies are issued */
+				for (int c = 0; c < CPR; ++c) {
+					mbar_wait(empty + slot, ph ^ 1u);
+					mbar_arrive_expect_tx(full + slot, (unsigned)chunk_bytes);
+					bulk_copy_g2s(stage + slot * chunk_bytes, src + (long long)c * chunk_bytes,
+						      (unsigned)chunk_bytes, full + slot);
+					if (++slot == nslots) {
+						slot = 0;
+						ph ^= 1u;
+					}
+				}
+			}
+		}
+		return;
+	}
+
+	if (t >= kStreamFftThreads) {
+		/* ================= boxcar role ================= */
+		const int bt = t - kStreamFftThreads;
+		int slot = 0, wsn = 0, par = 0;
+		unsigned ph = 0;
+		for (int seg = blockIdx.x; seg < prm.n_segs; seg += gridDim.x) {
+			const int4 sg = prm.segs[seg];
+			const int count = sg.z;
+			for (int rd = 0; rd < count; ++rd) {
+				const int rw = rd % RPW;
+				const int buf = wsn & 1;
+				if (rw == 0)
+					mbar_wait(img_empty + buf, ((unsigned)(wsn >> 1) & 1u) ^ 1u); /* transform role has read it */
+				c16 *img = image + buf * kWS + rw * N;
+				int dI = 0, dQ = 0; /* |sum| <= N * 32768 / threads: fits */
+				for (int c = 0; c < CPR; ++c) {
+					mbar_wait(full + slot, ph);
+					const uint8_t *p = stage + slot * chunk_bytes;
+					{
+						const uint8_t *p0 = p + bt * 2 * ds, *p1 = p0 + kStreamBoxThreads * 2 * ds;
+						unsigned i0, q0, i1, q1;
+						if ((ds & 7) == 0)
+							boxcar_two_slot_sums<16>(p0, p1, 2 * ds, i0, q0, i1, q1);
+						else if ((ds & 3) == 0)
+							boxcar_two_slot_sums<8>(p0, p1, 2 * ds, i0, q0, i1, q1);
+						else if ((ds & 1) == 0)
+							boxcar_two_slot_sums<4>(p0, p1, 2 * ds, i0, q0, i1, q1);
+						else
+							boxcar_two_slot_sums<2>(p0, p1, 2 * ds, i0, q0, i1, q1);
+						const c16 v0 = c16_pack((int)i0 - 127 * ds, (int)q0 - 127 * ds);
+						const c16 v1 = c16_pack((int)i1 - 127 * ds, (int)q1 - 127 * ds);
+						img[c * kThreads + bt] = v0;
+						img[c * kThreads + bt + kStreamBoxThreads] = v1;
+						dI += c16_re(v0) + c16_re(v1); /* remove_dc sums the wrapped int16 values */
+						dQ += c16_im(v0) + c16_im(v1);
+					}
+					warp_sync();
+					if ((bt & 31) == 0)
+						mbar_arrive(empty + slot); /* this warp is done with the slot */
+					if (++slot == nslots) {
+						slot = 0;
+						ph ^= 1u;
+					}
+				}
+				/* ---- the read is complete: its DC averages (divisors 2N and 2N-1) ---- */
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) {
+					dI += __shfl_xor_sync(0xffffffffu, dI, o);
+					dQ += __shfl_xor_sync(0xffffffffu, dQ, o);
+				}
+				int *rr = red + par * 8; /* alternating: rewritten two reads later, one barrier in between */
+				par ^= 1;
+				if ((bt & 31) == 0) {
+					rr[(bt >> 5) * 2] = dI;
+					rr[(bt >> 5) * 2 + 1] = dQ;
+				}
+				named_bar_sync(2, kStreamBoxThreads);
+				if (bt == 0) {
+					long long sI = 0, sQ = 0;
+#pragma unroll
+					for (int w = 0; w < kStreamBoxThreads / 32; ++w) {
+						sI += rr[2 * w];
+						sQ += rr[2 * w + 1];
+					}
+					dc[(buf * 16 + rw) * 2] = dc_average(sI, 2 * N);
+					dc[(buf * 16 + rw) * 2 + 1] = dc_average(sQ, 2 * N - 1);
+				}
+				if (rw == RPW - 1 || rd == count - 1) {
+					mbar_arrive(img_full + buf); /* release: image and averages are visible to the waiters */
+					++wsn;
+				}
+			}
+		}
+		return;
+	}
+
+	/* ================= transform role ================= */
+	for (int i = t; i < (N - 16) / 2; i += kThreads)
+		cp_async16((uint8_t *)tws + 16 * i, (const uint8_t *)prm.twc + 16 * i);
+	for (int i = t; i < N / 8; i += kThreads)
+		cp_async16((uint8_t *)wins + 16 * i, (const uint8_t *)prm.win + 16 * i);
+	cp_async_commit();
+	cp_async_wait_all();
+	FftBar::sync();
+
+	TwSmall<L> tw;
+	tw.tws = tws;
+	tw.tw0 = &prm.tw0;
+	const int trev = brev_bits((unsigned)(t & ((1 << (L - 4)) - 1)), L - 4);
+	const int myblk = t >> (L - 4);
+	const int blkbase = myblk << L;
+	int flip = 0, wsn = 0;
+
+	for (int seg = blockIdx.x; seg < prm.n_segs; seg += gridDim.x) {
+		const int4 sg = prm.segs[seg];
+		const int hop = sg.x, count = sg.z;
+		unsigned long long acc[kPts];
+#pragma unroll
+		for (int r = 0; r < kPts; ++r)
+			acc[r] = 0ull;
+
+		for (int rd0 = 0; rd0 < count; rd0 += RPW, ++wsn) {
+			const int nvalid = (count - rd0 < RPW) ? count - rd0 : RPW;
+			const int buf = wsn & 1;
+			mbar_wait(img_full + buf, (unsigned)(wsn >> 1) & 1u);
+			const c16 *img = image + buf * kWS;
+			const int kI = dc[(buf * 16 + myblk) * 2], kQ = dc[(buf * 16 + myblk) * 2 + 1];
+
+			/* ---- DC, window, bit-reversed placement ---- */
+			X2 x[kPts];
+#pragma unroll
+			for (int r = 0; r < kPts; ++r) {
+				const int nblk = (brev4(r) << (L - 4)) + trev;
+				const c16 raw = img[blkbase + nblk];
+				const int wv = wins[nblk];
+				x[r].re = ((c16_re(raw) - kI) * wv) << 16;
+				x[r].im = ((c16_im(raw) - kQ) * wv) << 16;
+			}
+			mbar_arrive(img_empty + buf); /* the boxcar role may refill this image */
+
+			engine_fft_db<L, TwSmall<L>, FftBar>(x, xch, flip, t, tw);
+#pragma unroll
+			for (int r = 0; r < kPts; ++r) {
+				const int re = x[r].re >> 16, im = x[r].im >> 16;
+				const unsigned pw = (unsigned)(re * re) + (unsigned)(im * im);
+				if ((last_pos<L>(t, r) >> L) < nvalid) {
+					if constexpr (PEAK)
+						acc[r] = acc[r] > pw ? acc[r] : (unsigned long long)pw;
+					else
+						acc[r] += pw;
+				}
+			}
+		}
+
+		pdl_wait();
+		if (t == 0)
+			atomicAdd((unsigned long long *)(prm.samples + hop), (unsigned long long)((long long)count * ds));
+		long long *out = prm.avg + ((long long)hop << L);
+		if constexpr (L == 12) {
+#pragma unroll
+			for (int r = 0; r < kPts; ++r) {
+				const int bin = last_pos<L>(t, r) & (N - 1);
+				if constexpr (PEAK)
+					atomicMax(out + bin, (long long)acc[r]);
+				else
+					atomicAdd((unsigned long long *)(out + bin), acc[r]);
+			}
+		} else {
+			/* both transpose buffers are idle here: every transform thread is past its last exchange
+			 * read once it has passed the first barrier below */
+			unsigned long long *bins = (unsigned long long *)xch; /* 2 * kXchWords * 4 >= N * 8 */
+			FftBar::sync();
+			for (int i = t; i < N; i += kThreads)
+				bins[i] = 0ull;
+			FftBar::sync();
+#pragma unroll
+			for (int r = 0; r < kPts; ++r) {
+				const int bin = last_pos<L>(t, r) & (N - 1);
+				if constexpr (PEAK)
+					atomicMax(bins + bin, acc[r]);
+				else
+					atomicAdd(bins + bin, acc[r]);
+			}
+			FftBar::sync();
+			for (int i = t; i < N; i += kThreads) {
+				if constexpr (PEAK)
+					atomicMax(out + i, (long long)bins[i]);
+				else
+					atomicAdd((unsigned long long *)(out + i), bins[i]);
+			}
+			FftBar::sync();
 		}
 	}
 }

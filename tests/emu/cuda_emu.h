@@ -16,7 +16,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -65,6 +67,79 @@ inline T shfl_idx(T v, unsigned src_lane)
 	return out;
 }
 
+
+/* ---- mbarrier / bulk copy / named barriers (functional model) ---- */
+struct EmuMbar {
+	int init = 0, pending = 0;
+	long long tx = 0;
+	unsigned phase = 0; /* parity of the phase in progress */
+};
+inline std::mutex g_mbar_mu;
+inline std::map<const void *, EmuMbar> g_mbar;
+inline std::map<int, std::unique_ptr<std::barrier<>>> g_named_bar;
+
+inline void mbar_settle(EmuMbar &m)
+{
+	if (m.pending == 0 && m.tx == 0) {
+		m.phase ^= 1u;
+		m.pending = m.init;
+	}
+}
+inline void mbar_init(const void *bar, int count)
+{
+	std::lock_guard<std::mutex> lk(g_mbar_mu);
+	EmuMbar m;
+	m.init = m.pending = count;
+	g_mbar[bar] = m;
+}
+inline void mbar_arrive(const void *bar, unsigned expect_bytes)
+{
+	std::lock_guard<std::mutex> lk(g_mbar_mu);
+	EmuMbar &m = g_mbar.at(bar);
+	m.tx += expect_bytes;
+	if (--m.pending < 0) {
+		fprintf(stderr, "cuda_emu: more arrivals than the mbarrier was initialised for\n");
+		abort();
+	}
+	mbar_settle(m);
+}
+inline void mbar_wait(const void *bar, unsigned parity)
+{
+	for (;;) {
+		{
+			std::lock_guard<std::mutex> lk(g_mbar_mu);
+			if (g_mbar.at(bar).phase != (parity & 1u))
+				return;
+		}
+		std::this_thread::yield();
+	}
+}
+inline void bulk_copy(void *d, const void *s, unsigned bytes, const void *bar)
+{
+	if (((uintptr_t)d & 15) || ((uintptr_t)s & 15) || (bytes & 15)) {
+		fprintf(stderr, "cuda_emu: cp.async.bulk with a misaligned address or size\n");
+		abort();
+	}
+	memcpy(d, s, bytes);
+	std::lock_guard<std::mutex> lk(g_mbar_mu);
+	EmuMbar &m = g_mbar.at(bar);
+	m.tx -= bytes;
+	mbar_settle(m);
+}
+inline void named_bar_sync(int id, int count)
+{
+	std::barrier<> *b;
+	{
+		std::lock_guard<std::mutex> lk(g_mbar_mu);
+		auto &slot = g_named_bar[id];
+		if (!slot)
+			slot.reset(new std::barrier<>((std::ptrdiff_t)count));
+		b = slot.get();
+	}
+	b->arrive_and_wait();
+}
+inline void warp_sync() { g_warp_bar[linear_tid() / 32]->arrive_and_wait(); }
+
 /* run `body` for every thread of every block; blocks are sequential */
 inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()> &body)
 {
@@ -83,6 +158,8 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function
 		g_warp_bar.emplace_back(new std::barrier<>((std::ptrdiff_t)cnt));
 	}
 	g_shfl.assign((size_t)nwarps * 32, 0);
+	g_mbar.clear();
+	g_named_bar.clear();
 	std::vector<std::thread> pool;
 	pool.reserve(nthreads);
 	for (unsigned tid = 0; tid < nthreads; tid++) {

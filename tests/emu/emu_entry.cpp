@@ -351,6 +351,47 @@ void emu_fused_boxcar(int L, int peak, const uint8_t *reads, int n_reads, int ds
 #undef FB
 }
 
+/* warp-specialised streaming variant of the same pipeline (producer / boxcar / transform roles) */
+void emu_stream_boxcar(int L, int peak, const uint8_t *reads, int n_reads, int ds, int slots, int grid, const int *segs,
+		       int n_segs, const int *tw, const uint16_t *win, long long *avg, long long *samples)
+{
+	const int N = 1 << L;
+	std::vector<long long> offs(n_reads);
+	for (int i = 0; i < n_reads; i++)
+		offs[i] = (long long)i * 2 * N * ds;
+	FusedBoxcarParams p;
+	memset(&p, 0, sizeof(p));
+	p.base = reads;
+	p.read_off = offs.data();
+	p.segs = (const int4 *)segs;
+	p.n_segs = n_segs;
+	p.ds = ds;
+	p.slots = slots;
+	p.avg = avg;
+	p.samples = samples;
+	std::vector<int2> twc = compact_tw((const int2 *)tw, L);
+	p.twc = twc.data();
+	p.win = win;
+	fill_tw0(p.tw0, (const int2 *)tw, L);
+#define SB(LV)                                                                                        \
+	do {                                                                                          \
+		if (peak)                                                                             \
+			cuda_emu::launch(dim3(grid), dim3(kStreamThreads), StreamSmem<LV>::bytes(ds, slots), \
+					 [&]() { scan_boxcar_stream_kernel<LV, true>(p); });          \
+		else                                                                                  \
+			cuda_emu::launch(dim3(grid), dim3(kStreamThreads), StreamSmem<LV>::bytes(ds, slots), \
+					 [&]() { scan_boxcar_stream_kernel<LV, false>(p); });         \
+	} while (0)
+	switch (L) {
+	case 8: SB(8); break;
+	case 9: SB(9); break;
+	case 10: SB(10); break;
+	case 11: SB(11); break;
+	case 12: SB(12); break;
+	}
+#undef SB
+}
+
 #include "emu_large.inl"
 
 } /* extern "C" */

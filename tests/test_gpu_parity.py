@@ -529,3 +529,24 @@ def test_fused_boxcar_path(scan_mod, port_oracle, bin_e, ds, peak):
     assert np.array_equal(got[0], want[0])
     assert np.array_equal(got[1], want[1])
     assert db_close(got[2], want[2])
+
+
+@pytest.mark.parametrize("bin_e,ds", [(8, 2), (8, 13), (8, 56), (9, 28), (10, 28), (10, 64), (11, 5), (11, 24), (12, 3), (12, 16)])
+@pytest.mark.parametrize("peak", [0, 1])
+@pytest.mark.parametrize("stream", ["0", "1"])
+def test_boxcar_stream_kernel_forced(scan_mod, port_oracle, monkeypatch, bin_e, ds, peak, stream):
+    """both narrow-scan kernels (single-role / warp-specialised producer-boxcar-transform) on the same inputs;
+    many short segments so that ring slots, image buffers and barrier phases wrap several times"""
+    monkeypatch.setenv("RTLSDR_GPU_BOXCAR_STREAM", stream)
+    n = 1 << bin_e
+    plan = plan_dict(bin_e, buf_len=2 * n * ds, downsample=ds, tune_count=2, peak_hold=peak, crop=0.1)
+    w = port_oracle.window_coefs("blackman-harris", n)
+    passes = 650  # 1300 reads -> ~300 segments of 4-5 reads, two per CTA of the one-CTA-per-SM kernel
+    reads, hops = make_reads(port_oracle.lib, plan, passes, SYNTH_BIASED, seed=bin_e * 1000 + ds, param=31)
+    reads[5, :] = 255
+    reads[8, 1::2] = 0
+    want = expected(port_oracle, plan, w, reads, hops)
+    got = run_gpu(scan_mod, plan, w, reads, hops, how="device")
+    assert np.array_equal(got[0], want[0])
+    assert np.array_equal(got[1], want[1])
+    assert db_close(got[2], want[2])

@@ -17,7 +17,10 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--range", required=True)
+    ap.add_argument("--range", default=None)
+    ap.add_argument("--boxcar", default=None, metavar="BIN_E:DS",
+                    help="narrow boxcar scan given directly (one hop, buf_len = 2 * 2^BIN_E * DS) instead of --range")
+    ap.add_argument("--hops", type=int, default=1, help="with --boxcar: hop count")
     ap.add_argument("-c", "--crop", type=float, default=0.0)
     ap.add_argument("-w", "--window", default="rectangle")
     ap.add_argument("-F", "--fir", type=int, default=None)
@@ -33,8 +36,13 @@ def main():
     import rtlsdr_b200.scan as rs
     from rtlsdr_b200.planner import plan_scan
 
-    plan = plan_scan(args.range, args.crop, args.fir)
-    pd = plan.as_dict()
+    if args.boxcar:
+        be, ds = (int(v) for v in args.boxcar.split(":"))
+        pd = dict(tune_count=args.hops, bin_e=be, buf_len=2 * (1 << be) * ds, downsample=ds, downsample_passes=0,
+                  boxcar=1, comp_fir_size=0, rate=2800000, crop=args.crop)
+        args.range = "boxcar " + args.boxcar
+    else:
+        pd = plan_scan(args.range, args.crop, args.fir).as_dict()
     pd["peak_hold"] = 1 if args.peak else 0
     tc, b, n = pd["tune_count"], pd["buf_len"], 1 << pd["bin_e"]
     g = rs.GpuScan.from_plan(pd, window_coefs=rs.window_coefs(args.window, n) if pd["bin_e"] else None)
