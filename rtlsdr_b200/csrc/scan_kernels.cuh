@@ -1346,15 +1346,17 @@ scan_boxcar_fused_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
 
 /*
  * The same narrow-scan pipeline, warp specialised (one CTA per SM, three roles):
- *   - warp 12, one lane: the producer.  It walks the CTA's segments and issues one
+ *   - warp 16, one lane: the producer.  It walks the CTA's segments and issues one
  *     bulk asynchronous copy (cp.async.bulk, the TMA engine's 1-D form) per 512*ds-byte
  *     chunk into a ring of `slots` shared-memory slots; full[]/empty[] transaction
  *     barriers hand the slots back and forth.  The copies never stop while the other
  *     roles compute, which the single-role kernel above cannot do (its CTAs alternate
  *     between a streaming phase and a transform phase: measured time = sum of both).
- *   - warps 8..11: the boxcar role.  256 output slots per chunk, two per thread, summed
- *     from shared memory with IDP.4A (rtl_power.c:666-681 in closed form) into one of
- *     TWO 4096-sample images; per read the DC averages (rtl_power.c:581-596, 692-693).
+ *   - warps 8..15: the boxcar role, two groups of four warps that take alternate chunks.
+ *     256 output slots per chunk, two per thread, summed from shared memory with IDP.4A
+ *     (rtl_power.c:666-681 in closed form) into one of TWO 4096-sample images; per read
+ *     the DC averages (rtl_power.c:581-596, 692-693).  (One group was the bottleneck:
+ *     a lone warp per scheduler runs this dependent code at 0.19 instructions per clock.)
  *   - warps 0..7: the transform role.  It waits for a complete image, applies DC and
  *     window, hands the image back at once (img_empty) and runs the register-blocked
  *     fix_fft + |X|^2 with its own named barrier while the other image fills.
@@ -1362,7 +1364,9 @@ scan_boxcar_fused_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
  * streaming side dominates (large ds) and the ring fits.
  */
 constexpr int kStreamFftThreads = kThreads;  /* 8 warps */
-constexpr int kStreamBoxThreads = 128;       /* 4 warps */
+constexpr int kStreamBoxGroup = 128;         /* 4 warps: two slots of a chunk per thread */
+constexpr int kStreamBoxGroups = 2;          /* the groups take alternate chunks */
+constexpr int kStreamBoxThreads = kStreamBoxGroup * kStreamBoxGroups;
 constexpr int kStreamThreads = kStreamFftThreads + kStreamBoxThreads + 32;
 constexpr int kStreamMaxSlots = 16;
 
@@ -1374,8 +1378,8 @@ struct StreamSmem {
 	static constexpr int off_tw = off_xch + 2 * kXchWords * 4;
 	static constexpr int off_win = off_tw + (N - 16) * 8;
 	static constexpr int off_dc = (off_win + N * 2 + 15) & ~15;  /* [2 images][16 reads][2] int */
-	static constexpr int off_red = off_dc + 2 * 16 * 2 * 4;      /* [2][4 warps][2] int */
-	static constexpr int off_bar = off_red + 2 * 4 * 2 * 4;      /* full[16] empty[16] img_full[2] img_empty[2] */
+	static constexpr int off_red = off_dc + 2 * 16 * 2 * 4;      /* [2][8 warps][2] int */
+	static constexpr int off_bar = off_red + 2 * 8 * 2 * 4;      /* full[16] empty[16] img_full[2] img_empty[2] */
 	static constexpr int off_stage = (off_bar + (2 * kStreamMaxSlots + 4) * 8 + 127) & ~127;
 	static int bytes(int ds, int slots) { return off_stage + slots * 512 * ds; }
 };
@@ -1461,7 +1465,7 @@ scan_boxcar_stream_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
 	if (t == 0) {
 		for (int s = 0; s < nslots; ++s) {
 			mbar_init(full + s, 1);
-			mbar_init(empty + s, kStreamBoxThreads / 32);
+			mbar_init(empty + s, kStreamBoxGroup / 32);
 		}
 		for (int b = 0; b < 2; ++b) {
 			mbar_init(img_full + b, kStreamBoxThreads);
@@ -1501,8 +1505,10 @@ scan_boxcar_stream_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
 
 	if (t >= kStreamFftThreads) {
 		/* ================= boxcar role ================= */
-		const int bt = t - kStreamFftThreads;
-		int slot = 0, wsn = 0, par = 0;
+		const int bt = (t - kStreamFftThreads) & (kStreamBoxGroup - 1); /* thread within its group */
+		const int grp = (t - kStreamFftThreads) / kStreamBoxGroup;
+		const int bw = (t - kStreamFftThreads) >> 5;                    /* warp within the role */
+		int slot = 0, wsn = 0, par = 0, seq = 0;
 		unsigned ph = 0;
 		for (int seg = blockIdx.x; seg < prm.n_segs; seg += gridDim.x) {
 			const int4 sg = prm.segs[seg];
@@ -1514,11 +1520,11 @@ scan_boxcar_stream_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
 					mbar_wait(img_empty + buf, ((unsigned)(wsn >> 1) & 1u) ^ 1u); /* transform role has read it */
 				c16 *img = image + buf * kWS + rw * N;
 				int dI = 0, dQ = 0; /* |sum| <= N * 32768 / threads: fits */
-				for (int c = 0; c < CPR; ++c) {
-					mbar_wait(full + slot, ph);
-					const uint8_t *p = stage + slot * chunk_bytes;
-					{
-						const uint8_t *p0 = p + bt * 2 * ds, *p1 = p0 + kStreamBoxThreads * 2 * ds;
+				for (int c = 0; c < CPR; ++c, ++seq) {
+					if ((seq & (kStreamBoxGroups - 1)) == grp) {
+						mbar_wait(full + slot, ph);
+						const uint8_t *p0 = stage + slot * chunk_bytes + bt * 2 * ds;
+						const uint8_t *p1 = p0 + kStreamBoxGroup * 2 * ds;
 						unsigned i0, q0, i1, q1;
 						if ((ds & 7) == 0)
 							boxcar_two_slot_sums<16>(p0, p1, 2 * ds, i0, q0, i1, q1);
@@ -1531,13 +1537,13 @@ scan_boxcar_stream_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
 						const c16 v0 = c16_pack((int)i0 - 127 * ds, (int)q0 - 127 * ds);
 						const c16 v1 = c16_pack((int)i1 - 127 * ds, (int)q1 - 127 * ds);
 						img[c * kThreads + bt] = v0;
-						img[c * kThreads + bt + kStreamBoxThreads] = v1;
+						img[c * kThreads + bt + kStreamBoxGroup] = v1;
 						dI += c16_re(v0) + c16_re(v1); /* remove_dc sums the wrapped int16 values */
 						dQ += c16_im(v0) + c16_im(v1);
+						warp_sync();
+						if ((bt & 31) == 0)
+							mbar_arrive(empty + slot); /* this warp is done with the slot */
 					}
-					warp_sync();
-					if ((bt & 31) == 0)
-						mbar_arrive(empty + slot); /* this warp is done with the slot */
 					if (++slot == nslots) {
 						slot = 0;
 						ph ^= 1u;
@@ -1549,14 +1555,14 @@ scan_boxcar_stream_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
 					dI += __shfl_xor_sync(0xffffffffu, dI, o);
 					dQ += __shfl_xor_sync(0xffffffffu, dQ, o);
 				}
-				int *rr = red + par * 8; /* alternating: rewritten two reads later, one barrier in between */
+				int *rr = red + par * 16; /* alternating: rewritten two reads later, one barrier in between */
 				par ^= 1;
 				if ((bt & 31) == 0) {
-					rr[(bt >> 5) * 2] = dI;
-					rr[(bt >> 5) * 2 + 1] = dQ;
+					rr[bw * 2] = dI;
+					rr[bw * 2 + 1] = dQ;
 				}
 				named_bar_sync(2, kStreamBoxThreads);
-				if (bt == 0) {
+				if (t == kStreamFftThreads) {
 					long long sI = 0, sQ = 0;
 #pragma unroll
 					for (int w = 0; w < kStreamBoxThreads / 32; ++w) {
