@@ -55,6 +55,22 @@ def read_traffic():
         return None
 
 
+def issue_roofline(kernel_ms, sm_mhz, n_sms):
+    """The bound this kernel actually runs against: warp instructions per clock per SM.  The instruction count
+    per launch comes from the committed ncu capture of the same workload (it does not depend on the input
+    bytes), the peak from tools/ubench.cu's measured dual-issue rate of a perfectly mixed IMAD + ALU stream."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            d = json.load(f)
+        inst = d["scan_small_kernel_warp_instructions_per_launch"]
+        peak = d["issue_peak_warp_instr_per_clk_per_sm"]
+        ipc = inst / (kernel_ms * 1e-3 * sm_mhz * 1e6 * n_sms)
+        return {"bound": "issue", "achieved": ipc, "peak": peak, "unit": "warp-instr/clk/SM", "frac": ipc / peak,
+                "warp_instructions_per_launch": inst, "sm_mhz": sm_mhz, "sms": n_sms, "peak_source": d["issue_peak_source"]}
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -432,6 +448,9 @@ def run_gpu(args):
             "gpu_launches": launches,
             "clocks": clocks,
         }
+        if k_n and clocks and clocks.get("sm_mhz"):
+            line["roofline"]["issue"] = issue_roofline(
+                k_avg_ms, clocks["sm_mhz"], torch.cuda.get_device_properties(0).multi_processor_count)
         if world == 1 and not args.no_companions:
             try:
                 line["companions"] = [

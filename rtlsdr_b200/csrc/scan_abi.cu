@@ -476,59 +476,70 @@ int launch_fused_boxcar_l(rtlsdr_gpu_scan *h, const FusedBoxcarParams &prm_in)
 }
 
 /*
- * Warp-specialised variant (producer / boxcar / transform roles, one CTA per SM).  Taken when
- * the streaming side dominates: the single-role kernel's time is the SUM of its streaming and
- * transform phases, this one's is their maximum.  Below ds ~ 12 the transform dominates and two
- * single-role CTAs per SM (16 transform warps instead of 8) are faster.
- * RTLSDR_GPU_BOXCAR_STREAM=0 / 1 forces the choice (A/B measurements, tests).
+ * Warp-specialised variant (producer / boxcar / transform roles, one CTA per SM).  The
+ * single-role kernel's time is the SUM of its streaming and transform phases, this one's is
+ * their maximum; measured faster for every ds >= 4 (ds = 28: 53 -> 72 % of the HBM copy peak).
+ * RTLSDR_GPU_BOXCAR_STREAM=0 / 1 / 2 / 3 forces the choice (A/B measurements, tests).
  */
-constexpr int kStreamMinDs = 12;
+constexpr int kStreamMinDs = 4;
+constexpr int kStreamOneFftGroupDs = 24; /* from here on one transform group keeps up and leaves its registers unspilled */
 
-template <int L>
+template <int L, int FG>
 int stream_boxcar_slots(int ds)
 {
-	const int fit = (227 * 1024 - StreamSmem<L>::off_stage) / (512 * ds);
+	const int fit = (227 * 1024 - StreamSmem<L, FG>::off_stage) / (512 * ds);
 	return std::min(fit, kStreamMaxSlots);
 }
 
-template <int L>
-int launch_stream_boxcar_l(rtlsdr_gpu_scan *h, const FusedBoxcarParams &prm_in)
+template <int L, bool PEAK, int FG, int BG>
+int launch_stream_boxcar_t(rtlsdr_gpu_scan *h, const FusedBoxcarParams &prm_in)
 {
 	FusedBoxcarParams prm = prm_in;
-	prm.slots = stream_boxcar_slots<L>(prm.ds);
-	const int smem = StreamSmem<L>::bytes(prm.ds, prm.slots);
+	prm.slots = stream_boxcar_slots<L, FG>(prm.ds);
+	const int smem = StreamSmem<L, FG>::bytes(prm.ds, prm.slots);
 	const int grid = std::min(prm.n_segs, h->num_sms);
-	if (h->cfg.peak_hold) {
-		auto k = scan_boxcar_stream_kernel<L, true>;
-		CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-		k<<<grid, kStreamThreads, smem, h->stream>>>(prm);
-	} else {
-		auto k = scan_boxcar_stream_kernel<L, false>;
-		CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-		k<<<grid, kStreamThreads, smem, h->stream>>>(prm);
-	}
+	auto k = scan_boxcar_stream_kernel<L, PEAK, FG, BG>;
+	CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+	k<<<grid, StreamShape<FG, BG>::threads, smem, h->stream>>>(prm);
 	h->last_was_epilogue = false;
 	return check_launch(h, "scan_boxcar_stream_kernel");
 }
 
+/* 0 = single-role kernel; transform groups + boxcar groups: 1 = 1 + 2, 2 = 2 + 1, 3 = 2 + 2 */
 template <int L>
-bool stream_boxcar_wanted(const rtlsdr_gpu_scan *h)
+int stream_boxcar_mode(const rtlsdr_gpu_scan *h)
 {
 	const char *force = getenv("RTLSDR_GPU_BOXCAR_STREAM");
 	const int ds = h->cfg.downsample;
-	if (stream_boxcar_slots<L>(ds) < 3)
-		return false;
+	/* measured on B200 (profiles/r01l_stream_modes.txt): N = 256 has one chunk per read and a DC reduction per
+	 * chunk, there a single boxcar group wins; otherwise two boxcar groups, and a second transform group below ds ~ 24 */
+	int mode = ds < kStreamMinDs ? 0 : L == 8 ? 2 : ds < kStreamOneFftGroupDs ? 3 : 1;
 	if (force)
-		return atoi(force) != 0;
-	return ds >= kStreamMinDs;
+		mode = atoi(force);
+	if (mode == 1 && stream_boxcar_slots<L, 1>(ds) < 3)
+		mode = 0;
+	if (mode >= 2 && stream_boxcar_slots<L, 2>(ds) < 3)
+		mode = 0;
+	return mode;
+}
+
+template <int L>
+int launch_stream_boxcar_l(rtlsdr_gpu_scan *h, const FusedBoxcarParams &prm, int mode)
+{
+	const bool pk = h->cfg.peak_hold != 0;
+	if (mode == 1)
+		return pk ? launch_stream_boxcar_t<L, true, 1, 2>(h, prm) : launch_stream_boxcar_t<L, false, 1, 2>(h, prm);
+	if (mode == 2)
+		return pk ? launch_stream_boxcar_t<L, true, 2, 1>(h, prm) : launch_stream_boxcar_t<L, false, 2, 1>(h, prm);
+	return pk ? launch_stream_boxcar_t<L, true, 2, 2>(h, prm) : launch_stream_boxcar_t<L, false, 2, 2>(h, prm);
 }
 
 int launch_fused_boxcar(rtlsdr_gpu_scan *h, const FusedBoxcarParams &prm)
 {
 #define STREAM_CASE(LV)                                                                               \
 	case LV:                                                                                      \
-		if (stream_boxcar_wanted<LV>(h))                                                      \
-			return launch_stream_boxcar_l<LV>(h, prm);                                    \
+		if (int mode = stream_boxcar_mode<LV>(h))                                             \
+			return launch_stream_boxcar_l<LV>(h, prm, mode);                              \
 		break
 	switch (h->cfg.bin_e) {
 		STREAM_CASE(8);

@@ -133,6 +133,19 @@ SCAN_DEV void butterfly_x_im(X2 &a, X2 &b, int wi)
 	a.im = hi + ti * 65536;
 }
 
+/* real_conj + accumulate / peak hold (rtl_power.c:636-640, 708-716) on a register accumulator;
+ * re^2 + im^2 <= 2^31 fits an unsigned 32-bit value.  (A mad.wide spelling with the 64-bit
+ * accumulator as addend is split again by ptxas into multiply + add-with-carry: no gain.) */
+template <bool PEAK>
+SCAN_DEV void accumulate_power(unsigned long long &acc, int re, int im)
+{
+	const unsigned pw = (unsigned)(re * re) + (unsigned)(im * im);
+	if constexpr (PEAK)
+		acc = acc > pw ? acc : (unsigned long long)pw;
+	else
+		acc += pw;
+}
+
 /* ---- working-set geometry ---------------------------------------------- */
 
 /* Position (0..4095) of register r of thread t while pass K is in registers:
@@ -195,22 +208,22 @@ SCAN_DEV void run_pass(X2 (&x)[kPts], int t, const TW &tw)
  * exchange in between already orders those accesses, so one barrier suffices.
  */
 struct BlockBar { /* the 256 transform threads are the whole CTA */
-	static SCAN_DEV void sync() { __syncthreads(); }
+	SCAN_DEV void sync() const { __syncthreads(); }
 };
-template <int ID, int COUNT>
-struct GroupBar { /* the transform threads are one role of a warp-specialised CTA */
-	static SCAN_DEV void sync() { named_bar_sync(ID, COUNT); }
+struct GroupBar { /* the transform threads are one role of a warp-specialised CTA: named barrier `id` */
+	int id, count;
+	SCAN_DEV void sync() const { named_bar_sync(id, count); }
 };
 
 template <int KA, int KB, bool LEAD, class BAR = BlockBar>
-SCAN_DEV void exchange(X2 (&x)[kPts], c16 *xch, int t)
+SCAN_DEV void exchange(X2 (&x)[kPts], c16 *xch, int t, const BAR &bar = BAR())
 {
 	if (LEAD)
-		BAR::sync();
+		bar.sync();
 #pragma unroll
 	for (int r = 0; r < kPts; ++r)
 		xch[xch_idx(pos<KA>(t, r))] = x_pack(x[r]);
-	BAR::sync();
+	bar.sync();
 #pragma unroll
 	for (int r = 0; r < kPts; ++r)
 		x[r] = x_unpack(xch[xch_idx(pos<KB>(t, r))]);
@@ -235,16 +248,16 @@ SCAN_DEV void engine_fft(X2 (&x)[kPts], c16 *xch, int t, const TW &tw)
 /* Same, with two transpose buffers of kXchWords each; `flip` is the running
  * exchange parity (uniform across the CTA, carried across working sets). */
 template <int LE, class TW, class BAR = BlockBar>
-SCAN_DEV void engine_fft_db(X2 (&x)[kPts], c16 *xch2, int &flip, int t, const TW &tw)
+SCAN_DEV void engine_fft_db(X2 (&x)[kPts], c16 *xch2, int &flip, int t, const TW &tw, const BAR &bar = BAR())
 {
 	run_pass<0, LE>(x, t, tw);
 	if constexpr (LE > 4) {
-		exchange<0, 1, false, BAR>(x, xch2 + flip * kXchWords, t);
+		exchange<0, 1, false, BAR>(x, xch2 + flip * kXchWords, t, bar);
 		flip ^= 1;
 		run_pass<1, LE>(x, t, tw);
 	}
 	if constexpr (LE > 8) {
-		exchange<1, 2, false, BAR>(x, xch2 + flip * kXchWords, t);
+		exchange<1, 2, false, BAR>(x, xch2 + flip * kXchWords, t, bar);
 		flip ^= 1;
 		run_pass<2, LE>(x, t, tw);
 	}
@@ -514,7 +527,6 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 #pragma unroll
 				for (int r = 0; r < kPts; ++r) {
 					const int re = x[r].re >> 16, im = x[r].im >> 16;
-					const unsigned pw = (unsigned)(re * re) + (unsigned)(im * im);
 					bool ok = true;
 					if constexpr (IN16) {
 						const int gb = u * (kWS / N) + (last_pos<L>(t, r) >> L);
@@ -522,12 +534,8 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 						if (prm.blocks_padded != prm.n_blocks)
 							ok = ok && (gb % prm.blocks_padded) < prm.n_blocks;
 					}
-					if (ok) {
-						if constexpr (PEAK)
-							acc[r] = acc[r] > pw ? acc[r] : (unsigned long long)pw;
-						else
-							acc[r] += pw;
-					}
+					if (ok)
+						accumulate_power<PEAK>(acc[r], re, im);
 				}
 			}
 		}
@@ -1294,13 +1302,8 @@ scan_boxcar_fused_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
 #pragma unroll
 			for (int r = 0; r < kPts; ++r) {
 				const int re = x[r].re >> 16, im = x[r].im >> 16;
-				const unsigned pw = (unsigned)(re * re) + (unsigned)(im * im);
-				if ((last_pos<L>(t, r) >> L) < nvalid) {
-					if constexpr (PEAK)
-						acc[r] = acc[r] > pw ? acc[r] : (unsigned long long)pw;
-					else
-						acc[r] += pw;
-				}
+				if ((last_pos<L>(t, r) >> L) < nvalid)
+					accumulate_power<PEAK>(acc[r], re, im);
 			}
 			__syncthreads(); /* the image is rewritten by the next working set */
 		}
@@ -1363,19 +1366,25 @@ scan_boxcar_fused_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
  * Same requirements as scan_boxcar_fused_kernel; the host picks this kernel when the
  * streaming side dominates (large ds) and the ring fits.
  */
-constexpr int kStreamFftThreads = kThreads;  /* 8 warps */
+constexpr int kStreamFftThreads = kThreads;  /* 8 warps per transform group */
 constexpr int kStreamBoxGroup = 128;         /* 4 warps: two slots of a chunk per thread */
-constexpr int kStreamBoxGroups = 2;          /* the groups take alternate chunks */
-constexpr int kStreamBoxThreads = kStreamBoxGroup * kStreamBoxGroups;
-constexpr int kStreamThreads = kStreamFftThreads + kStreamBoxThreads + 32;
 constexpr int kStreamMaxSlots = 16;
 
-template <int L>
+/* FG transform groups (alternate working sets), BG boxcar groups (alternate chunks):
+ * (1, 2) when the streaming side dominates, (2, 1) when the transform does (small ds). */
+template <int FG, int BG>
+struct StreamShape {
+	static constexpr int fft_threads = FG * kStreamFftThreads;
+	static constexpr int box_threads = BG * kStreamBoxGroup;
+	static constexpr int threads = fft_threads + box_threads + 32;
+};
+
+template <int L, int FG>
 struct StreamSmem {
 	static constexpr int N = 1 << L;
 	static constexpr int off_image = 0;                          /* 2 x 4096 c16 */
-	static constexpr int off_xch = 2 * kWS * 4;                  /* two transpose buffers */
-	static constexpr int off_tw = off_xch + 2 * kXchWords * 4;
+	static constexpr int off_xch = 2 * kWS * 4;                  /* two transpose buffers per transform group */
+	static constexpr int off_tw = off_xch + FG * 2 * kXchWords * 4;
 	static constexpr int off_win = off_tw + (N - 16) * 8;
 	static constexpr int off_dc = (off_win + N * 2 + 15) & ~15;  /* [2 images][16 reads][2] int */
 	static constexpr int off_red = off_dc + 2 * 16 * 2 * 4;      /* [2][8 warps][2] int */
@@ -1438,18 +1447,17 @@ SCAN_DEV void boxcar_two_slot_sums(const uint8_t *p0, const uint8_t *p1, int nby
 	q1 = d0 + d1;
 }
 
-template <int L, bool PEAK>
-__global__ void __launch_bounds__(kStreamThreads, 1)
+template <int L, bool PEAK, int FG, int BG>
+__global__ void __launch_bounds__((StreamShape<FG, BG>::threads), 1)
 scan_boxcar_stream_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
 {
 	SCAN_DYN_SMEM(smem);
-	typedef StreamSmem<L> SM;
+	typedef StreamSmem<L, FG> SM;
+	typedef StreamShape<FG, BG> SH;
 	constexpr int N = 1 << L;
 	constexpr int RPW = kWS / N;      /* reads per working set */
 	constexpr int CPR = N / kThreads; /* 256-slot chunks per read */
-	typedef GroupBar<1, kStreamFftThreads> FftBar;
 	c16 *image = (c16 *)(smem + SM::off_image);
-	c16 *xch = (c16 *)(smem + SM::off_xch);
 	int2 *tws = (int2 *)(smem + SM::off_tw);
 	uint16_t *wins = (uint16_t *)(smem + SM::off_win);
 	int *dc = (int *)(smem + SM::off_dc);
@@ -1468,16 +1476,16 @@ scan_boxcar_stream_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
 			mbar_init(empty + s, kStreamBoxGroup / 32);
 		}
 		for (int b = 0; b < 2; ++b) {
-			mbar_init(img_full + b, kStreamBoxThreads);
+			mbar_init(img_full + b, SH::box_threads);
 			mbar_init(img_empty + b, kStreamFftThreads);
 		}
 		mbar_fence_init();
 	}
 	__syncthreads();
 
-	if (t >= kStreamFftThreads + kStreamBoxThreads) {
+	if (t >= SH::fft_threads + SH::box_threads) {
 		/* ================= producer ================= */
-		if (t != kStreamFftThreads + kStreamBoxThreads)
+		if (t != SH::fft_threads + SH::box_threads)
 			return;
 		int slot = 0;
 		unsigned ph = 0;
@@ -1503,11 +1511,11 @@ scan_boxcar_stream_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
 		return;
 	}
 
-	if (t >= kStreamFftThreads) {
+	if (t >= SH::fft_threads) {
 		/* ================= boxcar role ================= */
-		const int bt = (t - kStreamFftThreads) & (kStreamBoxGroup - 1); /* thread within its group */
-		const int grp = (t - kStreamFftThreads) / kStreamBoxGroup;
-		const int bw = (t - kStreamFftThreads) >> 5;                    /* warp within the role */
+		const int bt = (t - SH::fft_threads) & (kStreamBoxGroup - 1); /* thread within its group */
+		const int grp = (t - SH::fft_threads) / kStreamBoxGroup;
+		const int bw = (t - SH::fft_threads) >> 5;                    /* warp within the role */
 		int slot = 0, wsn = 0, par = 0, seq = 0;
 		unsigned ph = 0;
 		for (int seg = blockIdx.x; seg < prm.n_segs; seg += gridDim.x) {
@@ -1521,7 +1529,7 @@ scan_boxcar_stream_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
 				c16 *img = image + buf * kWS + rw * N;
 				int dI = 0, dQ = 0; /* |sum| <= N * 32768 / threads: fits */
 				for (int c = 0; c < CPR; ++c, ++seq) {
-					if ((seq & (kStreamBoxGroups - 1)) == grp) {
+					if ((seq & (BG - 1)) == grp) {
 						mbar_wait(full + slot, ph);
 						const uint8_t *p0 = stage + slot * chunk_bytes + bt * 2 * ds;
 						const uint8_t *p1 = p0 + kStreamBoxGroup * 2 * ds;
@@ -1561,11 +1569,11 @@ scan_boxcar_stream_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
 					rr[bw * 2] = dI;
 					rr[bw * 2 + 1] = dQ;
 				}
-				named_bar_sync(2, kStreamBoxThreads);
-				if (t == kStreamFftThreads) {
+				named_bar_sync(4, SH::box_threads);
+				if (t == SH::fft_threads) {
 					long long sI = 0, sQ = 0;
 #pragma unroll
-					for (int w = 0; w < kStreamBoxThreads / 32; ++w) {
+					for (int w = 0; w < SH::box_threads / 32; ++w) {
 						sI += rr[2 * w];
 						sQ += rr[2 * w + 1];
 					}
@@ -1582,21 +1590,25 @@ scan_boxcar_stream_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
 	}
 
 	/* ================= transform role ================= */
-	for (int i = t; i < (N - 16) / 2; i += kThreads)
+	/* group fg takes the working sets with number = fg (mod FG); its threads are tf = 0..255 */
+	const int fg = t / kStreamFftThreads, tf = t % kStreamFftThreads;
+	c16 *xch = (c16 *)(smem + SM::off_xch) + fg * 2 * kXchWords;
+	for (int i = t; i < (N - 16) / 2; i += SH::fft_threads)
 		cp_async16((uint8_t *)tws + 16 * i, (const uint8_t *)prm.twc + 16 * i);
-	for (int i = t; i < N / 8; i += kThreads)
+	for (int i = t; i < N / 8; i += SH::fft_threads)
 		cp_async16((uint8_t *)wins + 16 * i, (const uint8_t *)prm.win + 16 * i);
 	cp_async_commit();
 	cp_async_wait_all();
-	FftBar::sync();
+	named_bar_sync(3, SH::fft_threads); /* tables complete for every transform thread */
 
 	TwSmall<L> tw;
 	tw.tws = tws;
 	tw.tw0 = &prm.tw0;
-	const int trev = brev_bits((unsigned)(t & ((1 << (L - 4)) - 1)), L - 4);
-	const int myblk = t >> (L - 4);
+	const int trev = brev_bits((unsigned)(tf & ((1 << (L - 4)) - 1)), L - 4);
+	const int myblk = tf >> (L - 4);
 	const int blkbase = myblk << L;
 	int flip = 0, wsn = 0;
+	const GroupBar fft_bar = { 1 + fg, kStreamFftThreads };
 
 	for (int seg = blockIdx.x; seg < prm.n_segs; seg += gridDim.x) {
 		const int4 sg = prm.segs[seg];
@@ -1607,6 +1619,8 @@ scan_boxcar_stream_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
 			acc[r] = 0ull;
 
 		for (int rd0 = 0; rd0 < count; rd0 += RPW, ++wsn) {
+			if (FG > 1 && (wsn & (FG - 1)) != fg)
+				continue;
 			const int nvalid = (count - rd0 < RPW) ? count - rd0 : RPW;
 			const int buf = wsn & 1;
 			mbar_wait(img_full + buf, (unsigned)(wsn >> 1) & 1u);
@@ -1625,17 +1639,12 @@ scan_boxcar_stream_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
 			}
 			mbar_arrive(img_empty + buf); /* the boxcar role may refill this image */
 
-			engine_fft_db<L, TwSmall<L>, FftBar>(x, xch, flip, t, tw);
+			engine_fft_db<L, TwSmall<L>, GroupBar>(x, xch, flip, tf, tw, fft_bar);
 #pragma unroll
 			for (int r = 0; r < kPts; ++r) {
 				const int re = x[r].re >> 16, im = x[r].im >> 16;
-				const unsigned pw = (unsigned)(re * re) + (unsigned)(im * im);
-				if ((last_pos<L>(t, r) >> L) < nvalid) {
-					if constexpr (PEAK)
-						acc[r] = acc[r] > pw ? acc[r] : (unsigned long long)pw;
-					else
-						acc[r] += pw;
-				}
+				if ((last_pos<L>(tf, r) >> L) < nvalid)
+					accumulate_power<PEAK>(acc[r], re, im);
 			}
 		}
 
@@ -1646,7 +1655,7 @@ scan_boxcar_stream_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
 		if constexpr (L == 12) {
 #pragma unroll
 			for (int r = 0; r < kPts; ++r) {
-				const int bin = last_pos<L>(t, r) & (N - 1);
+				const int bin = last_pos<L>(tf, r) & (N - 1);
 				if constexpr (PEAK)
 					atomicMax(out + bin, (long long)acc[r]);
 				else
@@ -1656,26 +1665,26 @@ scan_boxcar_stream_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
 			/* both transpose buffers are idle here: every transform thread is past its last exchange
 			 * read once it has passed the first barrier below */
 			unsigned long long *bins = (unsigned long long *)xch; /* 2 * kXchWords * 4 >= N * 8 */
-			FftBar::sync();
-			for (int i = t; i < N; i += kThreads)
+			fft_bar.sync();
+			for (int i = tf; i < N; i += kThreads)
 				bins[i] = 0ull;
-			FftBar::sync();
+			fft_bar.sync();
 #pragma unroll
 			for (int r = 0; r < kPts; ++r) {
-				const int bin = last_pos<L>(t, r) & (N - 1);
+				const int bin = last_pos<L>(tf, r) & (N - 1);
 				if constexpr (PEAK)
 					atomicMax(bins + bin, acc[r]);
 				else
 					atomicAdd(bins + bin, acc[r]);
 			}
-			FftBar::sync();
-			for (int i = t; i < N; i += kThreads) {
+			fft_bar.sync();
+			for (int i = tf; i < N; i += kThreads) {
 				if constexpr (PEAK)
 					atomicMax(out + i, (long long)bins[i]);
 				else
 					atomicAdd((unsigned long long *)(out + i), bins[i]);
 			}
-			FftBar::sync();
+			fft_bar.sync();
 		}
 	}
 }

@@ -377,11 +377,7 @@ large_round_c_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
 #pragma unroll
 		for (int r = 0; r < R; ++r) {
 			const int re = c16_re(v[r]), im = c16_im(v[r]);
-			const unsigned pw = (unsigned)(re * re) + (unsigned)(im * im);
-			if (PEAK)
-				acc[r] = acc[r] > pw ? acc[r] : (unsigned long long)pw;
-			else
-				acc[r] += pw;
+			accumulate_power<PEAK>(acc[r], re, im);
 		}
 	}
 }

@@ -352,7 +352,7 @@ void emu_fused_boxcar(int L, int peak, const uint8_t *reads, int n_reads, int ds
 }
 
 /* warp-specialised streaming variant of the same pipeline (producer / boxcar / transform roles) */
-void emu_stream_boxcar(int L, int peak, const uint8_t *reads, int n_reads, int ds, int slots, int grid, const int *segs,
+void emu_stream_boxcar(int L, int peak, int mode, const uint8_t *reads, int n_reads, int ds, int slots, int grid, const int *segs,
 		       int n_segs, const int *tw, const uint16_t *win, long long *avg, long long *samples)
 {
 	const int N = 1 << L;
@@ -373,14 +373,16 @@ void emu_stream_boxcar(int L, int peak, const uint8_t *reads, int n_reads, int d
 	p.twc = twc.data();
 	p.win = win;
 	fill_tw0(p.tw0, (const int2 *)tw, L);
+#define SBM(LV, PK, FG, BG)                                                                           \
+	cuda_emu::launch(dim3(grid), dim3(StreamShape<FG, BG>::threads), StreamSmem<LV, FG>::bytes(ds, slots), \
+			 [&]() { scan_boxcar_stream_kernel<LV, PK, FG, BG>(p); })
 #define SB(LV)                                                                                        \
 	do {                                                                                          \
-		if (peak)                                                                             \
-			cuda_emu::launch(dim3(grid), dim3(kStreamThreads), StreamSmem<LV>::bytes(ds, slots), \
-					 [&]() { scan_boxcar_stream_kernel<LV, true>(p); });          \
-		else                                                                                  \
-			cuda_emu::launch(dim3(grid), dim3(kStreamThreads), StreamSmem<LV>::bytes(ds, slots), \
-					 [&]() { scan_boxcar_stream_kernel<LV, false>(p); });         \
+		if (mode == 1) {                                                                      \
+			if (peak) SBM(LV, true, 1, 2); else SBM(LV, false, 1, 2);                     \
+		} else {                                                                              \
+			if (peak) SBM(LV, true, 2, 1); else SBM(LV, false, 2, 1);                     \
+		}                                                                                     \
 	} while (0)
 	switch (L) {
 	case 8: SB(8); break;
@@ -390,6 +392,7 @@ void emu_stream_boxcar(int L, int peak, const uint8_t *reads, int n_reads, int d
 	case 12: SB(12); break;
 	}
 #undef SB
+#undef SBM
 }
 
 #include "emu_large.inl"

@@ -232,15 +232,17 @@ def test_fused_boxcar_kernel(emu, port_oracle, bin_e, ds, slots):
 
 @pytest.mark.parametrize("bin_e,ds,slots,grid", [(8, 2, 3, 1), (8, 13, 16, 2), (9, 28, 5, 3), (10, 28, 10, 2), (10, 64, 3, 1),
                                                  (11, 5, 4, 2), (12, 3, 3, 2), (12, 12, 8, 1)])
-def test_stream_boxcar_kernel(emu, port_oracle, bin_e, ds, slots, grid):
+@pytest.mark.parametrize("mode", [1, 2])
+def test_stream_boxcar_kernel(emu, port_oracle, bin_e, ds, slots, grid, mode):
     """warp-specialised narrow-scan kernel: bulk-copy producer, boxcar warps, transform warps (mbarrier hand-offs)"""
     n = 1 << bin_e
     buf_len = 2 * n * ds
     for peak in (0, 1):
         plan = plan_dict(bin_e, buf_len=buf_len, downsample=ds, tune_count=2, peak_hold=peak)
         win = port_oracle.window_coefs("blackman", n)
-        reads, hops = make_reads(port_oracle.lib, plan, 5, SYNTH_BIASED, seed=bin_e + ds, param=35)
-        reads, hops = reads[:9], hops[:9]
+        passes = 5 if n * ds > 4096 else 40   # small reads: several working sets per segment
+        reads, hops = make_reads(port_oracle.lib, plan, passes, SYNTH_BIASED, seed=bin_e + ds, param=35)
+        reads, hops = reads[:2 * passes - 1], hops[:2 * passes - 1]
         reads[3, :] = 255
         want, want_smp, _ = expected(port_oracle, plan, win, reads, hops)
         sreads, _, segs = sort_by_hop(reads, hops, 2, split=2)
@@ -248,7 +250,7 @@ def test_stream_boxcar_kernel(emu, port_oracle, bin_e, ds, slots, grid):
         w16 = (win & 0xFFFF).astype(np.uint16)
         avg = np.zeros((2, n), dtype=np.int64)
         smp = np.zeros(2, dtype=np.int64)
-        emu.emu_stream_boxcar(bin_e, peak, vp(sreads), len(sreads), ds, slots, grid, vp(segs), len(segs), vp(tw), vp(w16),
+        emu.emu_stream_boxcar(bin_e, peak, mode, vp(sreads), len(sreads), ds, slots, grid, vp(segs), len(segs), vp(tw), vp(w16),
                               vp(avg), vp(smp))
         assert np.array_equal(avg, want), (bin_e, ds, peak)
         assert np.array_equal(smp, want_smp)
