@@ -661,15 +661,50 @@ int run_decimators(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_o
 		/* level-0 span of a tile: (tile + 9) * 2^P + 5 * (2^P - 1) + 9 samples at most */
 		int tile = std::min(256, std::max(8, (kChainCap0 >> passes) - 16));
 		tile = std::min(tile, M);
+		/* P <= 5: the register-streaming kernel computes final samples >= 16, the tile kernel only
+		 * the eased-in head [0, 16) of every read (RTLSDR_GPU_NO_HB_STREAM=1: tile kernel for all) */
+		const bool stream = passes <= kHbStreamMaxPasses && M >= 2 * kHbStreamHead && !getenv("RTLSDR_GPU_NO_HB_STREAM");
+		if (stream)
+			tile = kHbStreamHead;
 		p.tile = tile;
 		p.cap0 = kChainCap0;
 		const int smem = (kChainCap0 + kChainCap0 / 2 + 16) * 4;
 		CU(cudaFuncSetAttribute(halfband_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 		CU(cudaMemsetAsync(sc.sums, 0, (size_t)n * 16, h->stream));
-		dim3 grid((M + tile - 1) / tile, n);
+		dim3 grid(stream ? 1 : (M + tile - 1) / tile, n);
 		halfband_chain_kernel<<<grid, 256, smem, h->stream>>>(p);
 		if ((rc = check_launch(h, "halfband_chain_kernel")))
 			return rc;
+		if (stream) {
+			HalfbandStreamParams q;
+			q.base = base;
+			q.read_off = d_offs;
+			q.n_reads = n;
+			q.pairs = pairs;
+			q.use_fir = p.use_fir;
+			q.f1 = p.f1; q.f2 = p.f2; q.f3 = p.f3; q.f4 = p.f4; q.f5 = p.f5;
+			q.out = sc.img;
+			q.out_stride = h->image_stride;
+			q.l_len = h->l_len;
+			q.sums = sc.sums;
+			/* span: as long as possible (16 warm-up samples per span are recomputed) while the grid
+			 * still offers about one resident wave of threads (512 per SM at <= 128 registers) */
+			int span = M;
+			while (span > 64 && (long long)n * ((M + span - 1) / span) < (long long)h->num_sms * 512)
+				span /= 2;
+			q.span = span;
+			const long long threads = (long long)n * ((M + span - 1) / span);
+			const int blocks = (int)((threads + 127) / 128);
+			switch (passes) {
+			case 1: halfband_stream_kernel<1><<<blocks, 128, 0, h->stream>>>(q); break;
+			case 2: halfband_stream_kernel<2><<<blocks, 128, 0, h->stream>>>(q); break;
+			case 3: halfband_stream_kernel<3><<<blocks, 128, 0, h->stream>>>(q); break;
+			case 4: halfband_stream_kernel<4><<<blocks, 128, 0, h->stream>>>(q); break;
+			default: halfband_stream_kernel<5><<<blocks, 128, 0, h->stream>>>(q); break;
+			}
+			if ((rc = check_launch(h, "halfband_stream_kernel")))
+				return rc;
+		}
 	} else {
 		const int passes = h->cfg.downsample_passes;
 		const c16 *cur = nullptr;

@@ -1020,6 +1020,199 @@ halfband_chain_kernel(const SCAN_GRID_CONSTANT HalfbandChainParams prm)
 	}
 }
 
+/*
+ * The same -F chain as a register-resident streaming filter (downsample_passes <= 5): no shared
+ * memory, no barriers, every intermediate sample is produced and consumed in registers.
+ *
+ * One thread owns `span` consecutive FINAL samples of one read and walks the input once,
+ * 2^P samples per final sample.  Level 1 (half of all the chain's outputs) is computed
+ * straight from the packed bytes: with W[m] the 32-bit word holding samples 2m and 2m+1
+ * (bytes I, Q, I, Q), output n = (a + 5(b+e) + 10(c+d) + f) >> 4 over samples 2n-5 .. 2n
+ * is four IDP.4A per component over W[n-3] .. W[n] with the coefficient words below, the
+ * -127 offsets (rtl_power.c:666-668) folded into the addend (-127 * 32).  Levels >= 2 keep
+ * the five newest samples of the level below as ints and take two new ones per output.
+ * int16 wrap at every level like the reference's in-place buffer.
+ *
+ * Why outputs are exact although a thread starts in the middle of a read with zeroed
+ * windows: a generic output n >= 5 of any level depends on samples 2n-5 .. 2n >= 5 of the
+ * level below only, so garbage never spreads: after a warm-up of 16 final samples (level-0
+ * reach 14 * 2^P - 5 samples incl. the 9 FIR taps) everything a thread stores is exact.  The
+ * reference's eased-in outputs 0..4 of every level (rtl_power.c:567-577) only reach final
+ * samples 0..13 (through the FIR); final samples [0, 16) of every read are therefore left to
+ * halfband_chain_kernel (one 16-sample tile per read), which also adds their DC terms.
+ */
+struct HalfbandStreamParams {
+	const uint8_t *base;
+	const long long *read_off;
+	int n_reads;
+	int pairs;                 /* complex samples per read */
+	int span;                  /* final samples per thread, a multiple of 4 */
+	int use_fir;
+	int f1, f2, f3, f4, f5;
+	c16 *out;
+	long long out_stride;
+	int l_len;
+	long long *sums;
+};
+
+constexpr int kHbStreamHead = 16; /* final samples [0, 16) come from the tile kernel */
+constexpr int kHbStreamWarm = 16; /* final samples computed and discarded in front of a span */
+constexpr int kHbStreamMaxPasses = 5;
+
+struct HbWin {
+	int r[5], i[5]; /* the five newest samples of a level, oldest first */
+};
+
+template <int P>
+struct HbState {
+	unsigned wq[3];                   /* W[n-3], W[n-2], W[n-1] */
+	HbWin win[P > 1 ? P - 1 : 1];     /* win[j]: samples of level j + 1, feeding level j + 2 */
+};
+
+SCAN_DEV void hb_level1(unsigned (&wq)[3], unsigned w, int &re, int &im)
+{
+	unsigned sr = (unsigned)-4064, si = (unsigned)-4064; /* -127 * (1 + 5 + 10 + 10 + 5 + 1) */
+	sr = __dp4a(wq[0], 0x00010000u, sr); si = __dp4a(wq[0], 0x01000000u, si); /* a = sample 2n-5 */
+	sr = __dp4a(wq[1], 0x000A0005u, sr); si = __dp4a(wq[1], 0x0A000500u, si); /* 5 b + 10 c */
+	sr = __dp4a(wq[2], 0x0005000Au, sr); si = __dp4a(wq[2], 0x05000A00u, si); /* 10 d + 5 e */
+	sr = __dp4a(w, 0x00000001u, sr);     si = __dp4a(w, 0x00000100u, si);     /* f = sample 2n */
+	re = (int)(int16_t)((int)sr >> 4);
+	im = (int)(int16_t)((int)si >> 4);
+	wq[0] = wq[1];
+	wq[1] = wq[2];
+	wq[2] = w;
+}
+
+/* output n of a level >= 2 from the window (samples 2n-5 .. 2n-1 of the level below) and its two
+ * new samples 2n, 2n+1 */
+SCAN_DEV void hb_combine(HbWin &w, int r0, int i0, int r1, int i1, int &re, int &im)
+{
+	re = (int)(int16_t)((w.r[0] + (w.r[1] + w.r[4]) * 5 + (w.r[2] + w.r[3]) * 10 + r0) >> 4);
+	im = (int)(int16_t)((w.i[0] + (w.i[1] + w.i[4]) * 5 + (w.i[2] + w.i[3]) * 10 + i0) >> 4);
+	w.r[0] = w.r[2]; w.r[1] = w.r[3]; w.r[2] = w.r[4]; w.r[3] = r0; w.r[4] = r1;
+	w.i[0] = w.i[2]; w.i[1] = w.i[3]; w.i[2] = w.i[4]; w.i[3] = i0; w.i[4] = i1;
+}
+
+/* sample IDX (within the current macro step) of level J; level-1 sample m consumes word m */
+template <int J, int IDX, int P, int NW>
+SCAN_DEV void hb_produce(HbState<P> &st, const unsigned (&w)[NW], int &re, int &im)
+{
+	if constexpr (J == 1) {
+		hb_level1(st.wq, w[IDX], re, im);
+	} else {
+		int r0, i0, r1, i1;
+		hb_produce<J - 1, 2 * IDX, P, NW>(st, w, r0, i0);
+		hb_produce<J - 1, 2 * IDX + 1, P, NW>(st, w, r1, i1);
+		hb_combine(st.win[J - 2], r0, i0, r1, i1, re, im);
+	}
+}
+
+template <int P>
+__global__ void __launch_bounds__(128)
+halfband_stream_kernel(const SCAN_GRID_CONSTANT HalfbandStreamParams prm)
+{
+	constexpr int LS = (1 << P) < 8 ? 8 : (1 << P); /* input samples per macro step */
+	constexpr int NW = LS / 2, NV = NW / 4;         /* words / 16-byte loads per macro step */
+	constexpr int OUTS = LS >> P;                   /* final samples per macro step */
+	const int M = prm.pairs >> P;
+	const int spans = (M + prm.span - 1) / prm.span;
+	const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const int e = (int)(gid / spans), sp = (int)(gid % spans);
+	if (e >= prm.n_reads)
+		return;
+	const int k0 = sp * prm.span;
+	const int k1 = (k0 + prm.span < M) ? k0 + prm.span : M;
+	const int kb = (k0 >= kHbStreamWarm) ? k0 - kHbStreamWarm : 0;
+	const int first_store = (k0 > kHbStreamHead) ? k0 : kHbStreamHead;
+	const uint4 *src = (const uint4 *)(prm.base + prm.read_off[e] + (long long)kb * (2 << P));
+
+	HbState<P> st;
+#pragma unroll
+	for (int j = 0; j < 3; ++j)
+		st.wq[j] = 0u;
+#pragma unroll
+	for (int j = 0; j < (P > 1 ? P - 1 : 1); ++j) {
+#pragma unroll
+		for (int q = 0; q < 5; ++q)
+			st.win[j].r[q] = st.win[j].i[q] = 0;
+	}
+	int hr[9], hi[9]; /* the nine final samples before the current one (generic_fir, rtl_power.c:598-626) */
+#pragma unroll
+	for (int q = 0; q < 9; ++q)
+		hr[q] = hi[q] = 0;
+	long long dI = 0, dQ = 0;
+	c16 *dst = prm.out + e * prm.out_stride;
+
+	uint4 nxt[NV];
+#pragma unroll
+	for (int j = 0; j < NV; ++j)
+		nxt[j] = __ldg(src + j);
+	for (int k = kb; k < k1; k += OUTS) {
+		unsigned w[NW];
+#pragma unroll
+		for (int j = 0; j < NV; ++j) {
+			w[4 * j] = nxt[j].x; w[4 * j + 1] = nxt[j].y; w[4 * j + 2] = nxt[j].z; w[4 * j + 3] = nxt[j].w;
+		}
+		src += NV;
+		if (k + OUTS < k1) { /* next macro step's bytes, in flight during this one's arithmetic */
+#pragma unroll
+			for (int j = 0; j < NV; ++j)
+				nxt[j] = __ldg(src + j);
+		}
+		int fr[OUTS], fi[OUTS];
+		if constexpr (OUTS == 4) {
+			hb_produce<P, 0, P, NW>(st, w, fr[0], fi[0]);
+			hb_produce<P, 1, P, NW>(st, w, fr[1], fi[1]);
+			hb_produce<P, 2, P, NW>(st, w, fr[2], fi[2]);
+			hb_produce<P, 3, P, NW>(st, w, fr[3], fi[3]);
+		} else if constexpr (OUTS == 2) {
+			hb_produce<P, 0, P, NW>(st, w, fr[0], fi[0]);
+			hb_produce<P, 1, P, NW>(st, w, fr[1], fi[1]);
+		} else {
+			hb_produce<P, 0, P, NW>(st, w, fr[0], fi[0]);
+		}
+#pragma unroll
+		for (int o = 0; o < OUTS; ++o) {
+			const int kk = k + o;
+			int re = fr[o], im = fi[o];
+			if (prm.use_fir) {
+				/* the 9 samples BEFORE kk, int32 wrap-around arithmetic (all kk stored here are >= 16 > 9) */
+				unsigned sr = 0, si = 0;
+				sr += (unsigned)(hr[0] + hr[8]) * (unsigned)prm.f1;
+				sr += (unsigned)(hr[1] + hr[7]) * (unsigned)prm.f2;
+				sr += (unsigned)(hr[2] + hr[6]) * (unsigned)prm.f3;
+				sr += (unsigned)(hr[3] + hr[5]) * (unsigned)prm.f4;
+				sr += (unsigned)hr[4] * (unsigned)prm.f5;
+				si += (unsigned)(hi[0] + hi[8]) * (unsigned)prm.f1;
+				si += (unsigned)(hi[1] + hi[7]) * (unsigned)prm.f2;
+				si += (unsigned)(hi[2] + hi[6]) * (unsigned)prm.f3;
+				si += (unsigned)(hi[3] + hi[5]) * (unsigned)prm.f4;
+				si += (unsigned)hi[4] * (unsigned)prm.f5;
+				re = (int)(int16_t)((int)sr >> 15);
+				im = (int)(int16_t)((int)si >> 15);
+#pragma unroll
+				for (int q = 0; q < 8; ++q) {
+					hr[q] = hr[q + 1];
+					hi[q] = hi[q + 1];
+				}
+				hr[8] = fr[o];
+				hi[8] = fi[o];
+			}
+			if (kk >= first_store) {
+				dst[kk] = c16_pack(re, im);
+				if (2 * kk < prm.l_len)
+					dI += re;
+				if (2 * kk + 1 < prm.l_len)
+					dQ += im;
+			}
+		}
+	}
+	if (dI != 0)
+		atomicAdd((unsigned long long *)(prm.sums + 2 * e), (unsigned long long)dI);
+	if (dQ != 0)
+		atomicAdd((unsigned long long *)(prm.sums + 2 * e + 1), (unsigned long long)dQ);
+}
+
 struct FirParams {
 	const c16 *in;
 	long long in_stride;

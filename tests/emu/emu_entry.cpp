@@ -100,6 +100,9 @@ void emu_small_u8(int L, int peak, const uint8_t *reads, int n_reads, const int 
  * decimating path: u8 reads [n_reads][buf_len] -> images -> spectra.
  * mode 0 = boxcar(ds), mode 1 = fifth_order x ds_p (+ 9-tap FIR if fir5 != NULL)
  */
+static int g_hb_span = 64;
+void emu_set_hb_span(int span) { g_hb_span = span; }
+
 void emu_small_decim(int L, int peak, const uint8_t *reads, int n_reads, int buf_len, int ds, int ds_p,
 		     int mode, const int *fir5, const int *segs, int n_segs, const int *tw,
 		     const uint16_t *win, long long *avg, uint32_t *image_out, long long *sums_out)
@@ -159,10 +162,36 @@ void emu_small_decim(int L, int peak, const uint8_t *reads, int n_reads, int buf
 		if (tile > 256) tile = 256;
 		if (tile < 8) tile = 8;
 		if (tile > M) tile = M;
+		const bool stream = mode == 2 && ds_p <= kHbStreamMaxPasses; /* mode 2: streaming kernel + 16-sample head tiles */
+		if (stream)
+			tile = kHbStreamHead;
 		hp.tile = tile;
 		hp.cap0 = cap0;
-		cuda_emu::launch(dim3((M + tile - 1) / tile, n_reads), dim3(256), (cap0 + cap0 / 2 + 16) * 4,
+		cuda_emu::launch(dim3(stream ? 1 : (M + tile - 1) / tile, n_reads), dim3(256), (cap0 + cap0 / 2 + 16) * 4,
 				 [&]() { halfband_chain_kernel(hp); });
+		if (stream) {
+			HalfbandStreamParams q;
+			q.base = reads;
+			q.read_off = offs.data();
+			q.n_reads = n_reads;
+			q.pairs = pairs;
+			q.use_fir = hp.use_fir;
+			q.f1 = hp.f1; q.f2 = hp.f2; q.f3 = hp.f3; q.f4 = hp.f4; q.f5 = hp.f5;
+			q.out = img.data();
+			q.out_stride = stride;
+			q.l_len = l_len;
+			q.sums = sums.data();
+			q.span = g_hb_span;
+			const long long threads = (long long)n_reads * ((M + q.span - 1) / q.span);
+			const dim3 grid((unsigned)((threads + 127) / 128));
+			switch (ds_p) {
+			case 1: cuda_emu::launch(grid, dim3(128), 0, [&]() { halfband_stream_kernel<1>(q); }); break;
+			case 2: cuda_emu::launch(grid, dim3(128), 0, [&]() { halfband_stream_kernel<2>(q); }); break;
+			case 3: cuda_emu::launch(grid, dim3(128), 0, [&]() { halfband_stream_kernel<3>(q); }); break;
+			case 4: cuda_emu::launch(grid, dim3(128), 0, [&]() { halfband_stream_kernel<4>(q); }); break;
+			default: cuda_emu::launch(grid, dim3(128), 0, [&]() { halfband_stream_kernel<5>(q); }); break;
+			}
+		}
 	} else {
 		std::vector<c16> a((size_t)n_reads * (pairs / 2)), b((size_t)n_reads * (pairs / 4 + 4));
 		const c16 *cur = nullptr;

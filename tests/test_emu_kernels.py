@@ -254,3 +254,31 @@ def test_stream_boxcar_kernel(emu, port_oracle, bin_e, ds, slots, grid, mode):
                               vp(avg), vp(smp))
         assert np.array_equal(avg, want), (bin_e, ds, peak)
         assert np.array_equal(smp, want_smp)
+
+
+@pytest.mark.parametrize("passes,fir,span", [(1, 9, 64), (1, 0, 4096), (2, 9, 256), (3, 9, 64), (3, 0, 1024), (4, 9, 128),
+                                             (4, 5, 512), (5, 9, 64), (5, 0, 256)])
+def test_fifth_order_streaming_kernel(emu, port_oracle, passes, fir, span):
+    """register-streaming -F chain (levels in registers, level 1 straight from the bytes) + 16-sample head tiles"""
+    bin_e = 6
+    n, ds = 1 << bin_e, 1 << passes
+    buf_len = max(16384, 2 * n * ds)
+    plan = plan_dict(bin_e, buf_len=buf_len, downsample=ds, downsample_passes=passes, boxcar=0,
+                     comp_fir_size=fir, tune_count=1)
+    win = port_oracle.window_coefs("hamming", n)
+    reads, hops = make_reads(port_oracle.lib, plan, 3, SYNTH_BIASED, seed=40 + passes, param=-45)
+    reads[1, 100:300] = 255
+    reads[2, :64] = 0
+    reads[2, 5000:5100] = 255
+    want, _, _ = expected(port_oracle, plan, win, reads, hops)
+    segs = np.array([(0, 0, 3, 0)], dtype=np.int32)
+    tw = twiddles(port_oracle.sine_table(bin_e), bin_e)
+    w16 = (win & 0xFFFF).astype(np.uint16)
+    avg = np.zeros((1, n), dtype=np.int64)
+    fir5 = None
+    if fir == 9:
+        fir5 = np.array(list(port_oracle.lib.oracle_cic9(passes).contents)[1:6], dtype=np.int32)
+    emu.emu_set_hb_span(span)
+    emu.emu_small_decim(bin_e, 0, vp(reads), 3, buf_len, ds, passes, 2, vp(fir5), vp(segs), 1, vp(tw), vp(w16),
+                        vp(avg), None, None)
+    assert np.array_equal(avg, want)
