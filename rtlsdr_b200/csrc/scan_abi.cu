@@ -667,12 +667,13 @@ int run_decimators(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_o
 		if (stream)
 			tile = kHbStreamHead;
 		p.tile = tile;
-		p.cap0 = kChainCap0;
-		const int smem = (kChainCap0 + kChainCap0 / 2 + 16) * 4;
+		/* head tiles span (16 + 9) * 2^P + 5 * (2^P - 1) + 9 <= 964 level-0 samples: small buffers, many CTAs per SM */
+		p.cap0 = stream ? 1024 : kChainCap0;
+		const int smem = (p.cap0 + p.cap0 / 2 + 16) * 4;
 		CU(cudaFuncSetAttribute(halfband_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 		CU(cudaMemsetAsync(sc.sums, 0, (size_t)n * 16, h->stream));
 		dim3 grid(stream ? 1 : (M + tile - 1) / tile, n);
-		halfband_chain_kernel<<<grid, 256, smem, h->stream>>>(p);
+		halfband_chain_kernel<<<grid, stream ? 64 : 256, smem, h->stream>>>(p);
 		if ((rc = check_launch(h, "halfband_chain_kernel")))
 			return rc;
 		if (stream) {
@@ -688,9 +689,9 @@ int run_decimators(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_o
 			q.l_len = h->l_len;
 			q.sums = sc.sums;
 			/* span: as long as possible (16 warm-up samples per span are recomputed) while the grid
-			 * still offers about one resident wave of threads (512 per SM at <= 128 registers) */
+			 * still fills at least half of the resident thread slots (640 per SM at 87 registers) */
 			int span = M;
-			while (span > 64 && (long long)n * ((M + span - 1) / span) < (long long)h->num_sms * 512)
+			while (span > 64 && (long long)n * ((M + span - 1) / span) < (long long)h->num_sms * 256)
 				span /= 2;
 			q.span = span;
 			const long long threads = (long long)n * ((M + span - 1) / span);

@@ -922,6 +922,7 @@ halfband_chain_kernel(const SCAN_GRID_CONSTANT HalfbandChainParams prm)
 	c16 *buf0 = (c16 *)smem;
 	c16 *buf1 = buf0 + prm.cap0;
 	const int e = blockIdx.y, t = threadIdx.x, P = prm.passes;
+	const int nt = blockDim.x; /* 256 for full tiles, 64 for the 16-sample head tiles of the streaming path */
 	const int M = prm.pairs >> P;
 	const int k0 = blockIdx.x * prm.tile;
 	const int k1 = (k0 + prm.tile < M) ? k0 + prm.tile : M;
@@ -952,7 +953,7 @@ halfband_chain_kernel(const SCAN_GRID_CONSTANT HalfbandChainParams prm)
 	{
 		const uint16_t *src = (const uint16_t *)(prm.base + prm.read_off[e]);
 		const int lo = lo_s[0], n = hi_s[0] - lo + 1;
-		for (int i = t; i < n; i += 256) {
+		for (int i = t; i < n; i += nt) {
 			const unsigned raw = __ldg(src + lo + i);
 			buf0[i] = c16_pack((int)(raw & 0xFFu) - 127, (int)(raw >> 8) - 127);
 		}
@@ -961,7 +962,7 @@ halfband_chain_kernel(const SCAN_GRID_CONSTANT HalfbandChainParams prm)
 	c16 *cur = buf0, *nxt = buf1;
 	for (int j = 1; j <= P; ++j) {
 		const int lo = lo_s[j], n = hi_s[j] - lo + 1, plo = lo_s[j - 1];
-		for (int i = t; i < n; i += 256)
+		for (int i = t; i < n; i += nt)
 			nxt[i] = halfband_output(cur, plo, lo + i);
 		__syncthreads();
 		c16 *tmp = cur;
@@ -972,7 +973,7 @@ halfband_chain_kernel(const SCAN_GRID_CONSTANT HalfbandChainParams prm)
 	/* droop-compensation FIR (or plain copy), image store, DC sums */
 	long long dI = 0, dQ = 0;
 	const int lo = lo_s[P];
-	for (int k = k0 + t; k < k1; k += 256) {
+	for (int k = k0 + t; k < k1; k += nt) {
 		c16 o = cur[k - lo];
 		if (prm.use_fir && k >= 9) {
 			const c16 *hsrc = cur + (k - 9 - lo);
@@ -1013,7 +1014,7 @@ halfband_chain_kernel(const SCAN_GRID_CONSTANT HalfbandChainParams prm)
 	__syncthreads();
 	if (t < 2) {
 		long long s = 0;
-		for (int w = 0; w < 8; ++w)
+		for (int w = 0; w < (nt >> 5); ++w)
 			s += red[2 * w + t];
 		if (s != 0)
 			atomicAdd((unsigned long long *)(prm.sums + 2 * e + t), (unsigned long long)s);
@@ -1059,16 +1060,24 @@ constexpr int kHbStreamHead = 16; /* final samples [0, 16) come from the tile ke
 constexpr int kHbStreamWarm = 16; /* final samples computed and discarded in front of a span */
 constexpr int kHbStreamMaxPasses = 5;
 
+/* Levels >= 2 keep the level below as PAIR words: samples 2m (low half) and 2m+1 (high half)
+ * of one component, so that output n = a + 5(b+e) + 10(c+d) + f over samples 2n-5 .. 2n is four
+ * IDP.2A (16-bit x 8-bit dot products) over pair words n-3 .. n; packing a pair (PRMT) is also
+ * the int16 wrap of the reference's buffer. */
 struct HbWin {
-	int r[5], i[5]; /* the five newest samples of a level, oldest first */
+	unsigned r[3], i[3]; /* pair words n-3, n-2, n-1 of the level below */
 };
 
 template <int P>
 struct HbState {
-	unsigned wq[3];                   /* W[n-3], W[n-2], W[n-1] */
-	HbWin win[P > 1 ? P - 1 : 1];     /* win[j]: samples of level j + 1, feeding level j + 2 */
+	unsigned wq[3];                   /* byte words W[n-3], W[n-2], W[n-1] */
+	HbWin win[P > 1 ? P - 1 : 1];     /* win[j]: pair words of level j + 1, feeding level j + 2 */
 };
 
+constexpr unsigned kHbK1 = 0x0A050100u; /* bytes (0, 1 | 5, 10): _lo on pair n-3, _hi on pair n-2 */
+constexpr unsigned kHbK2 = 0x0001050Au; /* bytes (10, 5 | 1, 0): _lo on pair n-1, _hi on pair n   */
+
+/* level-1 output, NOT yet wrapped to int16 (the consumer's PRMT / the final sign extension does that) */
 SCAN_DEV void hb_level1(unsigned (&wq)[3], unsigned w, int &re, int &im)
 {
 	unsigned sr = (unsigned)-4064, si = (unsigned)-4064; /* -127 * (1 + 5 + 10 + 10 + 5 + 1) */
@@ -1076,21 +1085,29 @@ SCAN_DEV void hb_level1(unsigned (&wq)[3], unsigned w, int &re, int &im)
 	sr = __dp4a(wq[1], 0x000A0005u, sr); si = __dp4a(wq[1], 0x0A000500u, si); /* 5 b + 10 c */
 	sr = __dp4a(wq[2], 0x0005000Au, sr); si = __dp4a(wq[2], 0x05000A00u, si); /* 10 d + 5 e */
 	sr = __dp4a(w, 0x00000001u, sr);     si = __dp4a(w, 0x00000100u, si);     /* f = sample 2n */
-	re = (int)(int16_t)((int)sr >> 4);
-	im = (int)(int16_t)((int)si >> 4);
+	re = (int)sr >> 4;
+	im = (int)si >> 4;
 	wq[0] = wq[1];
 	wq[1] = wq[2];
 	wq[2] = w;
 }
 
-/* output n of a level >= 2 from the window (samples 2n-5 .. 2n-1 of the level below) and its two
- * new samples 2n, 2n+1 */
+/* output n of a level >= 2 (not yet wrapped) from the window and the new pair n of the level below */
 SCAN_DEV void hb_combine(HbWin &w, int r0, int i0, int r1, int i1, int &re, int &im)
 {
-	re = (int)(int16_t)((w.r[0] + (w.r[1] + w.r[4]) * 5 + (w.r[2] + w.r[3]) * 10 + r0) >> 4);
-	im = (int)(int16_t)((w.i[0] + (w.i[1] + w.i[4]) * 5 + (w.i[2] + w.i[3]) * 10 + i0) >> 4);
-	w.r[0] = w.r[2]; w.r[1] = w.r[3]; w.r[2] = w.r[4]; w.r[3] = r0; w.r[4] = r1;
-	w.i[0] = w.i[2]; w.i[1] = w.i[3]; w.i[2] = w.i[4]; w.i[3] = i0; w.i[4] = i1;
+	const unsigned pr = __byte_perm((unsigned)r0, (unsigned)r1, 0x5410); /* low halves: int16 wrap */
+	const unsigned pi = __byte_perm((unsigned)i0, (unsigned)i1, 0x5410);
+	int sr = __dp2a_lo((int)w.r[0], (int)kHbK1, 0), si = __dp2a_lo((int)w.i[0], (int)kHbK1, 0);
+	sr = __dp2a_hi((int)w.r[1], (int)kHbK1, sr);
+	si = __dp2a_hi((int)w.i[1], (int)kHbK1, si);
+	sr = __dp2a_lo((int)w.r[2], (int)kHbK2, sr);
+	si = __dp2a_lo((int)w.i[2], (int)kHbK2, si);
+	sr = __dp2a_hi((int)pr, (int)kHbK2, sr);
+	si = __dp2a_hi((int)pi, (int)kHbK2, si);
+	re = sr >> 4;
+	im = si >> 4;
+	w.r[0] = w.r[1]; w.r[1] = w.r[2]; w.r[2] = pr;
+	w.i[0] = w.i[1]; w.i[1] = w.i[2]; w.i[2] = pi;
 }
 
 /* sample IDX (within the current macro step) of level J; level-1 sample m consumes word m */
@@ -1133,8 +1150,8 @@ halfband_stream_kernel(const SCAN_GRID_CONSTANT HalfbandStreamParams prm)
 #pragma unroll
 	for (int j = 0; j < (P > 1 ? P - 1 : 1); ++j) {
 #pragma unroll
-		for (int q = 0; q < 5; ++q)
-			st.win[j].r[q] = st.win[j].i[q] = 0;
+		for (int q = 0; q < 3; ++q)
+			st.win[j].r[q] = st.win[j].i[q] = 0u;
 	}
 	int hr[9], hi[9]; /* the nine final samples before the current one (generic_fir, rtl_power.c:598-626) */
 #pragma unroll
@@ -1170,6 +1187,11 @@ halfband_stream_kernel(const SCAN_GRID_CONSTANT HalfbandStreamParams prm)
 			hb_produce<P, 1, P, NW>(st, w, fr[1], fi[1]);
 		} else {
 			hb_produce<P, 0, P, NW>(st, w, fr[0], fi[0]);
+		}
+#pragma unroll
+		for (int o = 0; o < OUTS; ++o) {
+			fr[o] = (int)(int16_t)fr[o]; /* the reference stores every level as int16 */
+			fi[o] = (int)(int16_t)fi[o];
 		}
 #pragma unroll
 		for (int o = 0; o < OUTS; ++o) {

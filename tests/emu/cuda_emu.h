@@ -213,6 +213,15 @@ static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c)
 		c += ((a >> (8 * i)) & 0xFFu) * ((b >> (8 * i)) & 0xFFu);
 	return c;
 }
+/* 16-bit x 8-bit dot products, signed x signed: _lo uses bytes 0, 1 of b, _hi bytes 2, 3 */
+static inline int emu_dp2a(int a, int b, int c, int byte0)
+{
+	const int lo = (int16_t)(a & 0xFFFF), hi = (int16_t)((unsigned)a >> 16);
+	const int b0 = (int8_t)(((unsigned)b >> (8 * byte0)) & 0xFF), b1 = (int8_t)(((unsigned)b >> (8 * byte0 + 8)) & 0xFF);
+	return c + lo * b0 + hi * b1;
+}
+static inline int __dp2a_lo(int a, int b, int c) { return emu_dp2a(a, b, c, 0); }
+static inline int __dp2a_hi(int a, int b, int c) { return emu_dp2a(a, b, c, 2); }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }

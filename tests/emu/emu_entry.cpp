@@ -166,8 +166,8 @@ void emu_small_decim(int L, int peak, const uint8_t *reads, int n_reads, int buf
 		if (stream)
 			tile = kHbStreamHead;
 		hp.tile = tile;
-		hp.cap0 = cap0;
-		cuda_emu::launch(dim3(stream ? 1 : (M + tile - 1) / tile, n_reads), dim3(256), (cap0 + cap0 / 2 + 16) * 4,
+		hp.cap0 = stream ? 1024 : cap0;
+		cuda_emu::launch(dim3(stream ? 1 : (M + tile - 1) / tile, n_reads), dim3(stream ? 64 : 256), (hp.cap0 + hp.cap0 / 2 + 16) * 4,
 				 [&]() { halfband_chain_kernel(hp); });
 		if (stream) {
 			HalfbandStreamParams q;

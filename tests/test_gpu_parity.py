@@ -550,3 +550,26 @@ def test_boxcar_stream_kernel_forced(scan_mod, port_oracle, monkeypatch, bin_e, 
     assert np.array_equal(got[0], want[0])
     assert np.array_equal(got[1], want[1])
     assert db_close(got[2], want[2])
+
+
+@pytest.mark.parametrize("passes,fir", [(1, 0), (2, 9), (3, 9), (4, 9), (5, 0)])
+@pytest.mark.parametrize("tile_kernel", [False, True])
+def test_fifth_order_streaming_big_batch(scan_mod, port_oracle, monkeypatch, passes, fir, tile_kernel):
+    """-F chain on one large device batch: the register-streaming kernel picks long spans (256 final samples per
+    thread with 2400 reads) + head tiles; the tile kernel alone must give the same bins"""
+    if tile_kernel:
+        monkeypatch.setenv("RTLSDR_GPU_NO_HB_STREAM", "1")
+    bin_e = 7
+    n, ds = 1 << bin_e, 1 << passes
+    buf_len = max(16384, 2 * n * ds)
+    plan = plan_dict(bin_e, buf_len=buf_len, downsample=ds, downsample_passes=passes, boxcar=0,
+                     comp_fir_size=fir, tune_count=2, peak_hold=0, crop=0.3)
+    w = port_oracle.window_coefs("bartlett", n)
+    reads, hops = make_reads(port_oracle.lib, plan, 1200, SYNTH_BIASED, seed=77 + passes, param=21)
+    reads[7, 100:300] = 255
+    reads[11, :40] = 0
+    want = expected(port_oracle, plan, w, reads, hops)
+    got = run_gpu(scan_mod, plan, w, reads, hops, how="device")
+    assert np.array_equal(got[0], want[0])
+    assert np.array_equal(got[1], want[1])
+    assert db_close(got[2], want[2])
