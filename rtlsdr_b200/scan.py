@@ -26,7 +26,8 @@ class _Cfg(ctypes.Structure):
 
 
 def lib_path():
-    return os.path.join(PKG, "librtlsdr_gpu_scan.so")
+    """RTLSDR_GPU_SCAN_LIB selects another build of the same CUDA library (kernel experiments)."""
+    return os.environ.get("RTLSDR_GPU_SCAN_LIB") or os.path.join(PKG, "librtlsdr_gpu_scan.so")
 
 
 def load_library():
