@@ -215,18 +215,47 @@ struct GroupBar { /* the transform threads are one role of a warp-specialised CT
 	SCAN_DEV void sync() const { named_bar_sync(id, count); }
 };
 
+/* tw_ = thread id whose pass-KA positions the registers hold, t = this thread's id in pass KB
+ * (they differ only after a permuted front end, see front_thread_map) */
 template <int KA, int KB, bool LEAD, class BAR = BlockBar>
-SCAN_DEV void exchange(X2 (&x)[kPts], c16 *xch, int t, const BAR &bar = BAR())
+SCAN_DEV void exchange(X2 (&x)[kPts], c16 *xch, int tw_, int t, const BAR &bar = BAR())
 {
 	if (LEAD)
 		bar.sync();
 #pragma unroll
 	for (int r = 0; r < kPts; ++r)
-		xch[xch_idx(pos<KA>(t, r))] = x_pack(x[r]);
+		xch[xch_idx(pos<KA>(tw_, r))] = x_pack(x[r]);
 	bar.sync();
 #pragma unroll
 	for (int r = 0; r < kPts; ++r)
 		x[r] = x_unpack(xch[xch_idx(pos<KB>(t, r))]);
+}
+
+/*
+ * Which samples a thread takes in the front end.  Natural choice: thread t holds positions
+ * 16t + r, i.e. the samples n = (brev4(r) << (L-4)) + bitrev(t) -- but then the lanes of a warp
+ * read 16-bit samples 16 bytes apart (4-way bank conflicts on every front-end load, 8-way on
+ * the 32-bit loads of a decimated image).  For L = 12 the lanes instead take
+ *   g = brev5(lane) << 3 | (brev5(lane)[4:3] ^ warp[1:0]) << 1 | warp[2]
+ * as the low 8 sample bits: still a bijection, the 32 lanes now hit 32 different banks on the
+ * sample and window loads, and the positions they hold, 16 * brev8(g) + r, are congruent to
+ * 16 * lane + r modulo 512, so the first transpose's stores stay conflict-free.
+ * Returns the low sample bits; t0 = the thread id whose natural positions this thread holds in pass 0.
+ */
+template <int L>
+SCAN_DEV int front_thread_map(int t, int &t0)
+{
+	if constexpr (L == 12) {
+		const int b = brev_bits((unsigned)(t & 31), 5), w = t >> 5;
+		const int g = (b << 3) | ((((b >> 3) & 3) ^ (w & 3)) << 1) | (w >> 2);
+		t0 = brev_bits((unsigned)g, 8);
+		return g;
+	} else {
+		t0 = t;
+		if constexpr (L >= 4)
+			return brev_bits((unsigned)(t & ((1 << (L - 4)) - 1)), L - 4);
+		return 0;
+	}
 }
 
 /* Runs stages 0..LE-1; on return register r of thread t holds position
@@ -236,11 +265,11 @@ SCAN_DEV void engine_fft(X2 (&x)[kPts], c16 *xch, int t, const TW &tw)
 {
 	run_pass<0, LE>(x, t, tw);
 	if constexpr (LE > 4) {
-		exchange<0, 1, true>(x, xch, t);
+		exchange<0, 1, true>(x, xch, t, t);
 		run_pass<1, LE>(x, t, tw);
 	}
 	if constexpr (LE > 8) {
-		exchange<1, 2, true>(x, xch, t);
+		exchange<1, 2, true>(x, xch, t, t);
 		run_pass<2, LE>(x, t, tw);
 	}
 }
@@ -248,16 +277,18 @@ SCAN_DEV void engine_fft(X2 (&x)[kPts], c16 *xch, int t, const TW &tw)
 /* Same, with two transpose buffers of kXchWords each; `flip` is the running
  * exchange parity (uniform across the CTA, carried across working sets). */
 template <int LE, class TW, class BAR = BlockBar>
-SCAN_DEV void engine_fft_db(X2 (&x)[kPts], c16 *xch2, int &flip, int t, const TW &tw, const BAR &bar = BAR())
+SCAN_DEV void engine_fft_db(X2 (&x)[kPts], c16 *xch2, int &flip, int t, const TW &tw, const BAR &bar = BAR(), int t0 = -1)
 {
-	run_pass<0, LE>(x, t, tw);
+	if (t0 < 0)
+		t0 = t; /* natural front end: the registers hold positions 16t + r */
+	run_pass<0, LE>(x, t0, tw);
 	if constexpr (LE > 4) {
-		exchange<0, 1, false, BAR>(x, xch2 + flip * kXchWords, t, bar);
+		exchange<0, 1, false, BAR>(x, xch2 + flip * kXchWords, t0, t, bar);
 		flip ^= 1;
 		run_pass<1, LE>(x, t, tw);
 	}
 	if constexpr (LE > 8) {
-		exchange<1, 2, false, BAR>(x, xch2 + flip * kXchWords, t, bar);
+		exchange<1, 2, false, BAR>(x, xch2 + flip * kXchWords, t, t, bar);
 		flip ^= 1;
 		run_pass<2, LE>(x, t, tw);
 	}
@@ -372,11 +403,10 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 
 	/* sample index (inside its FFT block) that feeds position (16t + r), minus
 	 * the r-dependent part: n = blkbase + (brev4(r) << (L-4)) + trev   (L >= 4) */
-	int trev = 0, blkbase = 0;
-	if constexpr (L >= 4) {
-		trev = brev_bits((unsigned)(t & ((1 << (L - 4)) - 1)), L - 4);
+	int blkbase = 0, t0;
+	const int trev = front_thread_map<L>(t, t0);
+	if constexpr (L >= 4)
 		blkbase = (t >> (L - 4)) << L;
-	}
 
 	constexpr int kWsPerUnit = IN16 ? 1 : 2; /* a 16 KiB slot = 8192 u8 pairs or 4096 c16 */
 	int flip = 0;
@@ -521,7 +551,7 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 					x[r].im = im << 16;
 				}
 
-				engine_fft_db<L>(x, xch, flip, t, tw);
+				engine_fft_db<L>(x, xch, flip, t, tw, BlockBar(), t0);
 
 				/* ---- |X|^2 (rtl_power.c:636-640, 708-716) ---- */
 #pragma unroll
@@ -1396,7 +1426,8 @@ scan_boxcar_fused_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
 	TwSmall<L> tw;
 	tw.tws = tws;
 	tw.tw0 = &prm.tw0;
-	const int trev = brev_bits((unsigned)(t & ((1 << (L - 4)) - 1)), L - 4);
+	int t0;
+	const int trev = front_thread_map<L>(t, t0);
 	const int myblk = t >> (L - 4);
 	const int blkbase = myblk << L;
 	int flip = 0;
@@ -1513,7 +1544,7 @@ scan_boxcar_fused_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
 				x[r].re = ((c16_re(raw) - kI) * wv) << 16;
 				x[r].im = ((c16_im(raw) - kQ) * wv) << 16;
 			}
-			engine_fft_db<L>(x, xch, flip, t, tw);
+			engine_fft_db<L>(x, xch, flip, t, tw, BlockBar(), t0);
 #pragma unroll
 			for (int r = 0; r < kPts; ++r) {
 				const int re = x[r].re >> 16, im = x[r].im >> 16;
@@ -1819,7 +1850,8 @@ scan_boxcar_stream_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
 	TwSmall<L> tw;
 	tw.tws = tws;
 	tw.tw0 = &prm.tw0;
-	const int trev = brev_bits((unsigned)(tf & ((1 << (L - 4)) - 1)), L - 4);
+	int t0;
+	const int trev = front_thread_map<L>(tf, t0);
 	const int myblk = tf >> (L - 4);
 	const int blkbase = myblk << L;
 	int flip = 0, wsn = 0;
@@ -1854,7 +1886,7 @@ scan_boxcar_stream_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
 			}
 			mbar_arrive(img_empty + buf); /* the boxcar role may refill this image */
 
-			engine_fft_db<L, TwSmall<L>, GroupBar>(x, xch, flip, tf, tw, fft_bar);
+			engine_fft_db<L, TwSmall<L>, GroupBar>(x, xch, flip, tf, tw, fft_bar, t0);
 #pragma unroll
 			for (int r = 0; r < kPts; ++r) {
 				const int re = x[r].re >> 16, im = x[r].im >> 16;
