@@ -1,9 +1,8 @@
 # one GPU-box call: parity suite, bench line, ncu launch list of the bench command, full captures of the dominant kernels
 mkdir -p gpurun_out
-TAG=${TAG:-r01l}
-(time timeout 1200 python -m pytest tests -m gpu -x -q) > gpurun_out/${TAG}_pytest.log 2>&1; tail -3 gpurun_out/${TAG}_pytest.log
-timeout 900 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -c 600 gpurun_out/${TAG}_bench.json
+TAG=${TAG:-r01m}
+(time timeout 1200 python -m pytest tests -m gpu -x -q) > gpurun_out/${TAG}_pytest.log 2>&1; tail -4 gpurun_out/${TAG}_pytest.log | head -2
+timeout 900 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -c 300 gpurun_out/${TAG}_bench.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 3 --warmup 3 --no-companions --no-cpu > gpurun_out/${TAG}_ncu_bench.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on --kernel-name regex:scan_small_kernel -s 4 -c 1 -f -o gpurun_out/${TAG}_scan_small python bench.py --steps 3 --warmup 3 --no-companions --no-cpu > gpurun_out/${TAG}_ncu_small.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on --kernel-name regex:scan_boxcar_stream -s 3 -c 1 -f -o gpurun_out/${TAG}_stream_ds28 python tools/scan_bench.py --range 100M:100.1M:100 --passes 8192 --steps 3 --no-kernel-time > gpurun_out/${TAG}_ncu_stream.log 2>&1
-ls -la gpurun_out | tail -12
+ls -la gpurun_out | grep ${TAG}
