@@ -257,6 +257,10 @@ def companion(rs, plan_scan, torch, name, freq, crop, window, fir, peak, passes,
             "bytes_per_step": step_bytes, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / peak_gbs}
 
 
+# diagnostic only (never set by the driver): time the multi-GPU step without its per-interval gather
+NO_GATHER = bool(os.environ.get("BENCH_DIAG_NO_GATHER"))
+
+
 def run_gpu(args):
     import numpy as np
     import torch
@@ -317,7 +321,7 @@ def run_gpu(args):
         p_db = p_avg + tc * n * 8
         p_smp = p_db + tc * db_count * 8
         g.submit_device(0, tc, PASSES, dev_in[i % n_sets].data_ptr(), tc * b, b)
-        if world > 1:
+        if world > 1 and not NO_GATHER:
             if step_device.pending is not None:
                 gather_interval(step_device.pending)
             stream.wait_event(gathered[k])          # buffer k's previous gather has finished
