@@ -304,12 +304,39 @@ def run_gpu(args):
     ready = [torch.cuda.Event() for _ in range(2)]
     gathered = [torch.cuda.Event() for _ in range(2)]
 
+    # Per-interval exchange, preferred form: no copy and no collective kernel at all.  Every rank's report
+    # epilogue stores its bins / dB / sample counts straight into rank 0's buffer through an NVLink peer mapping
+    # (torch symmetric memory), and one symmetric-memory barrier per interval (a one-CTA signalling kernel on a
+    # second stream) tells rank 0 that every slot is complete.  An NCCL send/receive kernel needs SM resources
+    # that two resident transform CTAs per SM do not leave: measured 4 % (2 GPUs) to 10 % (8 GPUs) of the step.
+    # BENCH_NCCL_GATHER=1, or a box without peer access, selects the grouped NCCL gather instead.
+    peer = None
+    if world > 1 and not NO_GATHER:
+        ok = 0
+        if not os.environ.get("BENCH_NCCL_GATHER"):
+            try:
+                import torch.distributed._symmetric_memory as symm
+                pbuf = symm.empty(2 * world * out_words, dtype=torch.int64, device=torch.device("cuda", local))
+                pbuf.zero_()
+                hdl = symm.rendezvous(pbuf, dist.group.WORLD)
+                peer = (pbuf, hdl, int(hdl.buffer_ptrs[0]))
+                ok = 1
+            except Exception as exc:  # noqa: BLE001 -- any failure means: use NCCL
+                print(f"bench.py: symmetric memory unavailable ({exc!r}); using the NCCL gather", file=sys.stderr)
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            peer = None
+
     def gather_interval(k):
         """report buffer k is complete once everything enqueued so far on `stream` has run"""
         ready[k].record(stream)
         with torch.cuda.stream(comm):
             comm.wait_event(ready[k])
-            dist.gather(sends[k], gathers[k], dst=0)
+            if peer is not None:
+                peer[1].barrier(channel=k)
+            else:
+                dist.gather(sends[k], gathers[k], dst=0)
             gathered[k].record(comm)
 
     def step_device(i):
@@ -317,7 +344,10 @@ def run_gpu(args):
         # Nothing sits between epilogue(i-1) and scan(i), so the transform can be launched
         # programmatically dependent on the previous report (it only waits before its flush).
         k = i & 1
-        p_avg = sends[k].data_ptr()
+        if peer is not None:
+            p_avg = peer[2] + (k * world + rank) * out_words * 8   # this rank's slot in rank 0's memory
+        else:
+            p_avg = sends[k].data_ptr()
         p_db = p_avg + tc * n * 8
         p_smp = p_db + tc * db_count * 8
         g.submit_device(0, tc, PASSES, dev_in[i % n_sets].data_ptr(), tc * b, b)
@@ -363,6 +393,11 @@ def run_gpu(args):
         e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
+    if peer is not None and rank == 0:
+        # every rank's last two reports must have landed in rank 0's buffer: sample counts = 2 * PASSES per hop
+        tail = peer[0].view(2, world, out_words)[:, :, tc * n + tc * db_count:].contiguous()
+        got = tail.view(torch.int32).view(2, world, 2 * tc)[:, :, :tc]   # int32 sample counts of the tc hops
+        assert bool((got == 2 * PASSES).all()), "peer-written reports are incomplete on rank 0"
     s1 = g.stats()
     k_ms, k_n = g.kernel_time()
     g.set_timing(0)
@@ -437,7 +472,10 @@ def run_gpu(args):
                        "hops_per_gpu": tc, "bins": n, "reads_per_step_per_gpu": PASSES * tc,
                        "bytes_per_step_per_gpu": step_bytes,
                        "cache": f"inputs larger than L2: {n_sets} distinct interval sets ({n_sets * step_bytes >> 20} MiB) rotated",
-                       "gather": ("one NCCL gather of int64 bins + dB per step, on a second stream, overlapped with "
+                       "gather": ("none: every rank's report epilogue stores its int64 bins + dB straight into rank 0's "
+                                  "buffer over NVLink (symmetric-memory peer mapping); one symmetric-memory barrier per "
+                                  "step on a second stream") if (world > 1 and peer is not None) else
+                                 ("one NCCL gather of int64 bins + dB per step, on a second stream, overlapped with "
                                   "the next interval's transform") if world > 1 else "none"},
             "per_gpu_value": value / world,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
