@@ -66,13 +66,13 @@ dc_sums_u8_kernel(const SCAN_GRID_CONSTANT DcSumU8Params prm)
 	const uint8_t *src = prm.base + prm.read_off[prm.entry_base + rel];
 	unsigned sI = 0, sQ = 0; /* <= 2^21 bytes of 255 per component: fits */
 	const int stride = gridDim.x * blockDim.x * 16;
-	for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 16; i < prm.buf_len; i += 4 * stride) {
-		uint4 q[4];
+	for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 16; i < prm.buf_len; i += 8 * stride) {
+		uint4 q[8]; /* 128 bytes in flight per thread: one resident wave of CTAs streams at HBM speed */
 #pragma unroll
-		for (int j = 0; j < 4; ++j)
+		for (int j = 0; j < 8; ++j)
 			q[j] = (i + j * stride < prm.buf_len) ? __ldg((const uint4 *)(src + i + j * stride)) : uint4{ 0, 0, 0, 0 };
 #pragma unroll
-		for (int j = 0; j < 4; ++j) {
+		for (int j = 0; j < 8; ++j) {
 			sI = __dp4a(q[j].x, 0x00010001u, sI);
 			sQ = __dp4a(q[j].x, 0x01000100u, sQ);
 			sI = __dp4a(q[j].y, 0x00010001u, sI);

@@ -102,7 +102,7 @@ int large_process(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_of
 			d.entry_base = e0;
 			d.buf_len = h->cfg.buf_len;
 			d.sums = sums;
-			dim3 g((unsigned)std::max<size_t>(1, std::min<size_t>(32, (size_t)h->cfg.buf_len / (256 * 16 * 4))), (unsigned)cnt);
+			dim3 g((unsigned)std::max<size_t>(1, std::min<size_t>(32, (size_t)h->cfg.buf_len / (256 * 16 * 8))), (unsigned)cnt);
 			dc_sums_u8_kernel<<<g, 256, 0, h->stream>>>(d);
 			if ((rc = check_launch(h, "dc_sums_u8_kernel")))
 				return rc;
