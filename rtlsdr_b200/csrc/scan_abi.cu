@@ -349,7 +349,35 @@ int build_desc(rtlsdr_gpu_scan *h, const std::vector<long long> &offs, const std
 	/* the decimating path runs in kDecimChunks chunks, each should still fill the GPU */
 	const bool big_decim = h->path == PATH_SMALL_DECIM && (size_t)n * (size_t)h->cfg.buf_len >= kDecimOverlapBytes;
 	const int target = std::max(1, h->num_sms * h->ctas_per_sm) * (big_decim ? kDecimChunks : 1);
-	const int chunk = std::max(1, (n + target - 1) / target);
+	int chunk = std::max(1, (n + target - 1) / target);
+	/*
+	 * A hop is at least one segment, so with many hops (or reads per hop that `chunk` does not divide) the
+	 * default can leave a mostly empty last wave of CTAs: 623 hops x 16 reads on 296 slots = 3 rounds of 16
+	 * reads where 33.7 per slot would do.  Among the shorter segment lengths pick the one with the smallest
+	 * makespan: rounds of resident CTAs x (reads per segment + the cost of a segment's flush and pipeline fill).
+	 */
+	{
+		const double per_seg = 0.35; /* flush + cold first load of a segment, in units of one read */
+		double best = 1e300;
+		int best_chunk = chunk;
+		for (int k = 1; k <= 16; k++) {
+			const int c = std::max(1, (chunk + k - 1) / k);
+			long long nseg = 0;
+			for (int hp = 0; hp < tc; hp++) {
+				const int cnt = count[hp + 1] - count[hp];
+				nseg += (cnt + c - 1) / c;
+			}
+			const long long rounds = (nseg + target - 1) / target;
+			const double cost = (double)rounds * (c + per_seg);
+			if (cost < best * 0.98) { /* prefer longer segments unless the gain is real */
+				best = cost;
+				best_chunk = c;
+			}
+			if (c == 1)
+				break;
+		}
+		chunk = best_chunk;
+	}
 	segs.clear();
 	for (int hp = 0; hp < tc; hp++) {
 		int lo = count[hp], hi = count[hp + 1];
