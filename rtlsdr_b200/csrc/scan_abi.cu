@@ -524,6 +524,8 @@ int launch_stream_boxcar_t(rtlsdr_gpu_scan *h, const FusedBoxcarParams &prm_in)
 {
 	FusedBoxcarParams prm = prm_in;
 	prm.slots = stream_boxcar_slots<L, FG>(prm.ds);
+	if (BG == 2)
+		prm.slots &= ~1; /* even: a slot then always serves the same boxcar group, which sees every phase of its barriers */
 	const int smem = StreamSmem<L, FG>::bytes(prm.ds, prm.slots);
 	const int grid = std::min(prm.n_segs, h->num_sms);
 	auto k = scan_boxcar_stream_kernel<L, PEAK, FG, BG>;
@@ -533,20 +535,52 @@ int launch_stream_boxcar_t(rtlsdr_gpu_scan *h, const FusedBoxcarParams &prm_in)
 	return check_launch(h, "scan_boxcar_stream_kernel");
 }
 
-/* 0 = single-role kernel; transform groups + boxcar groups: 1 = 1 + 2, 2 = 2 + 1, 3 = 2 + 2 */
+template <int L>
+int sym_boxcar_slots(int ds)
+{
+	const int fit = (227 * 1024 - SymSmem<L>::off_stage) / (512 * ds) / kSymGroups; /* per pipeline */
+	return std::min(fit, kStreamMaxSlots);
+}
+
+/* symmetric worker groups (scan_boxcar_sym_kernel) */
+template <int L, bool PEAK>
+int launch_sym_boxcar_t(rtlsdr_gpu_scan *h, const FusedBoxcarParams &prm_in)
+{
+	FusedBoxcarParams prm = prm_in;
+	prm.slots = sym_boxcar_slots<L>(prm.ds);
+	const int smem = SymSmem<L>::bytes(prm.ds, prm.slots);
+	const int grid = std::min(prm.n_segs, h->num_sms);
+	auto k = scan_boxcar_sym_kernel<L, PEAK>;
+	CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+	k<<<grid, kSymThreads, smem, h->stream>>>(prm);
+	h->last_was_epilogue = false;
+	return check_launch(h, "scan_boxcar_sym_kernel");
+}
+
+/* 0 = single-role kernel; transform groups + boxcar groups: 1 = 1 + 2, 2 = 2 + 1, 3 = 2 + 2; 5 = symmetric workers */
 template <int L>
 int stream_boxcar_mode(const rtlsdr_gpu_scan *h)
 {
 	const char *force = getenv("RTLSDR_GPU_BOXCAR_STREAM");
 	const int ds = h->cfg.downsample;
-	/* measured on B200 (profiles/r01l_stream_modes.txt): N = 256 has one chunk per read and a DC reduction per
-	 * chunk, there a single boxcar group wins; otherwise two boxcar groups, and a second transform group below ds ~ 24 */
-	int mode = ds < kStreamMinDs ? 0 : L == 8 ? 2 : ds < kStreamOneFftGroupDs ? 3 : 1;
+	/* measured on B200 (profiles/r01l_stream_modes.txt, r01n_stream_modes.txt): up to 512 bins and, at 1024 bins,
+	 * below ds ~ 24 the symmetric worker kernel wins (N = 256: +25 %, N = 512: +8..16 %); the three-role kernel
+	 * keeps the large-ds and the 2048 / 4096-bin cases (there the symmetric kernel's two rings get too shallow),
+	 * with a second transform group below ds ~ 24 */
+	int mode;
+	if (ds < kStreamMinDs)
+		mode = 0;
+	else if (L <= 9 || (L == 10 && ds < kStreamOneFftGroupDs))
+		mode = 5;
+	else
+		mode = ds < kStreamOneFftGroupDs ? 3 : 1;
 	if (force)
 		mode = atoi(force);
-	if (mode == 1 && stream_boxcar_slots<L, 1>(ds) < 3)
+	if (mode == 5 && sym_boxcar_slots<L>(ds) < 3)
+		mode = 1;
+	if (mode == 1 && stream_boxcar_slots<L, 1>(ds) < 4)
 		mode = 0;
-	if (mode >= 2 && stream_boxcar_slots<L, 2>(ds) < 3)
+	if ((mode == 2 || mode == 3) && stream_boxcar_slots<L, 2>(ds) < 4)
 		mode = 0;
 	return mode;
 }
@@ -555,6 +589,8 @@ template <int L>
 int launch_stream_boxcar_l(rtlsdr_gpu_scan *h, const FusedBoxcarParams &prm, int mode)
 {
 	const bool pk = h->cfg.peak_hold != 0;
+	if (mode == 5)
+		return pk ? launch_sym_boxcar_t<L, true>(h, prm) : launch_sym_boxcar_t<L, false>(h, prm);
 	if (mode == 1)
 		return pk ? launch_stream_boxcar_t<L, true, 1, 2>(h, prm) : launch_stream_boxcar_t<L, false, 1, 2>(h, prm);
 	if (mode == 2)

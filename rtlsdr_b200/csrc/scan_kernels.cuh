@@ -1936,6 +1936,286 @@ scan_boxcar_stream_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
 	}
 }
 
+/*
+ * Symmetric variant of the warp-specialised narrow-scan kernel: instead of dedicated boxcar and
+ * transform roles two pipelines share the CTA (and the twiddle / window tables), each with its
+ * own producer lane, its own ring and a WORKER group of 8 warps that owns alternate working sets
+ * end to end -- sum the working set's chunks out of the ring into a
+ * private 4096-sample image (one output slot per thread and chunk), take the DC averages, then
+ * run the register-blocked transform on it.  While one group transforms, the other sums; no warp
+ * idles in a role that has nothing to do (in the three-role kernel the transform role waits for
+ * images 58 % of its time at ds = 28 while the boxcar warps are the limit), and no image hand-off
+ * barriers are needed.  544 threads, so the transform keeps its 117 registers.
+ */
+constexpr int kSymGroups = 2;
+constexpr int kSymThreads = kSymGroups * kThreads + kSymGroups * 32; /* + one producer warp per pipeline */
+
+template <int L>
+struct SymSmem {
+	static constexpr int N = 1 << L;
+	static constexpr int off_image = 0;                                   /* one 4096 c16 image per group */
+	static constexpr int off_xch = kSymGroups * kWS * 4;                  /* two transpose buffers per group */
+	static constexpr int off_tw = off_xch + kSymGroups * 2 * kXchWords * 4;
+	static constexpr int off_win = off_tw + (N - 16) * 8;
+	static constexpr int off_red = (off_win + N * 2 + 15) & ~15;          /* [group][2][8 warps][2] int */
+	static constexpr int off_bar = off_red + kSymGroups * 2 * 16 * 4;     /* full[group][16] empty[group][16] */
+	static constexpr int off_stage = (off_bar + 2 * kSymGroups * kStreamMaxSlots * 8 + 127) & ~127;
+	static int bytes(int ds, int slots) { return off_stage + kSymGroups * slots * 512 * ds; } /* slots per group */
+};
+
+/* byte sums of one boxcar slot: I = even addresses, Q = odd addresses of [p, p + nbytes) */
+template <int ALIGN>
+SCAN_DEV void boxcar_one_slot_sums(const uint8_t *p, int nbytes, unsigned &si, unsigned &sq)
+{
+	unsigned a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+	if constexpr (ALIGN == 16) {
+#pragma unroll 2
+		for (int o = 0; o < nbytes; o += 16) {
+			const uint4 q = *(const uint4 *)(p + o);
+			a0 = __dp4a(q.x, 0x00010001u, a0); b0 = __dp4a(q.x, 0x01000100u, b0);
+			a1 = __dp4a(q.y, 0x00010001u, a1); b1 = __dp4a(q.y, 0x01000100u, b1);
+			a2 = __dp4a(q.z, 0x00010001u, a2); b2 = __dp4a(q.z, 0x01000100u, b2);
+			a3 = __dp4a(q.w, 0x00010001u, a3); b3 = __dp4a(q.w, 0x01000100u, b3);
+		}
+	} else if constexpr (ALIGN == 8) {
+#pragma unroll 4
+		for (int o = 0; o < nbytes; o += 8) {
+			const uint2 q = *(const uint2 *)(p + o);
+			a0 = __dp4a(q.x, 0x00010001u, a0); b0 = __dp4a(q.x, 0x01000100u, b0);
+			a1 = __dp4a(q.y, 0x00010001u, a1); b1 = __dp4a(q.y, 0x01000100u, b1);
+		}
+	} else if constexpr (ALIGN == 4) {
+#pragma unroll 4
+		for (int o = 0; o < nbytes; o += 4) {
+			const unsigned q = *(const unsigned *)(p + o);
+			a0 = __dp4a(q, 0x00010001u, a0);
+			b0 = __dp4a(q, 0x01000100u, b0);
+		}
+	} else {
+#pragma unroll 4
+		for (int o = 0; o < nbytes; o += 2) {
+			const unsigned q = *(const uint16_t *)(p + o);
+			a0 += q & 0xFFu;
+			b0 += q >> 8;
+		}
+	}
+	si = (a0 + a1) + (a2 + a3);
+	sq = (b0 + b1) + (b2 + b3);
+}
+
+template <int L, bool PEAK>
+__global__ void __launch_bounds__(kSymThreads, 1)
+scan_boxcar_sym_kernel(const SCAN_GRID_CONSTANT FusedBoxcarParams prm)
+{
+	SCAN_DYN_SMEM(smem);
+	typedef SymSmem<L> SM;
+	constexpr int N = 1 << L;
+	constexpr int RPW = kWS / N;      /* reads per working set */
+	constexpr int CPR = N / kThreads; /* 256-slot chunks per read */
+	int2 *tws = (int2 *)(smem + SM::off_tw);
+	uint16_t *wins = (uint16_t *)(smem + SM::off_win);
+
+	/* prm.slots = ring depth PER GROUP: each group has its own ring and its own producer lane, so every
+	 * transaction barrier has exactly one consumer group, which sees every phase of it in order (a parity
+	 * wait may never skip a phase) */
+	const int t = threadIdx.x, ds = prm.ds, nslots = prm.slots;
+	const int chunk_bytes = 512 * ds;
+	const int role = t / kThreads; /* 0, 1: worker groups; 2: the producer warps */
+	const int pg = role < kSymGroups ? role : (t - kSymGroups * kThreads) / 32; /* pipeline this thread belongs to */
+	uint64_t *full = (uint64_t *)(smem + SM::off_bar) + pg * kStreamMaxSlots;
+	uint64_t *empty = full + kSymGroups * kStreamMaxSlots;
+	uint8_t *stage = smem + SM::off_stage + pg * nslots * chunk_bytes;
+	if (t == 0) {
+		for (int g = 0; g < kSymGroups; ++g)
+			for (int s = 0; s < nslots; ++s) {
+				mbar_init((uint64_t *)(smem + SM::off_bar) + g * kStreamMaxSlots + s, 1);
+				mbar_init((uint64_t *)(smem + SM::off_bar) + (kSymGroups + g) * kStreamMaxSlots + s, kThreads / 32);
+			}
+		mbar_fence_init();
+	}
+	__syncthreads();
+
+	if (role >= kSymGroups) {
+		/* ================= producers: one lane per pipeline ================= */
+		if ((t & 31) != 0)
+			return;
+		int slot = 0, wsn = 0;
+		unsigned ph = 0;
+		for (int seg = blockIdx.x; seg < prm.n_segs; seg += gridDim.x) {
+			const int4 sg = prm.segs[seg];
+			for (int rd0 = 0; rd0 < sg.z; rd0 += RPW, ++wsn) {
+				if ((wsn & (kSymGroups - 1)) != pg)
+					continue;
+				const int nvalid = (sg.z - rd0 < RPW) ? sg.z - rd0 : RPW;
+				long long off = prm.read_off[sg.y + rd0];
+				for (int rw = 0; rw < nvalid; ++rw) {
+					const uint8_t *src = prm.base + off;
+					if (rw + 1 < nvalid)
+						off = prm.read_off[sg.y + rd0 + rw + 1]; /* in flight while this read's copies are issued */
+					for (int c = 0; c < CPR; ++c) {
+						mbar_wait(empty + slot, ph ^ 1u);
+						mbar_arrive_expect_tx(full + slot, (unsigned)chunk_bytes);
+						bulk_copy_g2s(stage + slot * chunk_bytes, src + (long long)c * chunk_bytes,
+							      (unsigned)chunk_bytes, full + slot);
+						if (++slot == nslots) {
+							slot = 0;
+							ph ^= 1u;
+						}
+					}
+				}
+			}
+		}
+		return;
+	}
+
+	/* ================= worker groups ================= */
+	const int fg = t / kThreads, tf = t % kThreads;
+	c16 *image = (c16 *)(smem + SM::off_image) + fg * kWS;
+	c16 *xch = (c16 *)(smem + SM::off_xch) + fg * 2 * kXchWords;
+	int *red = (int *)(smem + SM::off_red) + fg * 32;
+	const GroupBar bar = { 1 + fg, kThreads };
+	for (int i = t; i < (N - 16) / 2; i += kSymGroups * kThreads)
+		cp_async16((uint8_t *)tws + 16 * i, (const uint8_t *)prm.twc + 16 * i);
+	for (int i = t; i < N / 8; i += kSymGroups * kThreads)
+		cp_async16((uint8_t *)wins + 16 * i, (const uint8_t *)prm.win + 16 * i);
+	cp_async_commit();
+	cp_async_wait_all();
+	named_bar_sync(3, kSymGroups * kThreads); /* tables complete for every worker */
+
+	TwSmall<L> tw;
+	tw.tws = tws;
+	tw.tw0 = &prm.tw0;
+	int t0;
+	const int trev = front_thread_map<L>(tf, t0);
+	const int myblk = tf >> (L - 4);
+	const int blkbase = myblk << L;
+	int flip = 0, wsn = 0, par = 0;
+	int slot = 0; /* position in this group's own ring */
+	unsigned ph = 0;
+
+	for (int seg = blockIdx.x; seg < prm.n_segs; seg += gridDim.x) {
+		const int4 sg = prm.segs[seg];
+		const int hop = sg.x, count = sg.z;
+		unsigned long long acc[kPts];
+#pragma unroll
+		for (int r = 0; r < kPts; ++r)
+			acc[r] = 0ull;
+
+		for (int rd0 = 0; rd0 < count; rd0 += RPW, ++wsn) {
+			const int nvalid = (count - rd0 < RPW) ? count - rd0 : RPW;
+			if ((wsn & (kSymGroups - 1)) != fg)
+				continue; /* the other pipeline's working set */
+			int kI = 0, kQ = 0;
+			/* ---- boxcar: sum this working set's chunks out of the ring (rtl_power.c:666-681) ---- */
+			for (int rw = 0; rw < nvalid; ++rw) {
+				int dI = 0, dQ = 0; /* |sum| <= N * 32768 / 256 per thread: fits */
+				for (int c = 0; c < CPR; ++c) {
+					mbar_wait(full + slot, ph);
+					const uint8_t *p = stage + slot * chunk_bytes + tf * 2 * ds;
+					unsigned ui, uq;
+					if ((ds & 7) == 0)
+						boxcar_one_slot_sums<16>(p, 2 * ds, ui, uq);
+					else if ((ds & 3) == 0)
+						boxcar_one_slot_sums<8>(p, 2 * ds, ui, uq);
+					else if ((ds & 1) == 0)
+						boxcar_one_slot_sums<4>(p, 2 * ds, ui, uq);
+					else
+						boxcar_one_slot_sums<2>(p, 2 * ds, ui, uq);
+					const c16 v = c16_pack((int)ui - 127 * ds, (int)uq - 127 * ds);
+					image[rw * N + c * kThreads + tf] = v;
+					dI += c16_re(v); /* remove_dc sums the wrapped int16 values */
+					dQ += c16_im(v);
+					warp_sync();
+					if ((tf & 31) == 0)
+						mbar_arrive(empty + slot); /* this warp is done with the slot */
+					if (++slot == nslots) {
+						slot = 0;
+						ph ^= 1u;
+					}
+				}
+				/* the read is complete: its DC averages (divisors 2N and 2N-1, rtl_power.c:581-596) */
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) {
+					dI += __shfl_xor_sync(0xffffffffu, dI, o);
+					dQ += __shfl_xor_sync(0xffffffffu, dQ, o);
+				}
+				int *rr = red + par * 16; /* alternating: rewritten two reads later, one barrier in between */
+				par ^= 1;
+				if ((tf & 31) == 0) {
+					rr[(tf >> 5) * 2] = dI;
+					rr[(tf >> 5) * 2 + 1] = dQ;
+				}
+				bar.sync(); /* also: the image rows of this read are complete */
+				if (myblk == rw) {
+					long long sI = 0, sQ = 0;
+#pragma unroll
+					for (int w = 0; w < kThreads / 32; ++w) {
+						sI += rr[2 * w];
+						sQ += rr[2 * w + 1];
+					}
+					kI = dc_average(sI, 2 * N);
+					kQ = dc_average(sQ, 2 * N - 1);
+				}
+			}
+
+			/* ---- DC, window, bit-reversed placement, transform, |X|^2 ---- */
+			X2 x[kPts];
+#pragma unroll
+			for (int r = 0; r < kPts; ++r) {
+				const int nblk = (brev4(r) << (L - 4)) + trev;
+				const c16 raw = image[blkbase + nblk];
+				const int wv = wins[nblk];
+				x[r].re = ((c16_re(raw) - kI) * wv) << 16;
+				x[r].im = ((c16_im(raw) - kQ) * wv) << 16;
+			}
+			engine_fft_db<L, TwSmall<L>, GroupBar>(x, xch, flip, tf, tw, bar, t0);
+#pragma unroll
+			for (int r = 0; r < kPts; ++r) {
+				const int re = x[r].re >> 16, im = x[r].im >> 16;
+				if ((last_pos<L>(tf, r) >> L) < nvalid)
+					accumulate_power<PEAK>(acc[r], re, im);
+			}
+		}
+
+		pdl_wait();
+		if (t == 0)
+			atomicAdd((unsigned long long *)(prm.samples + hop), (unsigned long long)((long long)count * ds));
+		long long *out = prm.avg + ((long long)hop << L);
+		if constexpr (L == 12) {
+#pragma unroll
+			for (int r = 0; r < kPts; ++r) {
+				const int bin = last_pos<L>(tf, r) & (N - 1);
+				if constexpr (PEAK)
+					atomicMax(out + bin, (long long)acc[r]);
+				else
+					atomicAdd((unsigned long long *)(out + bin), acc[r]);
+			}
+		} else {
+			unsigned long long *bins = (unsigned long long *)xch; /* 2 * kXchWords * 4 >= N * 8 */
+			bar.sync();
+			for (int i = tf; i < N; i += kThreads)
+				bins[i] = 0ull;
+			bar.sync();
+#pragma unroll
+			for (int r = 0; r < kPts; ++r) {
+				const int bin = last_pos<L>(tf, r) & (N - 1);
+				if constexpr (PEAK)
+					atomicMax(bins + bin, acc[r]);
+				else
+					atomicAdd(bins + bin, acc[r]);
+			}
+			bar.sync();
+			for (int i = tf; i < N; i += kThreads) {
+				if constexpr (PEAK)
+					atomicMax(out + i, (long long)bins[i]);
+				else
+					atomicAdd((unsigned long long *)(out + i), bins[i]);
+			}
+			bar.sync();
+		}
+	}
+}
+
 /* ======================================================================== *
  *  rms_power: 1-bin hops (rtl_power.c:410-436)                              *
  * ======================================================================== */

@@ -407,7 +407,14 @@ void emu_stream_boxcar(int L, int peak, int mode, const uint8_t *reads, int n_re
 			 [&]() { scan_boxcar_stream_kernel<LV, PK, FG, BG>(p); })
 #define SB(LV)                                                                                        \
 	do {                                                                                          \
-		if (mode == 1) {                                                                      \
+		if (mode == 5) {                                                                      \
+			if (peak)                                                                     \
+				cuda_emu::launch(dim3(grid), dim3(kSymThreads), SymSmem<LV>::bytes(ds, slots), \
+						 [&]() { scan_boxcar_sym_kernel<LV, true>(p); });     \
+			else                                                                          \
+				cuda_emu::launch(dim3(grid), dim3(kSymThreads), SymSmem<LV>::bytes(ds, slots), \
+						 [&]() { scan_boxcar_sym_kernel<LV, false>(p); });    \
+		} else if (mode == 1) {                                                                      \
 			if (peak) SBM(LV, true, 1, 2); else SBM(LV, false, 1, 2);                     \
 		} else {                                                                              \
 			if (peak) SBM(LV, true, 2, 1); else SBM(LV, false, 2, 1);                     \
