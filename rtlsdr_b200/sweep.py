@@ -9,7 +9,14 @@ hop order like the reference's report loop (rtl_power.c:995-1000).
 
 One process per GPU; torch.distributed is only the plumbing (NCCL over NVLink
 on the GPU box, gloo in the CPU tests).
+
+On a box with NVLink peer access the gather needs no collective at all: the report
+epilogue (rtlsdr_gpu_scan_collect_device) writes wherever it is pointed, so every
+rank points it at its slot of rank 0's buffer (torch symmetric memory peer mapping)
+and one symmetric-memory barrier per interval tells rank 0 that the slots are
+complete (RTLSDR_B200_NCCL_GATHER=1 keeps the NCCL gather).
 """
+import os
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -46,10 +53,35 @@ class SpectrumGather:
         self.world, self.rank = world, rank
         self.hmax = max_hops_per_rank(tune_count, world)
         self.words = self.hmax * (n_bins + db_count + 1)
-        self.send = torch.zeros(self.words, dtype=torch.int64, device=device)
-        self.recv = ([torch.zeros(self.words, dtype=torch.int64, device=device) for _ in range(world)]
-                     if rank == 0 and world > 1 else None)
         self.my_hops = shard_hops(tune_count, world, rank)
+        self.peer = self._try_peer(torch.device(device)) if world > 1 else None
+        if self.peer is not None:
+            # this rank's slot of rank 0's buffer, mapped into this process over NVLink
+            self.send = self.peer[2][rank * self.words:(rank + 1) * self.words]
+            self.recv = None
+        else:
+            self.send = torch.zeros(self.words, dtype=torch.int64, device=device)
+            self.recv = ([torch.zeros(self.words, dtype=torch.int64, device=device) for _ in range(world)]
+                         if rank == 0 and world > 1 else None)
+
+    def _try_peer(self, device):
+        """(local buffer, symmetric-memory handle, rank 0's buffer as seen from here), or None; all ranks agree"""
+        ok, peer = 0, None
+        if device.type == "cuda" and not os.environ.get("RTLSDR_B200_NCCL_GATHER"):
+            try:
+                import torch.distributed._symmetric_memory as symm
+                buf = symm.empty(self.world * self.words, dtype=torch.int64, device=device)
+                buf.zero_()
+                hdl = symm.rendezvous(buf, dist.group.WORLD)
+                root = hdl.get_buffer(0, (self.world * self.words,), torch.int64)
+                peer, ok = (buf, hdl, root), 1
+            except Exception:  # noqa: BLE001 -- any failure means: use the collective
+                peer = None
+        if device.type != "cuda":
+            return None  # (gloo tests: every rank takes this branch, no agreement round needed)
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return peer if int(flag.item()) == 1 else None
 
     # views into the send buffer, sized for THIS rank's hop count
     def views(self):
@@ -78,7 +110,16 @@ class SpectrumGather:
         self.send[o: o + h] = vals
 
     def gather(self) -> Optional[IntervalReport]:
-        if self.world > 1:
+        if self.peer is not None:
+            buf, hdl, _ = self.peer
+            hdl.barrier(channel=0)          # every rank's epilogue has stored into rank 0's buffer
+            if self.rank != 0:
+                hdl.barrier(channel=1)      # rank 0 has read it: the slot may be rewritten
+                return None
+            host = buf.cpu()                # synchronises with the barrier above
+            hdl.barrier(channel=1)
+            bufs = [host[r * self.words:(r + 1) * self.words] for r in range(self.world)]
+        elif self.world > 1:
             dist.gather(self.send, self.recv, dst=0)
             if self.rank != 0:
                 return None

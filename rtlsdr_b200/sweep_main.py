@@ -6,8 +6,10 @@
 Every rank plans the same scan (host/rtl_power_plan.c), takes a contiguous range of hops
 (`shard_hops`), drives its own rtlsdr_gpu_scan handle from the synthetic source (bytes are a pure
 function of (hop, sweep), so the result does not depend on N), and once per integration interval
-ONE gather (NCCL over NVLink) brings bins + dB rows + sample counts to rank 0, which prints the
-reference's CSV rows in hop order (rtl_power.c:995-1000).  With N = 1 no process group is created.
+bins + dB rows + sample counts reach rank 0 -- written by every rank's report epilogue straight
+into rank 0's buffer over NVLink (symmetric-memory peer mapping, one barrier per interval), or by
+ONE NCCL gather where peer mapping is unavailable / RTLSDR_B200_NCCL_GATHER=1 -- and rank 0 prints
+the reference's CSV rows in hop order (rtl_power.c:995-1000).  With N = 1 no process group is created.
 """
 import argparse
 import ctypes
@@ -64,6 +66,10 @@ def main(argv=None):
         g = rs.GpuScan.from_plan(pd, window_coefs=window, device=local, hops=list(mine))
     db_count = g.db_count if g else plan.db_count
     gather = SpectrumGather(tc, n, db_count, world, rank, torch.device("cuda", local))
+    if rank == 0 and world > 1:
+        print("sweep_main: interval reports " + ("are written by every rank straight into rank 0's buffer (NVLink peer "
+              "mapping, one symmetric-memory barrier per interval)" if gather.peer is not None else
+              "are gathered with one NCCL gather per interval"), file=sys.stderr)
     stream = torch.cuda.ExternalStream(g.get_stream()) if g else torch.cuda.current_stream()
     pinned = rs.PinnedBuffer(max(1, args.sweeps * len(mine) * b)) if g else None
 
