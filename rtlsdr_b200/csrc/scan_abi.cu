@@ -506,10 +506,11 @@ int launch_fused_boxcar_l(rtlsdr_gpu_scan *h, const FusedBoxcarParams &prm_in)
 /*
  * Warp-specialised variant (producer / boxcar / transform roles, one CTA per SM).  The
  * single-role kernel's time is the SUM of its streaming and transform phases, this one's is
- * their maximum; measured faster for every ds >= 4 (ds = 28: 53 -> 72 % of the HBM copy peak).
+ * their maximum; measured faster for every ds (ds = 28: 53 -> 72 % of the HBM copy peak), so the
+ * single-role kernel is only the fallback when the ring does not fit.
  * RTLSDR_GPU_BOXCAR_STREAM=0 / 1 / 2 / 3 forces the choice (A/B measurements, tests).
  */
-constexpr int kStreamMinDs = 4;
+constexpr int kStreamMinDs = 2; /* every boxcar factor (measured down to ds = 2: +20..30 % over the single-role kernel) */
 constexpr int kStreamOneFftGroupDs = 24; /* from here on one transform group keeps up and leaves its registers unspilled */
 
 template <int L, int FG>
