@@ -416,6 +416,8 @@ void emu_stream_boxcar(int L, int peak, int mode, const uint8_t *reads, int n_re
 						 [&]() { scan_boxcar_sym_kernel<LV, false>(p); });    \
 		} else if (mode == 1) {                                                                      \
 			if (peak) SBM(LV, true, 1, 2); else SBM(LV, false, 1, 2);                     \
+		} else if (mode == 3) {                                                               \
+			if (peak) SBM(LV, true, 2, 2); else SBM(LV, false, 2, 2);                     \
 		} else {                                                                              \
 			if (peak) SBM(LV, true, 2, 1); else SBM(LV, false, 2, 1);                     \
 		}                                                                                     \

@@ -232,7 +232,7 @@ def test_fused_boxcar_kernel(emu, port_oracle, bin_e, ds, slots):
 
 @pytest.mark.parametrize("bin_e,ds,slots,grid", [(8, 2, 3, 1), (8, 13, 16, 2), (9, 28, 5, 3), (10, 28, 10, 2), (10, 64, 3, 1),
                                                  (11, 5, 4, 2), (12, 3, 3, 2), (12, 12, 8, 1)])
-@pytest.mark.parametrize("mode", [1, 2, 5])
+@pytest.mark.parametrize("mode", [1, 2, 3, 5])
 def test_stream_boxcar_kernel(emu, port_oracle, bin_e, ds, slots, grid, mode):
     """warp-specialised narrow-scan kernel: bulk-copy producer, boxcar warps, transform warps (mbarrier hand-offs)"""
     n = 1 << bin_e
@@ -250,7 +250,7 @@ def test_stream_boxcar_kernel(emu, port_oracle, bin_e, ds, slots, grid, mode):
         w16 = (win & 0xFFFF).astype(np.uint16)
         avg = np.zeros((2, n), dtype=np.int64)
         smp = np.zeros(2, dtype=np.int64)
-        if mode == 1:
+        if mode in (1, 3):
             slots = max(4, slots & ~1)   # two boxcar groups: even ring, a slot always serves the same group
         emu.emu_stream_boxcar(bin_e, peak, mode, vp(sreads), len(sreads), ds, slots, grid, vp(segs), len(segs), vp(tw), vp(w16),
                               vp(avg), vp(smp))

@@ -533,7 +533,7 @@ def test_fused_boxcar_path(scan_mod, port_oracle, bin_e, ds, peak):
 
 @pytest.mark.parametrize("bin_e,ds", [(8, 2), (8, 13), (8, 56), (9, 28), (10, 28), (10, 64), (11, 5), (11, 24), (12, 3), (12, 16)])
 @pytest.mark.parametrize("peak", [0, 1])
-@pytest.mark.parametrize("stream", ["0", "1", "2", "5"])
+@pytest.mark.parametrize("stream", ["0", "1", "2", "3", "5"])
 def test_boxcar_stream_kernel_forced(scan_mod, port_oracle, monkeypatch, bin_e, ds, peak, stream):
     """both narrow-scan kernels (single-role / warp-specialised producer-boxcar-transform) on the same inputs;
     many short segments so that ring slots, image buffers and barrier phases wrap several times"""
