@@ -398,19 +398,19 @@ int build_desc(rtlsdr_gpu_scan *h, const std::vector<long long> &offs, const std
 
 int large_process(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_offs, const int *d_hops, int n_reads);
 
-template <int L, bool PEAK, bool IN16>
-int launch_small_t(rtlsdr_gpu_scan *h, const SmallParams &prm)
+/*
+ * Launch a transform kernel; when the report epilogue is the previous kernel on the handle's own stream, as a
+ * programmatic dependent launch: the epilogue calls griddepcontrol.launch_dependents at its top, the kernel reads
+ * only its own inputs until griddepcontrol.wait in front of its first accumulator update, so the report costs no
+ * time on the transform's critical path.  Every kernel launched through here has that wait (pdl_wait()).
+ */
+template <class K, class P>
+int launch_after_epilogue(rtlsdr_gpu_scan *h, K kern, int grid, int block, int smem, const P &prm, bool allow_pdl = true)
 {
-	auto kern = scan_small_kernel<L, PEAK, IN16>;
-	/* RTLSDR_GPU_DEBUG_SMEM_PAD: occupancy experiments only (extra bytes -> fewer CTAs per SM) */
-	static const int pad = getenv("RTLSDR_GPU_DEBUG_SMEM_PAD") ? atoi(getenv("RTLSDR_GPU_DEBUG_SMEM_PAD")) : 0;
-	const int smem = SmallSmem<L>::bytes + pad;
-	CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-	const int grid = std::min(prm.n_segs, h->num_sms * 8);
-	if (!IN16 && h->last_was_epilogue && h->stream == h->own_stream) {
+	if (allow_pdl && h->last_was_epilogue && h->stream == h->own_stream) {
 		cudaLaunchConfig_t cfg = {};
 		cfg.gridDim = dim3(grid);
-		cfg.blockDim = dim3(kThreads);
+		cfg.blockDim = dim3(block);
 		cfg.dynamicSmemBytes = smem;
 		cfg.stream = h->stream;
 		cudaLaunchAttribute attr[1];
@@ -420,9 +420,23 @@ int launch_small_t(rtlsdr_gpu_scan *h, const SmallParams &prm)
 		cfg.numAttrs = 1;
 		CU(cudaLaunchKernelEx(&cfg, kern, prm));
 	} else {
-		kern<<<grid, kThreads, smem, h->stream>>>(prm);
+		kern<<<grid, block, smem, h->stream>>>(prm);
 	}
 	h->last_was_epilogue = false;
+	return 0;
+}
+
+template <int L, bool PEAK, bool IN16>
+int launch_small_t(rtlsdr_gpu_scan *h, const SmallParams &prm)
+{
+	auto kern = scan_small_kernel<L, PEAK, IN16>;
+	/* RTLSDR_GPU_DEBUG_SMEM_PAD: occupancy experiments only (extra bytes -> fewer CTAs per SM) */
+	static const int pad = getenv("RTLSDR_GPU_DEBUG_SMEM_PAD") ? atoi(getenv("RTLSDR_GPU_DEBUG_SMEM_PAD")) : 0;
+	const int smem = SmallSmem<L>::bytes + pad;
+	CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+	const int grid = std::min(prm.n_segs, h->num_sms * 8);
+	if (int rc = launch_after_epilogue(h, kern, grid, kThreads, smem, prm, !IN16))
+		return rc;
 	return check_launch(h, "scan_small_kernel");
 }
 
@@ -461,8 +475,8 @@ int launch_fused_boxcar_t(rtlsdr_gpu_scan *h, const FusedBoxcarParams &prm)
 	const int smem = FusedSmem<L>::bytes(prm.ds, NS);
 	const int grid = std::min(prm.n_segs, h->num_sms * 8);
 	CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-	k<<<grid, kThreads, smem, h->stream>>>(prm);
-	h->last_was_epilogue = false;
+	if (int rc = launch_after_epilogue(h, k, grid, kThreads, smem, prm))
+		return rc;
 	return check_launch(h, "scan_boxcar_fused_kernel");
 }
 
@@ -531,8 +545,8 @@ int launch_stream_boxcar_t(rtlsdr_gpu_scan *h, const FusedBoxcarParams &prm_in)
 	const int grid = std::min(prm.n_segs, h->num_sms);
 	auto k = scan_boxcar_stream_kernel<L, PEAK, FG, BG>;
 	CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-	k<<<grid, StreamShape<FG, BG>::threads, smem, h->stream>>>(prm);
-	h->last_was_epilogue = false;
+	if (int rc = launch_after_epilogue(h, k, grid, StreamShape<FG, BG>::threads, smem, prm))
+		return rc;
 	return check_launch(h, "scan_boxcar_stream_kernel");
 }
 
@@ -553,8 +567,8 @@ int launch_sym_boxcar_t(rtlsdr_gpu_scan *h, const FusedBoxcarParams &prm_in)
 	const int grid = std::min(prm.n_segs, h->num_sms);
 	auto k = scan_boxcar_sym_kernel<L, PEAK>;
 	CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-	k<<<grid, kSymThreads, smem, h->stream>>>(prm);
-	h->last_was_epilogue = false;
+	if (int rc = launch_after_epilogue(h, k, grid, kSymThreads, smem, prm))
+		return rc;
 	return check_launch(h, "scan_boxcar_sym_kernel");
 }
 
@@ -843,7 +857,10 @@ int launch_batch(rtlsdr_gpu_scan *h, const uint8_t *base, const uint8_t *d_desc,
 	const int4 *d_segs = (const int4 *)(d_desc + lay.off_segs);
 	const int *d_hops = (const int *)(d_desc + lay.off_hops);
 	int rc = 0;
-	if (h->path != PATH_SMALL_U8 || h->d_level)
+	/* paths whose first kernel after a report is a transform kernel with a pdl_wait() keep the flag */
+	const bool pdl_path = h->path == PATH_SMALL_U8 || h->path == PATH_RMS ||
+			      (h->path == PATH_SMALL_DECIM && fused_boxcar_ok(h));
+	if (!pdl_path || h->d_level)
 		h->last_was_epilogue = false;
 
 	if (h->d_level) {
@@ -872,7 +889,8 @@ int launch_batch(rtlsdr_gpu_scan *h, const uint8_t *base, const uint8_t *d_desc,
 		p.samples = h->d_smp64;
 		TimedScope ts(h);
 		const int blocks = std::max(1, std::min((n_reads + 7) / 8, h->num_sms * 8));
-		rms_kernel<<<blocks, 256, 0, h->stream>>>(p);
+		if ((rc = launch_after_epilogue(h, rms_kernel, blocks, 256, 0, p)))
+			return rc;
 		return check_launch(h, "rms_kernel");
 	}
 

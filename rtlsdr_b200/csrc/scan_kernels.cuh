@@ -2270,6 +2270,7 @@ rms_kernel(const SCAN_GRID_CONSTANT RmsParams prm)
 			const double dc = __ddiv_rn((double)t, dn);
 			const double err = __dsub_rn(__dmul_rn((double)(t * 2), dc), __dmul_rn(__dmul_rn(dc, dc), dn));
 			p -= (long long)round(err);
+			pdl_wait(); /* the accumulators may still be read by the previous interval's report epilogue */
 			atomicAdd((unsigned long long *)(prm.samples + prm.hop_of[e]), 1ull);
 			long long *dst = prm.avg + prm.hop_of[e];
 			if (prm.peak)
