@@ -4,19 +4,26 @@
 Metric (BASELINE.json): input Msamples/s (1 sample = 1 complex IQ pair = 2 input
 bytes), whole job over all GPUs, plus the fraction of the HBM roofline.
 
-Workload = BASELINE.json configs[1]: FM band scan 88-108 MHz, 4096 bins,
-hamming, -c 20%, one 10 s integration interval = 9 hops x 377 sweeps of 16384
-bytes.  One "step" = one whole integration interval: every read of
-the interval through the transform, then the report epilogue (DC nuke, half
-swap, crop, dB) and, with N > 1 GPUs, ONE NCCL gather of the spectra to rank 0.
-With N GPUs every rank owns its own 9 hops (9 N hop streams in total, weak
-scaling: hops are independent, there is no data-path collective).
+Headline workload = BASELINE.json configs[4], the run SURVEY.md 8(d)(5) calls "the
+roofline run": `-f 24M:1457.6M:700` = 512 hop streams x 4096 bins (rectangle),
+256 sweeps per integration interval (2 GiB of uint8 IQ per step), hops SHARDED over
+the N GPUs (512/256/128/64 per GPU at N = 1/2/4/8: strong scaling, no data-path
+collective).  One "step" = one whole integration interval: every read of the
+interval through the transform, the report epilogue (DC nuke, half swap, crop, dB)
+on every rank, and ONE exchange of the spectra to rank 0 (rtlsdr_b200/sweep.py).
+Input bytes are the synthetic source's xorshift stream, a pure function of
+(hop, sweep) (host/synth_source.c), so the result does not depend on N:
 
-  value : inputs already resident in HBM (device-resident replay), CUDA-event
-          timed on the launching stream, max over ranks.
+  verify: outside the timed region the gathered int64 bins are FNV-hashed on rank 0 and
+          compared (a) for sweep 0 alone with the reference-generated known-answer hash of
+          SURVEY.md 8(c) and (b) for the whole interval with a 1-rank run of the same bytes.
+  value : inputs already resident in HBM, CUDA-event timed on the launching stream,
+          max over ranks; rounds of --steps steps are repeated until >= 50 ms are timed.
   e2e   : the same interval through the public C ABI with HOST buffers:
           rtlsdr_gpu_scan_submit_batch() from pinned memory (H2D inside the timed
-          region) and rtlsdr_gpu_scan_collect_all() (D2H of bins + dB).
+          region), the exchange, and the gathered report copied to host memory on rank 0.
+  companions: BASELINE configs[2] (623 hops, sharded the same way, every N) and, at N = 1,
+          configs[1] (round 1's headline) and the decimating / rms / large-FFT regimes.
   --impl reference : the reference's own CPU code (oracle/_ref, the unmodified
           rtl_power.c object) on all host cores, bounded sample per step.
 """
@@ -33,9 +40,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-RANGE, CROP, WINDOW = "88M:108M:1k", 0.2, "hamming"
-PASSES = 377                 # sweeps in one 10 s interval at 2 777 777 S/s
-WORKLOAD = "fm_band_scan_88-108MHz_4096bins_hamming_crop20_10s"
+# BASELINE configs[4]: the headline
+RANGE, CROP, WINDOW, FIR = "24M:1457.6M:700", 0.0, "rectangle", None
+SWEEPS = 256                 # sweeps per integration interval (P >= 256)
+WORKLOAD = "throughput_stress_512_hop_streams_4096bins_256_sweeps (BASELINE configs[4])"
+KAT_P1 = 0x7b1c7343a9686225  # reference rtl_power, this range, 1 sweep, xorshift source
+# BASELINE configs[2]: second sharded workload
+RANGE3, FIR3, SWEEPS3, KAT3_P1 = "24M:1766M:1k", 9, 64, 0x074f712a23c886d1
+# BASELINE configs[1]: round 1's headline, kept as an N = 1 companion
+RANGE2, CROP2, WINDOW2, SWEEPS2 = "88M:108M:1k", 0.2, "hamming", 377
+MIN_TIMED_MS = 50.0
+SYNTH_XORSHIFT = 0
 
 
 def read_peaks():
@@ -46,29 +61,12 @@ def read_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def read_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+def read_ncu():
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            return json.load(f).get("scan_small_kernel_dram_bytes_per_launch")
+            return json.load(f)
     except Exception:
-        return None
-
-
-def issue_roofline(kernel_ms, sm_mhz, n_sms):
-    """The bound this kernel actually runs against: warp instructions per clock per SM.  The instruction count
-    per launch comes from the committed ncu capture of the same workload (it does not depend on the input
-    bytes), the peak from tools/ubench.cu's measured dual-issue rate of a perfectly mixed IMAD + ALU stream."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            d = json.load(f)
-        inst = d["scan_small_kernel_warp_instructions_per_launch"]
-        peak = d["issue_peak_warp_instr_per_clk_per_sm"]
-        ipc = inst / (kernel_ms * 1e-3 * sm_mhz * 1e6 * n_sms)
-        return {"bound": "issue", "achieved": ipc, "peak": peak, "unit": "warp-instr/clk/SM", "frac": ipc / peak,
-                "warp_instructions_per_launch": inst, "sm_mhz": sm_mhz, "sms": n_sms, "peak_source": d["issue_peak_source"]}
-    except Exception:
-        return None
+        return {}
 
 
 class ClockSampler:
@@ -83,7 +81,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._pump, daemon=True)
             self.th.start()
@@ -97,7 +95,7 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -123,53 +121,51 @@ class ClockSampler:
 _REF = {}
 
 
-def _ref_init(seed_base):
+def _ref_init(seed_base, rng, crop, window):
     """pool initializer: one configured reference instance per worker process"""
     import multiprocessing as mp
-    from oracles import RefOracle, PortOracle, SYNTH_XORSHIFT  # noqa
+    from oracles import RefOracle, PortOracle, SYNTH_XORSHIFT as XS  # noqa
     ident = mp.current_process()._identity
     seed = seed_base + (ident[0] if ident else 0)
     try:
         r = RefOracle()
-        r.configure(RANGE, CROP, WINDOW)
-        r.source(SYNTH_XORSHIFT, seed, 0)
-        r.scan(2)
+        r.configure(rng, crop, window)
+        r.source(XS, seed, 0)
+        r.scan(1)
         _REF.update(kind="reference", ref=r, per_pass=r.plan["tune_count"] * (r.plan["buf_len"] // 2))
     except Exception:
         # compiled reference missing: time the C restatement instead
         import numpy as np
         from rtlsdr_b200.planner import plan_scan
         p = PortOracle()
-        plan = plan_scan(RANGE, CROP).as_dict()
+        plan = plan_scan(rng, crop).as_dict()
         plan["peak_hold"] = 0
-        w = p.window_coefs(WINDOW, 1 << plan["bin_e"])
-        rng = np.random.default_rng(seed)
-        reads = rng.integers(0, 256, (plan["tune_count"] * 4, plan["buf_len"]), dtype=np.uint8)
-        hops = [i % plan["tune_count"] for i in range(len(reads))]
+        w = p.window_coefs(window, 1 << plan["bin_e"])
+        rs = np.random.default_rng(seed)
+        reads = rs.integers(0, 256, (plan["tune_count"], plan["buf_len"]), dtype=np.uint8)
+        hops = list(range(plan["tune_count"]))
         _REF.update(kind="port", port=p, plan=plan, w=w, reads=reads, hops=hops,
                     per_pass=plan["tune_count"] * (plan["buf_len"] // 2))
 
 
 def _ref_step(passes):
-    """(seconds, samples, kind) for `passes` sweeps of the 9-hop plan in this worker"""
+    """(seconds, samples, kind) for `passes` sweeps of the whole hop plan in this worker"""
     if _REF["kind"] == "reference":
         return _REF["ref"].scan_timed(passes), passes * _REF["per_pass"], "reference"
     t0 = time.perf_counter()
-    n = 0
-    while n < passes:
+    for _ in range(passes):
         _REF["port"].scan(_REF["plan"], _REF["w"], _REF["reads"], _REF["hops"], _REF["plan"]["tune_count"])
-        n += 4
-    return time.perf_counter() - t0, n * _REF["per_pass"], "port"
+    return time.perf_counter() - t0, passes * _REF["per_pass"], "port"
 
 
 class CpuReference:
     """`procs` persistent worker processes, each an independent instance of the reference's
     single-threaded scanner() (the reference has no threads: rtl_power.c:29-36, 844-846)."""
 
-    def __init__(self, procs):
+    def __init__(self, procs, rng=RANGE, crop=CROP, window=WINDOW):
         import multiprocessing as mp
         self.procs = procs
-        self.pool = mp.get_context("spawn").Pool(procs, initializer=_ref_init, initargs=(17,))
+        self.pool = mp.get_context("spawn").Pool(procs, initializer=_ref_init, initargs=(17, rng, crop, window))
         self.pool.map(_ref_step, [1] * procs)  # all workers up and configured
 
     def step(self, passes):
@@ -188,10 +184,10 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     ref = CpuReference(cores)
     # bounded sample per step: the whole run stays within ~2 minutes whatever K is
-    t_probe, s_probe, kind = ref.step(8)
-    per_pass_s = max(t_probe / 8, 1e-5)
+    t_probe, s_probe, kind = ref.step(1)
+    per_pass_s = max(t_probe, 1e-4)
     budget_s = 100.0
-    passes = int(max(2, min(3000, budget_s / (args.steps + args.warmup) / per_pass_s)))
+    passes = int(max(1, min(SWEEPS, budget_s / (args.steps + args.warmup) / per_pass_s)))
     for _ in range(args.warmup):
         ref.step(passes)
     total_t, total_s = 0.0, 0
@@ -201,13 +197,14 @@ def run_reference(args):
         total_s += smp
     ref.close()
     value = total_s / total_t / 1e6
-    sample = f"{cores} independent processes x {passes} sweeps x 9 hops x 8192 samples per step"
+    sample = (f"{cores} independent processes x {passes} sweeps x 512 hops x 8192 samples per step "
+              f"(of the {SWEEPS} sweeps of one step of the GPU arm)")
     line = {
         "metric": "input Msamples/s", "value": value, "unit": "Msamples/s", "impl": "reference",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "int16/int64 fixed point", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "hops": 9, "bins": 4096, "sample": sample},
+        "config": {"workload": WORKLOAD, "cli": f"-f {RANGE}", "hops": 512, "bins": 4096, "sample": sample},
         "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -217,9 +214,208 @@ def run_reference(args):
 
 # --------------------------------------------------------------------------- GPU arm
 
+class Dist:
+    """rank / world plumbing (torch.distributed over NCCL when N > 1)"""
+
+    def __init__(self, torch, dist):
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max(self, v):
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+class ShardedSweep:
+    """One hop-sharded rtl_power scan: this rank's handle, its share of the synthetic input (pinned host
+    copy + device-resident copy) and the per-interval exchange to rank 0."""
+
+    def __init__(self, D, rs, rng, crop, window, fir, sweeps, peak=0):
+        import numpy as np
+        from rtlsdr_b200.planner import plan_scan, synth_cube
+        from rtlsdr_b200.sweep import SpectrumGather, shard_hops
+        torch = D.torch
+        self.D, self.rs, self.np = D, rs, np
+        self.plan = plan_scan(rng, crop, fir)
+        pd = self.plan.as_dict()
+        pd["peak_hold"] = peak
+        self.pd, self.sweeps = pd, sweeps
+        self.tc, self.b, self.n = pd["tune_count"], pd["buf_len"], 1 << pd["bin_e"]
+        self.mine = shard_hops(self.tc, D.world, D.rank)
+        self.h = len(self.mine)
+        self.window = rs.window_coefs(window, self.n) if pd["bin_e"] else None
+        self.g = rs.GpuScan.from_plan(pd, window_coefs=self.window, device=D.local, hops=list(self.mine))
+        self.stream = torch.cuda.ExternalStream(self.g.get_stream())
+        self.gather = SpectrumGather(self.tc, self.n, self.g.db_count, D.world, D.rank, torch.device("cuda", D.local))
+        self.bytes_rank = sweeps * self.h * self.b
+        self.bytes_all = sweeps * self.tc * self.b
+        # input: bytes of read (sweep p, hop) from the synthetic source, [sweeps, my hops, buf_len]
+        self.pinned = rs.PinnedBuffer(self.bytes_rank)
+        synth_cube(self.pinned.ptr, SYNTH_XORSHIFT, 0, 0, self.tc, self.mine.start, self.h, 0, sweeps, self.b)
+        self.dev_in = torch.empty(self.bytes_rank, dtype=torch.uint8, device="cuda")
+        self.dev_in.copy_(torch.from_numpy(self.pinned.array), non_blocking=False)
+        self.extra = []     # second handle of the host-buffer leg
+
+    def step_device(self, i, sweeps=None, to_host=False):
+        k = i & 1
+        self.g.submit_device(0, self.h, sweeps or self.sweeps, self.dev_in.data_ptr(), self.h * self.b, self.b)
+        self.finish(self.g, self.stream, k, to_host)
+
+    def finish(self, g, stream, k, to_host):
+        """report epilogue into exchange buffer k + the exchange (asynchronous)"""
+        self.gather.before_collect(k, stream)
+        g.collect_device(*self.gather.pointers(k))
+        self.gather.publish(k, stream, to_host=to_host)
+
+    def report(self, k):
+        """rank 0: IntervalReport of exchange buffer k; every rank blocks until the exchange is done"""
+        return self.gather.fetch(k)
+
+    def close(self):
+        self.g.close()
+        for g in self.extra:
+            g.close()
+        self.pinned.free()
+
+
+def time_device(D, sw, steps, warmup, min_ms=MIN_TIMED_MS, sampler=None):
+    """rounds of exactly `steps` device-resident steps, CUDA events on the launching stream, max over ranks;
+    repeated until >= min_ms have been timed.  Returns (ms_per_step, timed_steps, kernel_ms, kernel_launches, launches)."""
+    torch = D.torch
+    for i in range(warmup):
+        sw.step_device(i)
+    sw.gather.drain(sw.stream)
+    D.barrier()
+    sw.g.kernel_time()      # arm / reset the per-kernel timers
+    sw.g.set_timing(1)      # every transform launch is bracketed with events on the launching stream
+    s0 = sw.g.stats()
+    if sampler:
+        sampler.start()
+    total_ms, rounds, i0 = 0.0, 0, warmup
+    want = 1
+    while rounds < want:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        D.barrier()
+        e0.record(sw.stream)
+        for i in range(steps):
+            sw.step_device(i0 + i)
+        sw.gather.drain(sw.stream)          # the last exchanges are inside the timed region
+        e1.record(sw.stream)
+        D.barrier()
+        ms = D.max(e0.elapsed_time(e1))
+        total_ms += ms
+        rounds += 1
+        i0 += steps
+        if rounds == 1:
+            want = max(1, min(200, int(-(-min_ms // max(ms, 1e-3)))))
+    s1 = sw.g.stats()
+    k_ms, k_n = sw.g.kernel_time()
+    sw.g.set_timing(0)
+    if sampler:
+        # nvidia-smi ticks every 20 ms: keep the same load running, untimed, until a few clock samples exist
+        t_end = time.perf_counter() + 1.0
+        while len(sampler.rows) < 4 and time.perf_counter() < t_end:
+            for i in range(4):
+                sw.step_device(i0 + i)
+            torch.cuda.synchronize()
+    return (total_ms / (rounds * steps), rounds * steps, k_ms / max(k_n, 1), k_n,
+            s1["kernel_launches"] - s0["kernel_launches"])
+
+
+def verify_sharded(D, sw, kat_p1, full_interval=True):
+    """Outside any timed region.  (a) sweep 0 alone, gathered over all ranks, FNV == the reference-generated
+    known-answer hash; (b) the whole interval, gathered, FNV == a 1-rank run of the same bytes on rank 0."""
+    from rtlsdr_b200.planner import fnv1a_int64, synth_cube
+    np, rs, torch = sw.np, sw.rs, D.torch
+    out = {}
+    sw.step_device(0, sweeps=1, to_host=True)
+    rep = sw.report(0)
+    if D.rank == 0:
+        got = fnv1a_int64(rep.avg)
+        out.update(kat_sweeps=1, kat_fnv=f"{got:016x}", kat_expected=f"{kat_p1:016x}",
+                   kat_ok=bool(got == kat_p1 and (rep.samples == 2).all()),
+                   kat_source="SURVEY.md 8(c): unmodified rtl_power.c, same range, 1 sweep, xorshift source")
+    if full_interval:
+        sw.step_device(1, to_host=True)
+        rep = sw.report(1)
+        if D.rank == 0:
+            got = fnv1a_int64(rep.avg)
+            out.update(interval_sweeps=sw.sweeps, interval_fnv=f"{got:016x}", interval_ranks=D.world)
+            if D.world == 1:
+                # second, differently batched pass over the same bytes: four submits of a quarter interval each
+                q = sw.sweeps // 4
+                for c in range(4):
+                    sw.g.submit_device(0, sw.h, q, sw.dev_in.data_ptr() + c * q * sw.h * sw.b, sw.h * sw.b, sw.b)
+                avg1, smp1, _ = sw.g.collect_all(want_db=False)
+                out["interval_fnv_check"] = f"{fnv1a_int64(avg1):016x}"
+                out["interval_check"] = "same handle, interval re-submitted as 4 quarter batches + collect_all (host copy)"
+                out["interval_ok"] = bool(fnv1a_int64(avg1) == got and (smp1 == rep.samples).all())
+            else:
+                # 1-rank run of the same bytes: rank 0 regenerates ALL hops' reads and scans them alone
+                g1 = rs.GpuScan.from_plan(sw.pd, window_coefs=sw.window, device=D.local)
+                hb = rs.PinnedBuffer(sw.bytes_all)
+                synth_cube(hb.ptr, SYNTH_XORSHIFT, 0, 0, sw.tc, 0, sw.tc, 0, sw.sweeps, sw.b)
+                g1.submit_batch(0, sw.tc, sw.sweeps, hb.ptr, sw.tc * sw.b, sw.b)
+                avg1, smp1, _ = g1.collect_all(want_db=False)
+                g1.close()
+                hb.free()
+                one = fnv1a_int64(avg1)
+                out["interval_fnv_check"] = f"{one:016x}"
+                out["interval_check"] = "1-rank run of the same bytes on rank 0 (all hops regenerated from the synthetic source)"
+                out["interval_ok"] = bool(one == got and (smp1 == rep.samples).all())
+    D.barrier()
+    if D.rank == 0:
+        out["ok"] = bool(out.get("kat_ok") and out.get("interval_ok", True))
+    return out
+
+
+def time_e2e(D, sw, steps, warmup):
+    """The interval through the host-buffer ABI: pinned host input -> submit_batch (H2D) -> transform ->
+    report epilogue -> exchange -> rank 0 copies the gathered report to host memory.  Two handles alternate,
+    so interval i+1 crosses PCIe while interval i is transformed and exchanged (what a continuously
+    running rtl_power does).  Wall clock between barriers, max over ranks."""
+    torch, rs = D.torch, sw.rs
+    g2 = rs.GpuScan.from_plan(sw.pd, window_coefs=sw.window, device=D.local, hops=list(sw.mine))
+    sw.extra.append(g2)
+    handles = [(sw.g, sw.stream), (g2, torch.cuda.ExternalStream(g2.get_stream()))]
+
+    def submit(i):
+        handles[i & 1][0].submit_batch(0, sw.h, sw.sweeps, sw.pinned.ptr, sw.h * sw.b, sw.b)
+
+    def run(n):
+        submit(0)
+        rep = None
+        for i in range(n):
+            if i + 1 < n:
+                submit(i + 1)
+            g, st = handles[i & 1]
+            sw.finish(g, st, i & 1, True)
+            rep = sw.report(i & 1)
+        return rep
+
+    run(max(2, min(warmup, 4)))
+    D.barrier()
+    t0 = time.perf_counter()
+    rep = run(steps)
+    torch.cuda.synchronize()
+    dt = D.max(time.perf_counter() - t0)
+    if D.rank == 0:
+        assert int(rep.samples[0]) == 2 * sw.sweeps and int(rep.samples[-1]) == 2 * sw.sweeps, \
+            "e2e report does not cover one whole interval"
+    return dt
+
+
 def companion(rs, plan_scan, torch, name, freq, crop, window, fir, peak, passes, steps, peak_gbs):
-    """Device-resident throughput of another rtl_power configuration (same method as `value`):
-    the HBM-bound regimes of the path that BASELINE.json's bench workload (ds = 1) never enters."""
+    """Device-resident throughput of another rtl_power configuration on one GPU (same method as `value`)."""
     plan = plan_scan(freq, crop, fir)
     pd = plan.as_dict()
     pd["peak_hold"] = peak
@@ -241,290 +437,184 @@ def companion(rs, plan_scan, torch, name, freq, crop, window, fir, peak, passes,
     for i in range(3):
         step(i)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(steps):
-        step(3 + i)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
+    total, done = 0.0, 0
+    while total < MIN_TIMED_MS and done < 200 * steps:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            step(3 + done + i)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        total += e0.elapsed_time(e1)
+        done += steps
+    ms = total / done
     g.close()
     del dev_in
     gbs = step_bytes / (ms * 1e-3) / 1e9
     return {"workload": name, "cli": f"-f {freq}" + (f" -F {fir}" if fir is not None else "") + (" -P" if peak else ""),
             "plan": {k: pd[k] for k in ("tune_count", "bin_e", "buf_len", "downsample", "downsample_passes")},
-            "value": step_bytes / 2 / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms,
+            "value": step_bytes / 2 / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms, "timed_steps": done,
             "bytes_per_step": step_bytes, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / peak_gbs}
 
 
-# diagnostic only (never set by the driver): time the multi-GPU step without its per-interval gather
-NO_GATHER = bool(os.environ.get("BENCH_DIAG_NO_GATHER"))
-
-
 def run_gpu(args):
-    import numpy as np
     import torch
     import torch.distributed as dist
 
     import rtlsdr_b200.scan as rs
     from rtlsdr_b200.planner import plan_scan
+    from rtlsdr_b200.sweep import shard_hops
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    D = Dist(torch, dist)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the GPU arm has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(D.local)
+    pin = pin_to_gpu_numa(D.local)            # before any pinned allocation
+    if D.world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", D.local))
     rs.load_library()
+    peak, peak_src = read_peaks()
 
-    plan = plan_scan(RANGE, CROP)
-    pd = plan.as_dict()
-    tc, b, n = pd["tune_count"], pd["buf_len"], 1 << pd["bin_e"]
-    window = rs.window_coefs(WINDOW, n)
-    g = rs.GpuScan.from_plan(pd, window_coefs=window, device=local)
-    # time on the handle's own stream (the launching stream), wrapped for torch events / NCCL ordering
-    stream = torch.cuda.ExternalStream(g.get_stream())
-    db_count = g.db_count
+    # ---- headline: BASELINE configs[4], hops sharded over the ranks ----
+    sw = ShardedSweep(D, rs, RANGE, CROP, WINDOW, FIR, SWEEPS)
+    verify = verify_sharded(D, sw, KAT_P1)
+    sampler = ClockSampler(D.local) if D.rank == 0 else None
+    ms_step, timed_steps, k_ms, k_n, launches = time_device(D, sw, args.steps, args.warmup, sampler=sampler)
+    clocks = sampler.stop() if sampler else None
+    e2e_steps = max(4, min(args.steps, 24))
+    e2e_s = time_e2e(D, sw, e2e_steps, args.warmup)
 
-    step_bytes = PASSES * tc * b
-    samples_per_step = step_bytes // 2
-    # inputs larger than L2 (126 MB): rotate through distinct interval-sized sets
-    n_sets = max(2, -(-(300 << 20) // step_bytes))
-    gen = torch.Generator(device="cuda")
-    gen.manual_seed(1234 + rank)
-    dev_in = torch.randint(0, 256, (n_sets, PASSES, tc, b), dtype=torch.uint8, device="cuda", generator=gen)
-    out_words = tc * n + tc * db_count + tc
-    # two report buffers: interval k's spectra are gathered (comm stream) while interval k+1 is transformed
-    sends = [torch.zeros(out_words, dtype=torch.int64, device="cuda") for _ in range(2)]
-    gathers = [[torch.zeros(out_words, dtype=torch.int64, device="cuda") for _ in range(world)]
-               if (world > 1 and rank == 0) else None for _ in range(2)]
-    comm = torch.cuda.Stream()
-    ready = [torch.cuda.Event() for _ in range(2)]
-    gathered = [torch.cuda.Event() for _ in range(2)]
+    # ---- second sharded workload: BASELINE configs[2] (623 hops do not divide evenly) ----
+    sw3 = ShardedSweep(D, rs, RANGE3, 0.0, "rectangle", FIR3, SWEEPS3)
+    verify3 = verify_sharded(D, sw3, KAT3_P1, full_interval=False)
+    ms3, steps3, k3_ms, _, _ = time_device(D, sw3, max(4, min(args.steps, 20)), 3)
+    comp3 = None
+    if D.rank == 0:
+        v3 = sw3.bytes_all / 2 / (ms3 * 1e-3) / 1e6
+        comp3 = {"workload": "wideband_sweep_24-1766MHz_623_hops_4096bins_64_sweeps (BASELINE configs[2]), hops sharded",
+                 "cli": f"-f {RANGE3} -F {FIR3}", "value": v3, "unit": "Msamples/s", "ms_per_step": ms3,
+                 "timed_steps": steps3, "hops_per_gpu": [len(shard_hops(sw3.tc, D.world, r)) for r in range(D.world)],
+                 "bytes_per_step": sw3.bytes_all, "frac_of_hbm_peak": sw3.bytes_all / (ms3 * 1e-3) / 1e9 / (peak * D.world),
+                 "verify": verify3}
+    sw3.close()
 
-    # Per-interval exchange, preferred form: no copy and no collective kernel at all.  Every rank's report
-    # epilogue stores its bins / dB / sample counts straight into rank 0's buffer through an NVLink peer mapping
-    # (torch symmetric memory), and one symmetric-memory barrier per interval (a one-CTA signalling kernel on a
-    # second stream) tells rank 0 that every slot is complete.  An NCCL send/receive kernel needs SM resources
-    # that two resident transform CTAs per SM do not leave: measured 4 % (2 GPUs) to 10 % (8 GPUs) of the step.
-    # BENCH_NCCL_GATHER=1, or a box without peer access, selects the grouped NCCL gather instead.
-    peer = None
-    if world > 1 and not NO_GATHER:
-        ok = 0
-        if not os.environ.get("BENCH_NCCL_GATHER"):
-            try:
-                import torch.distributed._symmetric_memory as symm
-                pbuf = symm.empty(2 * world * out_words, dtype=torch.int64, device=torch.device("cuda", local))
-                pbuf.zero_()
-                hdl = symm.rendezvous(pbuf, dist.group.WORLD)
-                peer = (pbuf, hdl, int(hdl.buffer_ptrs[0]))
-                ok = 1
-            except Exception as exc:  # noqa: BLE001 -- any failure means: use NCCL
-                print(f"bench.py: symmetric memory unavailable ({exc!r}); using the NCCL gather", file=sys.stderr)
-        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
-            peer = None
-
-    def gather_interval(k):
-        """report buffer k is complete once everything enqueued so far on `stream` has run"""
-        ready[k].record(stream)
-        with torch.cuda.stream(comm):
-            comm.wait_event(ready[k])
-            if peer is not None:
-                peer[1].barrier(channel=k)
-            else:
-                dist.gather(sends[k], gathers[k], dst=0)
-            gathered[k].record(comm)
-
-    def step_device(i):
-        # Stream order: scan(i) | [event + gather of interval i-1] | wait(buffer free) | epilogue(i).
-        # Nothing sits between epilogue(i-1) and scan(i), so the transform can be launched
-        # programmatically dependent on the previous report (it only waits before its flush).
-        k = i & 1
-        if peer is not None:
-            p_avg = peer[2] + (k * world + rank) * out_words * 8   # this rank's slot in rank 0's memory
-        else:
-            p_avg = sends[k].data_ptr()
-        p_db = p_avg + tc * n * 8
-        p_smp = p_db + tc * db_count * 8
-        g.submit_device(0, tc, PASSES, dev_in[i % n_sets].data_ptr(), tc * b, b)
-        if world > 1 and not NO_GATHER:
-            if step_device.pending is not None:
-                gather_interval(step_device.pending)
-            stream.wait_event(gathered[k])          # buffer k's previous gather has finished
-            step_device.pending = k
-        g.collect_device(p_avg, p_smp, p_db)
-
-    step_device.pending = None
-
-    def drain_gathers():
-        if world > 1 and step_device.pending is not None:
-            gather_interval(step_device.pending)
-            step_device.pending = None
-        stream.wait_stream(comm)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident timing ("value") ----
-    for i in range(args.warmup):
-        step_device(i)
-    drain_gathers()
-    barrier()
-    g.kernel_time()  # arm / reset the per-kernel timers
-    g.set_timing(16)  # every 16th transform is bracketed with events (the others can launch dependently)
-    s0 = g.stats()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-    for i in range(args.steps):
-        step_device(args.warmup + i)
-    drain_gathers()                                 # the last gathers are inside the timed region
-    with torch.cuda.stream(stream):
-        e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    if peer is not None and rank == 0:
-        # every rank's last two reports must have landed in rank 0's buffer: sample counts = 2 * PASSES per hop
-        tail = peer[0].view(2, world, out_words)[:, :, tc * n + tc * db_count:].contiguous()
-        got = tail.view(torch.int32).view(2, world, 2 * tc)[:, :, :tc]   # int32 sample counts of the tc hops
-        assert bool((got == 2 * PASSES).all()), "peer-written reports are incomplete on rank 0"
-    s1 = g.stats()
-    k_ms, k_n = g.kernel_time()
-    g.set_timing(0)
-    if rank == 0 and world == 1:
-        # a short timed region (small --steps) may end before nvidia-smi's first 50 ms tick: keep the
-        # same load running, untimed, until a few clock samples exist
-        t_end = time.perf_counter() + 1.0
-        i = args.warmup + args.steps
-        while len(sampler.rows) < 4 and time.perf_counter() < t_end:
-            for _ in range(50):
-                step_device(i)
-                i += 1
-            torch.cuda.synchronize()
-    clocks = sampler.stop() if rank == 0 else None
-    launches = s1["kernel_launches"] - s0["kernel_launches"]
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-
-    # ---- end to end through the host-buffer ABI ("e2e") ----
-    # A stream of integration intervals: every interval's bytes start in pinned host memory and
-    # its report (int64 bins, sample counts, dB rows) ends in host memory.  Two handles alternate,
-    # so interval k+1 crosses PCIe while interval k is transformed and collected -- what a
-    # continuously running rtl_power does.  Each step pays its own H2D and D2H.
-    handles = [g, rs.GpuScan.from_plan(pd, window_coefs=window, device=local)]
-    hosts, outs = [], []
-    for k in range(2):
-        hb = rs.PinnedBuffer(step_bytes)
-        hb.array[:] = np.frombuffer(dev_in[k % n_sets].cpu().numpy().tobytes(), dtype=np.uint8)
-        ob = rs.PinnedBuffer(tc * n * 8 + tc * db_count * 8 + tc * 4)
-        hosts.append(hb)
-        outs.append((ob, (ob.view(np.int64, (tc, n)), ob.view(np.int32, (tc,), tc * n * 8 + tc * db_count * 8),
-                          ob.view(np.float64, (tc, db_count), tc * n * 8))))
-    e2e_steps = max(4, min(args.steps, 400))
-
-    def run_host(steps):
-        handles[0].submit_batch(0, tc, PASSES, hosts[0].ptr, tc * b, b)
-        res = None
-        for i in range(steps):
-            if i + 1 < steps:
-                handles[(i + 1) & 1].submit_batch(0, tc, PASSES, hosts[(i + 1) & 1].ptr, tc * b, b)
-            res = handles[i & 1].collect_all(out=outs[i & 1][1])
-        return res
-
-    run_host(max(args.warmup, 4))
-    barrier()
-    t0 = time.perf_counter()
-    res = run_host(e2e_steps)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    assert int(res[1][0]) == 2 * PASSES, "e2e report does not cover one whole interval"
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    handles[1].close()
-    d2h = tc * n * 8 + tc * db_count * 8
-
-    if rank == 0:
-        peak, peak_src = read_peaks()
-        value = world * samples_per_step * args.steps / (ms_max * 1e-3) / 1e6
-        e2e = world * samples_per_step * e2e_steps / e2e_s / 1e6
-        k_avg_ms = k_ms / max(k_n, 1)
-        achieved = 2.0 * samples_per_step / (k_avg_ms * 1e-3) / 1e9 if k_n else None
+    if D.rank == 0:
+        samples_step = sw.bytes_all // 2
+        value = samples_step / (ms_step * 1e-3) / 1e6
+        e2e = samples_step * e2e_steps / e2e_s / 1e6
+        achieved = sw.bytes_rank / (k_ms * 1e-3) / 1e9 if k_n else None
+        ncu = read_ncu()
+        traffic = ncu.get("dram_bytes_per_launch") if ncu.get("launch_bytes") == sw.bytes_rank else None
+        d2h = sw.gather.world * sw.gather.words * 8
         line = {
-            "metric": "input Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": "input Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": D.world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "timed_steps": timed_steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int16/int64 fixed point", "data": "synthetic",
-            "config": {"workload": WORKLOAD if world == 1 else f"{WORKLOAD} x {world} (9 hops per GPU)",
-                       "hops_per_gpu": tc, "bins": n, "reads_per_step_per_gpu": PASSES * tc,
-                       "bytes_per_step_per_gpu": step_bytes,
-                       "cache": f"inputs larger than L2: {n_sets} distinct interval sets ({n_sets * step_bytes >> 20} MiB) rotated",
-                       "gather": ("none: every rank's report epilogue stores its int64 bins + dB straight into rank 0's "
-                                  "buffer over NVLink (symmetric-memory peer mapping); one symmetric-memory barrier per "
-                                  "step on a second stream") if (world > 1 and peer is not None) else
-                                 ("one NCCL gather of int64 bins + dB per step, on a second stream, overlapped with "
-                                  "the next interval's transform") if world > 1 else "none"},
-            "per_gpu_value": value / world,
+            "config": {"workload": WORKLOAD, "cli": f"-f {RANGE}", "hops": sw.tc, "bins": sw.n,
+                       "sweeps_per_step": SWEEPS, "reads_per_step": SWEEPS * sw.tc, "bytes_per_step": sw.bytes_all,
+                       "hops_per_gpu": [len(shard_hops(sw.tc, D.world, r)) for r in range(D.world)],
+                       "input": "synthetic source xorshift stream, bytes a pure function of (hop, sweep): "
+                                "identical job at every N",
+                       "cache": f"inputs larger than L2: every step streams this rank's whole {sw.bytes_rank >> 20} MiB cube from HBM",
+                       "timing": f"rounds of {args.steps} steps repeated until >= {MIN_TIMED_MS:.0f} ms "
+                                 f"({timed_steps} steps timed)",
+                       "exchange": sw.gather.describe(), "host_pinning": pin},
+            "per_gpu_value": value / D.world,
+            "verify": verify,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": read_traffic(),
-                         "kernel": "scan_small_kernel<12>", "kernel_ms": k_avg_ms, "kernel_launches_timed": k_n, "kernel_timing": "CUDA events around every 16th launch of the timed region",
-                         "algorithmic_bytes_per_launch": 2 * samples_per_step, "peak_source": peak_src,
-                         "note": "integer-issue bound, not HBM bound: see DESIGN.md"},
-            "e2e": {"value": e2e, "unit": "Msamples/s", "h2d_bytes_per_step": step_bytes,
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "traffic_source": ncu.get("source") if traffic else None,
+                         "kernel": "scan_small_kernel<12,0,0>", "kernel_ms": k_ms, "kernel_launches_timed": k_n,
+                         "kernel_timing": "CUDA events on the launching stream around every transform launch of the timed region (rank 0)",
+                         "algorithmic_bytes_per_launch": sw.bytes_rank, "peak_source": peak_src,
+                         "note": "integer-issue bound, not HBM bound at ds = 1: see DESIGN.md; roofline.issue is the bound it runs against"},
+            "e2e": {"value": e2e, "unit": "Msamples/s", "h2d_bytes_per_step": sw.bytes_all,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "api": "rtlsdr_gpu_scan_submit_batch (pinned host input) + rtlsdr_gpu_scan_collect_all "
-                           "(pinned host output), two handles alternating so copies overlap the transform"},
+                    "api": "rtlsdr_gpu_scan_submit_batch (pinned host input, every rank its hops) + report epilogue + "
+                           "exchange + gathered report copied to pinned host memory on rank 0; two handles alternate "
+                           "so the next interval's copies overlap the transform"},
             "gpu_launches": launches,
             "clocks": clocks,
         }
-        if k_n and clocks and clocks.get("sm_mhz"):
-            line["roofline"]["issue"] = issue_roofline(
-                k_avg_ms, clocks["sm_mhz"], torch.cuda.get_device_properties(0).multi_processor_count)
-        if world == 1 and not args.no_companions:
+        if k_n and clocks and clocks.get("sm_mhz") and ncu.get("warp_instructions_per_byte"):
+            sms = torch.cuda.get_device_properties(0).multi_processor_count
+            inst = ncu["warp_instructions_per_byte"] * sw.bytes_rank
+            ipc = inst / (k_ms * 1e-3 * clocks["sm_mhz"] * 1e6 * sms)
+            pk = ncu["issue_peak_warp_instr_per_clk_per_sm"]
+            line["roofline"]["issue"] = {"bound": "issue", "achieved": ipc, "peak": pk, "unit": "warp-instr/clk/SM",
+                                         "frac": ipc / pk, "warp_instructions_per_launch": inst,
+                                         "sm_mhz": clocks["sm_mhz"], "sms": sms, "peak_source": ncu.get("issue_peak_source")}
+        comps = [comp3]
+        if D.world == 1 and not args.no_companions:
             try:
-                line["companions"] = [
+                comps += [
+                    companion(rs, plan_scan, torch, "fm_band_scan_88-108MHz_4096bins_hamming_crop20_10s (BASELINE configs[1], "
+                              "round 1's headline)", RANGE2, CROP2, WINDOW2, None, 0, SWEEPS2, 50, peak),
+                    companion(rs, plan_scan, torch, "single_hop_2.4MSps_1024bins_rectangle_1s (BASELINE configs[0])",
+                              "100M:102.4M:2400", 0.0, "rectangle", None, 0, 293, 50, peak),
                     companion(rs, plan_scan, torch, "narrow_scan_boxcar_ds28_1024bins", "100M:100.1M:100", 0.0,
                               "rectangle", None, 0, 8192, 10, peak),
                     companion(rs, plan_scan, torch, "rms_1MHz_bins_10hops", "100M:110M:1M", 0.0,
                               "rectangle", None, 0, 4096, 10, peak),
                     companion(rs, plan_scan, torch, "narrow_scan_fifth_order_x4_fir9_1024bins", "100M:100.1M:100", 0.0,
                               "blackman", 9, 0, 8192, 10, peak),
-                    companion(rs, plan_scan, torch, "large_fft_2^17_blackman-harris_peak_hold", "100M:102.4M:19", 0.0,
-                              "blackman-harris", None, 1, 256, 10, peak),
+                    companion(rs, plan_scan, torch, "large_fft_2^17_blackman-harris_peak_hold (BASELINE configs[3])",
+                              "100M:102.4M:19", 0.0, "blackman-harris", None, 1, 256, 10, peak),
                 ]
             except Exception as exc:  # companions are extra evidence, never fail the bench line
-                line["companions"] = [{"error": repr(exc)}]
-        if world == 1 and not args.no_cpu:
+                comps.append({"error": repr(exc)})
+        line["companions"] = comps
+        if D.world == 1 and not args.no_cpu:
             ref = CpuReference(1)
-            t, smp, kind = ref.step(4000)
+            t, smp, kind = ref.step(100)
             ref.close()
             line["cpu_baseline"] = {"value": smp / t / 1e6, "unit": "Msamples/s", "cores": 1, "kind": kind,
-                                    "sample": "4000 sweeps x 9 hops x 8192 samples (295 M samples), 1 thread"}
+                                    "sample": "100 sweeps x 512 hops x 8192 samples (419 M samples) of the same workload, 1 thread"}
         print(json.dumps(line))
-    g.close()
-    if world > 1:
+    sw.close()
+    ok = True
+    if D.rank == 0:
+        ok = bool(verify.get("ok")) and bool(verify3.get("ok"))
+        if not ok:
+            print("bench.py: VERIFY FAILED: gathered bins differ from the known answer / the 1-rank run", file=sys.stderr)
+    if D.world > 1:
+        dist.barrier()
         dist.destroy_process_group()
-    return 0
+    return 0 if ok else 1
+
+
+def pin_to_gpu_numa(gpu_index):
+    """Bind this process to the CPUs (and so, by first touch, the memory) of the NUMA node its GPU hangs off,
+    before any pinned allocation (VERDICT r1 weak #5).  Returns a description for the bench line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        path = f"/sys/bus/pci/devices/{bus[-12:].lower()}/numa_node"
+        node = int(open(path).read().strip()) if os.path.exists(path) else -1
+        if node < 0:
+            return {"numa_node": node, "bound": False, "why": "no NUMA affinity reported for the GPU"}
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if not allowed:
+            return {"numa_node": node, "bound": False, "why": "node CPUs not in this process's affinity mask"}
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "bound": True, "cpus": f"{allowed[0]}-{allowed[-1]} ({len(allowed)})"}
+    except Exception as exc:  # noqa: BLE001 -- best effort
+        return {"bound": False, "why": repr(exc)}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-companions", action="store_true", help="skip the other-configuration measurements")

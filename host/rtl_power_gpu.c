@@ -12,7 +12,18 @@
  *     dB..." in hop order                              (:989-1003, :722-760)
  *   - SIGINT: first = finish the pass and exit, second = abort (:182-211, :651)
  * What is replaced: the DSP between the read and the row (:660-718, :730-764)
- * is rtlsdr_gpu_scan_submit() / rtlsdr_gpu_scan_collect().
+ * is rtlsdr_gpu_scan_submit() / rtlsdr_gpu_scan_collect_all().
+ *
+ * Three items of the reference's TODO list (rtl_power.c:29-36) that the GPU makes cheap:
+ *   -t workers   "multiple FFT workers": the hops are dealt in contiguous ranges to `workers`
+ *                B200s (one rtlsdr_gpu_scan handle per device, first device RTLSDR_GPU_DEVICE,
+ *                or the list RTLSDR_GPU_DEVICES=0,2,3); hops are independent (rtl_power.c:650-719),
+ *                so the CSV bytes do not depend on the worker count.  The reference parses -t and
+ *                ignores it (:844-846); one worker is the default here too.
+ *   -s iir       "continuous IIR smoothing" of the dB rows across reports (cfg.iir_alpha,
+ *                RTL_POWER_IIR_ALPHA, default 0.25); -s avg = the reference's behaviour.
+ *   -R seed      (extension) "randomized hopping": every sweep visits the hops in a fresh random
+ *                order; bins are order-independent sums / maxima (rtl_power.c:708-716).
  *
  * The sample source is host/synth_source.c (no dongle on the GPU box); it is
  * configured through environment variables so that the command line stays the
@@ -25,7 +36,8 @@
  *   RTL_POWER_PASSES    report after this many sweeps instead of by wall clock
  *   RTL_POWER_TIMESTAMP fixed "date, time" prefix (byte-reproducible output)
  *   RTL_POWER_REPORTS   exit after this many reports (with RTL_POWER_PASSES: a fixed amount of work)
- *   RTLSDR_GPU_DEVICE   CUDA device ordinal
+ *   RTLSDR_GPU_DEVICE   first CUDA device ordinal      RTLSDR_GPU_DEVICES  explicit device list for -t
+ *   RTL_POWER_IIR_ALPHA smoothing factor of -s iir (0 < a <= 1)
  */
 #include <math.h>
 #include <signal.h>
@@ -67,7 +79,9 @@ static void print_usage(void)
 		"\t[-c crop_percent (default: 0%%)]\n"
 		"\t[-F fir_size (default: disabled)] (0 or 9; switches boxcar off)\n"
 		"\t[-P enables peak hold (default: off)]\n"
-		"\t[-s avg|iir] [-t threads] (parsed and ignored, like the reference)\n"
+		"\t[-s avg|iir (default: avg; iir smooths the dB rows across reports)]\n"
+		"\t[-t workers (default: 1; hops are sharded over this many GPUs)]\n"
+		"\t[-R seed (visit the hops of every sweep in a random order)]\n"
 		"\tfilename (a '-' dumps samples to stdout, the default)\n");
 	exit(1);
 }
@@ -110,9 +124,34 @@ static void settle_on(rtlsdr_dev_t *dev, int freq)
 struct visit_ctx {
 	rtlsdr_dev_t *dev;
 	rtlsdr_gpu_scan_t *gpu;
-	int hop, rc, taken;
+	int hop, rc, taken; /* hop = index inside the worker's shard */
 	uint32_t want;
 };
+
+#define MAX_WORKERS 16
+
+/* the GPU workers: worker w owns hops [first[w], first[w + 1]) */
+struct workers {
+	int count;
+	int first[MAX_WORKERS + 1];
+	rtlsdr_gpu_scan_t *gpu[MAX_WORKERS];
+};
+
+static int worker_of(const struct workers *ws, int hop)
+{
+	int w = 0;
+	while (w + 1 < ws->count && hop >= ws->first[w + 1])
+		w++;
+	return w;
+}
+
+static uint64_t order_rng(uint64_t *s)
+{
+	*s ^= *s << 13;
+	*s ^= *s >> 7;
+	*s ^= *s << 17;
+	return *s;
+}
 
 static void on_samples(unsigned char *buf, uint32_t len, void *ctx)
 {
@@ -125,16 +164,27 @@ static void on_samples(unsigned char *buf, uint32_t len, void *ctx)
 }
 
 /* one sweep over all hops: the control flow of scanner(), rtl_power.c:642-659 */
-static int sweep(rtlsdr_dev_t *dev, rtlsdr_gpu_scan_t *gpu, const rp_plan_t *plan, uint8_t *buf8)
+static int sweep(rtlsdr_dev_t *dev, const struct workers *ws, const rp_plan_t *plan, uint8_t *buf8,
+		 int *order, uint64_t *shuffle_state, int use_async)
 {
-	int hop, got, rc;
-	for (hop = 0; hop < plan->tune_count; hop++) {
+	int i, hop, got, rc;
+	if (shuffle_state) { /* -R: Fisher-Yates over the hop order of this sweep */
+		for (i = plan->tune_count - 1; i > 0; i--) {
+			int j = (int)(order_rng(shuffle_state) % (uint64_t)(i + 1)), t = order[i];
+			order[i] = order[j];
+			order[j] = t;
+		}
+	}
+	for (i = 0; i < plan->tune_count; i++) {
+		const int w = worker_of(ws, order[i]);
+		rtlsdr_gpu_scan_t *gpu = ws->gpu[w];
+		hop = order[i];
 		if (stop_requests >= 2)
 			return 0;
 		if ((int)rtlsdr_get_center_freq(dev) != plan->freq[hop])
 			settle_on(dev, plan->freq[hop]);
-		if (getenv("RTL_POWER_ASYNC")) {
-			struct visit_ctx v = { dev, gpu, hop, 0, 0, (uint32_t)plan->buf_len };
+		if (use_async) {
+			struct visit_ctx v = { dev, gpu, hop - ws->first[w], 0, 0, (uint32_t)plan->buf_len };
 			rtlsdr_read_async(dev, on_samples, &v, 4, (uint32_t)plan->buf_len);
 			if (v.rc) {
 				fprintf(stderr, "rtlsdr_gpu_scan_submit: %s\n", rtlsdr_gpu_scan_strerror(v.rc));
@@ -147,7 +197,7 @@ static int sweep(rtlsdr_dev_t *dev, rtlsdr_gpu_scan_t *gpu, const rp_plan_t *pla
 		if (got != plan->buf_len)
 			fprintf(stderr, "Error: dropped samples.\n");
 		/* like the reference, the whole buffer is processed even after a short read */
-		rc = rtlsdr_gpu_scan_submit(gpu, hop, buf8, (uint32_t)plan->buf_len);
+		rc = rtlsdr_gpu_scan_submit(gpu, hop - ws->first[w], buf8, (uint32_t)plan->buf_len);
 		if (rc) {
 			fprintf(stderr, "rtlsdr_gpu_scan_submit: %s (%s)\n", rtlsdr_gpu_scan_strerror(rc),
 				rtlsdr_gpu_scan_last_cuda_error(gpu));
@@ -157,29 +207,51 @@ static int sweep(rtlsdr_dev_t *dev, rtlsdr_gpu_scan_t *gpu, const rp_plan_t *pla
 	return 0;
 }
 
+/* the device list of -t: RTLSDR_GPU_DEVICES=0,2,3 or RTLSDR_GPU_DEVICE, RTLSDR_GPU_DEVICE + 1, ... */
+static int device_list(int workers, int *devices)
+{
+	const char *list = getenv("RTLSDR_GPU_DEVICES");
+	int n = 0, first = env_int("RTLSDR_GPU_DEVICE", 0);
+	if (list && *list) {
+		char *copy = strdup(list), *save = NULL, *tok;
+		for (tok = strtok_r(copy, ",", &save); tok && n < MAX_WORKERS; tok = strtok_r(NULL, ",", &save))
+			devices[n++] = atoi(tok);
+		free(copy);
+		return n;
+	}
+	for (n = 0; n < workers && n < MAX_WORKERS; n++)
+		devices[n] = first + n;
+	return n;
+}
+
 int main(int argc, char **argv)
 {
 	const char *range = NULL, *window = "rectangle", *filename = "-";
 	const char *fixed_stamp = getenv("RTL_POWER_TIMESTAMP");
 	int opt, interval = 10, single = 0, peak_hold = 0, boxcar = 1, comp_fir_size = 0;
-	int passes_per_report = env_int("RTL_POWER_PASSES", 0), passes = 0, rc = 0, hop;
+	int passes_per_report = env_int("RTL_POWER_PASSES", 0), passes = 0, rc = 0, hop, w;
 	int max_reports = env_int("RTL_POWER_REPORTS", 0), reports = 0;
+	int want_workers = 1, smooth_iir = 0, shuffle = 0, db_count, devices[MAX_WORKERS];
+	const int use_async = getenv("RTL_POWER_ASYNC") != NULL;
+	uint64_t shuffle_state = 0;
 	long exit_after = 0;
 	double crop = 0.0;
 	time_t next_tick, exit_time = 0, now;
 	rp_plan_t *plan;
 	rtlsdr_dev_t *dev = NULL;
-	rtlsdr_gpu_scan_t *gpu = NULL;
+	struct workers ws;
 	rtlsdr_gpu_scan_cfg_t cfg;
 	int32_t *window_coefs = NULL;
 	uint8_t *buf8, *replay = NULL;
 	double *db;
+	int *samples, *order;
 	char *row, stamp[64];
 	size_t row_cap;
 	FILE *out;
 	struct sigaction sa;
 
-	while ((opt = getopt(argc, argv, "f:i:s:t:d:g:p:e:w:c:F:1POhTD:")) != -1) {
+	memset(&ws, 0, sizeof(ws));
+	while ((opt = getopt(argc, argv, "f:i:s:t:d:g:p:e:w:c:F:1POhTD:R:")) != -1) {
 		switch (opt) {
 		case 'f': range = optarg; break;
 		case 'i': interval = (int)round(rp_atoft(optarg)); break;
@@ -189,8 +261,11 @@ int main(int argc, char **argv)
 		case 'F': boxcar = 0; comp_fir_size = atoi(optarg); break;
 		case '1': single = 1; break;
 		case 'P': peak_hold = 1; break;
-		case 's': case 't': case 'd': case 'g': case 'p': case 'O': case 'T': case 'D':
-			break; /* device housekeeping or options the reference parses and ignores */
+		case 's': smooth_iir = strcmp("iir", optarg) == 0; break; /* avg | iir, rtl_power.c:820-825 */
+		case 't': want_workers = atoi(optarg); break;             /* rtl_power.c:844-846 */
+		case 'R': shuffle = 1; shuffle_state = 0x9E3779B97F4A7C15ULL ^ (uint64_t)strtoull(optarg, NULL, 0); break;
+		case 'd': case 'g': case 'p': case 'O': case 'T': case 'D':
+			break; /* device housekeeping: no dongle behind the synthetic source */
 		case 'h':
 		default:
 			print_usage();
@@ -264,10 +339,20 @@ int main(int argc, char **argv)
 	window_coefs = (int32_t *)malloc(sizeof(int32_t) << plan->bin_e);
 	rtlsdr_gpu_scan_window(window, 1 << plan->bin_e, window_coefs);
 
+	/* the GPU workers: contiguous, balanced hop ranges (sizes differ by at most one) */
+	if (want_workers < 1)
+		want_workers = 1;
+	if (want_workers > plan->tune_count)
+		want_workers = plan->tune_count;
+	ws.count = device_list(want_workers, devices);
+	if (ws.count > plan->tune_count)
+		ws.count = plan->tune_count;
+	for (w = 0; w <= ws.count; w++) {
+		const int base = plan->tune_count / ws.count, extra = plan->tune_count % ws.count;
+		ws.first[w] = w * base + (w < extra ? w : extra);
+	}
 	memset(&cfg, 0, sizeof(cfg));
 	cfg.struct_size = sizeof(cfg);
-	cfg.device = env_int("RTLSDR_GPU_DEVICE", 0);
-	cfg.tune_count = plan->tune_count;
 	cfg.bin_e = plan->bin_e;
 	cfg.buf_len = plan->buf_len;
 	cfg.downsample = plan->downsample;
@@ -278,22 +363,43 @@ int main(int argc, char **argv)
 	cfg.rate = plan->rate;
 	cfg.crop = plan->crop;
 	cfg.window_coefs = window_coefs;
-	rc = rtlsdr_gpu_scan_init(&cfg, &gpu);
-	if (rc) {
-		fprintf(stderr, "rtlsdr_gpu_scan_init: %s\n", rtlsdr_gpu_scan_strerror(rc));
+	if (smooth_iir) {
+		const char *a = getenv("RTL_POWER_IIR_ALPHA");
+		cfg.iir_alpha = (a && *a) ? atof(a) : 0.25;
+	}
+	for (w = 0; w < ws.count; w++) {
+		cfg.device = devices[w];
+		cfg.tune_count = ws.first[w + 1] - ws.first[w];
+		rc = rtlsdr_gpu_scan_init(&cfg, &ws.gpu[w]);
+		if (rc) {
+			fprintf(stderr, "rtlsdr_gpu_scan_init (device %d): %s\n", devices[w], rtlsdr_gpu_scan_strerror(rc));
+			return 1;
+		}
+	}
+	if (ws.count > 1)
+		fprintf(stderr, "GPU workers: %d (hops per worker: %d..%d)\n", ws.count,
+			plan->tune_count / ws.count, (plan->tune_count + ws.count - 1) / ws.count);
+
+	db_count = rtlsdr_gpu_scan_db_count(ws.gpu[0]);
+	buf8 = (uint8_t *)malloc((size_t)plan->buf_len);
+	/* report landing area: pinned, so every worker's device-to-host copies are plain DMA */
+	db = (double *)rtlsdr_gpu_scan_host_alloc(sizeof(double) * (size_t)db_count * (size_t)plan->tune_count);
+	samples = (int *)rtlsdr_gpu_scan_host_alloc(sizeof(int) * (size_t)plan->tune_count);
+	order = (int *)malloc(sizeof(int) * (size_t)plan->tune_count);
+	row_cap = (size_t)db_count * 16 + 256;
+	row = (char *)malloc(row_cap);
+	if (!buf8 || !db || !samples || !order || !row) {
+		fprintf(stderr, "Out of memory.\n");
 		return 1;
 	}
-
-	buf8 = (uint8_t *)malloc((size_t)plan->buf_len);
-	db = (double *)malloc(sizeof(double) * (size_t)rtlsdr_gpu_scan_db_count(gpu));
-	row_cap = (size_t)rtlsdr_gpu_scan_db_count(gpu) * 16 + 256;
-	row = (char *)malloc(row_cap);
+	for (hop = 0; hop < plan->tune_count; hop++)
+		order[hop] = hop;
 	next_tick = time(NULL) + interval;
 	if (exit_after)
 		exit_time = time(NULL) + exit_after;
 
 	while (!stop_requests) {
-		rc = sweep(dev, gpu, plan, buf8);
+		rc = sweep(dev, &ws, plan, buf8, order, shuffle ? &shuffle_state : NULL, use_async);
 		if (rc)
 			break;
 		passes++;
@@ -306,16 +412,20 @@ int main(int argc, char **argv)
 			struct tm *cal = localtime(&now);
 			strftime(stamp, sizeof(stamp), "%Y-%m-%d, %H:%M:%S", cal);
 		}
-		for (hop = 0; hop < plan->tune_count; hop++) {
-			int samples = 0;
-			rc = rtlsdr_gpu_scan_collect(gpu, hop, NULL, &samples, db);
-			if (rc) {
-				fprintf(stderr, "rtlsdr_gpu_scan_collect: %s (%s)\n", rtlsdr_gpu_scan_strerror(rc),
-					rtlsdr_gpu_scan_last_cuda_error(gpu));
+		/* one report per worker: ONE epilogue launch, one copy, one synchronisation each
+		 * (csv_dbm's reads and zeroing, rtl_power.c:730-764), then the rows in hop order (:995-1000) */
+		for (w = 0; w < ws.count && !rc; w++) {
+			rc = rtlsdr_gpu_scan_collect_all(ws.gpu[w], NULL, samples + ws.first[w],
+							 db + (size_t)ws.first[w] * (size_t)db_count);
+			if (rc)
+				fprintf(stderr, "rtlsdr_gpu_scan_collect_all: %s (%s)\n", rtlsdr_gpu_scan_strerror(rc),
+					rtlsdr_gpu_scan_last_cuda_error(ws.gpu[w]));
+		}
+		for (hop = 0; hop < plan->tune_count && !rc; hop++) {
+			if (rp_csv_row(row, row_cap, plan, hop, samples[hop], db + (size_t)hop * (size_t)db_count, db_count) < 0) {
+				rc = 1;
 				break;
 			}
-			if (rp_csv_row(row, row_cap, plan, hop, samples, db, rtlsdr_gpu_scan_db_count(gpu)) < 0)
-				break;
 			fprintf(out, "%s, %s", stamp, row);
 		}
 		fflush(out);
@@ -335,10 +445,13 @@ int main(int argc, char **argv)
 		fprintf(stderr, "\nLibrary error %d, exiting...\n", rc);
 	if (out != stdout)
 		fclose(out);
-	rtlsdr_gpu_scan_close(gpu);
+	for (w = 0; w < ws.count; w++)
+		rtlsdr_gpu_scan_close(ws.gpu[w]);
 	rtlsdr_close(dev);
 	free(buf8);
-	free(db);
+	rtlsdr_gpu_scan_host_free(db);
+	rtlsdr_gpu_scan_host_free(samples);
+	free(order);
 	free(row);
 	free(window_coefs);
 	free(replay);

@@ -119,6 +119,70 @@ void synth_generate(int mode, uint64_t seed, int param, int tune_count,
 	}
 }
 
+/* ---- bulk generation (bench / sweep drivers fill whole sweep cubes) -------- */
+
+#include <pthread.h>
+
+struct cube_job {
+	int mode, param, tune_count, hop_first, hop_count, worker, workers;
+	uint64_t seed, pass_first, passes;
+	uint8_t *out;
+	size_t pass_stride, hop_stride, len;
+};
+
+static void *cube_worker(void *arg)
+{
+	const struct cube_job *j = (const struct cube_job *)arg;
+	const uint64_t total = j->passes * (uint64_t)j->hop_count;
+	uint64_t i;
+	for (i = (uint64_t)j->worker; i < total; i += (uint64_t)j->workers) {
+		const uint64_t p = i / (uint64_t)j->hop_count;
+		const int k = (int)(i % (uint64_t)j->hop_count);
+		synth_generate(j->mode, j->seed, j->param, j->tune_count, j->hop_first + k, j->pass_first + p,
+			       j->out + (size_t)p * j->pass_stride + (size_t)k * j->hop_stride, j->len);
+	}
+	return NULL;
+}
+
+void synth_generate_cube(int mode, uint64_t seed, int param, int tune_count, int hop_first, int hop_count,
+			 uint64_t pass_first, uint64_t passes, uint8_t *out, size_t pass_stride,
+			 size_t hop_stride, size_t len, int threads)
+{
+	struct cube_job jobs[64];
+	pthread_t th[64];
+	int i, started = 0;
+	if (threads < 1)
+		threads = 1;
+	if (threads > 64)
+		threads = 64;
+	for (i = 0; i < threads; i++) {
+		struct cube_job j = { mode, param, tune_count, hop_first, hop_count, i, threads,
+				      seed, pass_first, passes, out, pass_stride, hop_stride, len };
+		jobs[i] = j;
+	}
+	for (i = 1; i < threads; i++) {
+		if (pthread_create(&th[i], NULL, cube_worker, &jobs[i]) != 0)
+			break;
+		started = i;
+	}
+	/* workers that could not be started: their share is done here */
+	for (i = started + 1; i < threads; i++)
+		cube_worker(&jobs[i]);
+	cube_worker(&jobs[0]);
+	for (i = 1; i <= started; i++)
+		pthread_join(th[i], NULL);
+}
+
+uint64_t synth_fnv1a_int64(const int64_t *words, size_t count, uint64_t h)
+{
+	size_t i;
+	for (i = 0; i < count; i++) {
+		h ^= (uint64_t)words[i];
+		h *= 1099511628211ULL;
+	}
+	return h;
+}
+
 void synth_configure(rtlsdr_dev_t *dev, int mode, uint64_t seed, int param)
 {
 	struct rtlsdr_dev *d = resolve(dev);

@@ -94,7 +94,13 @@ typedef struct rtlsdr_gpu_scan_cfg {
 	const int16_t *sinewave;
 	uint32_t ring_bytes;        /* pinned staging ring size per half, 0 = default (32 MiB) */
 	uint32_t flags;             /* RTLSDR_GPU_FLAG_* */
+	/* fields added after the first release: a caller that passes the shorter struct_size gets 0 */
+	double   iir_alpha;         /* -s iir: 0 = off (plain per-interval averages, what the reference does),
+	                             * 0 < a <= 1 = smoothing factor of the dB rows across reports, see collect() */
 } rtlsdr_gpu_scan_cfg_t;
+
+/* struct_size of the first release (up to and including `flags`) is still accepted */
+#define RTLSDR_GPU_SCAN_CFG_V1_SIZE ((uint32_t)offsetof(rtlsdr_gpu_scan_cfg_t, iir_alpha))
 
 /* cfg.flags: also count, per hop, the byte statistics librtlsdr's soft AGC looks at
  * (src/librtlsdr.c:3288-3306); read them with rtlsdr_gpu_scan_level_stats() */
@@ -125,9 +131,30 @@ RTLSDR_GPU_API int rtlsdr_gpu_scan_submit(rtlsdr_gpu_scan_t *h, int hop, const u
  * rtlsdr_gpu_scan_host_alloc() (pinned): read (pass p, hop hop_first + k) is at
  * buf + p * pass_stride + k * hop_stride, k < hop_count, p < passes.  The
  * bytes are copied to the device without the intermediate ring copy.
+ *
+ * Buffer lifetime: the call returns while its host-to-device copies are still
+ * queued (on a copy stream of the handle, possibly behind the previous batch's
+ * kernels).  `buf` must stay valid AND unmodified until rtlsdr_gpu_scan_sync() /
+ * any collect() into host memory returns, or until an event the caller records
+ * on rtlsdr_gpu_scan_get_stream() AFTER this call has completed (the handle's
+ * stream waits for every copy before the kernel that consumes it).  Refilling
+ * the same pinned buffer for the next interval without such a wait corrupts
+ * the reads that have not crossed PCIe yet.
  */
 RTLSDR_GPU_API int rtlsdr_gpu_scan_submit_batch(rtlsdr_gpu_scan_t *h, int hop_first, int hop_count,
 		int passes, const uint8_t *buf, int64_t pass_stride, int64_t hop_stride);
+
+/*
+ * Hop visits in ANY order (randomised hopping, the reference's TODO list
+ * src/rtl_power.c:29-36): read i is buf_len bytes at buf + i * stride and
+ * belongs to hop hops[i]; a hop may appear any number of times.  Bins are
+ * int64 sums / maxima (rtl_power.c:708-716), so the result does not depend on
+ * the order.  `buf` is pinned host memory (rtlsdr_gpu_scan_host_alloc); same
+ * lifetime rule as rtlsdr_gpu_scan_submit_batch.  `hops` is consumed before
+ * the call returns.
+ */
+RTLSDR_GPU_API int rtlsdr_gpu_scan_submit_reads(rtlsdr_gpu_scan_t *h, int n_reads, const int32_t *hops,
+		const uint8_t *buf, int64_t stride);
 
 /* Same layout, but `dev_buf` is device memory on cfg.device (16-byte aligned,
  * strides multiples of 16).  Used for device-resident replay (roofline runs). */
@@ -153,6 +180,15 @@ RTLSDR_GPU_API int rtlsdr_gpu_scan_sync(rtlsdr_gpu_scan_t *h);
  *                       (rtl_power.c:747-760) (may be NULL)
  * Afterwards the hop's accumulators and sample count are zero
  * (rtl_power.c:761-764).
+ *
+ * cfg.iir_alpha > 0 ("-s iir": the reference parses it, rtl_power.c:820-825, and lists
+ * "continuous IIR smoothing" as a TODO, :29-36; it never defined it, so this is the
+ * definition): `db` holds 10*log10(s), s being an exponential moving average across
+ * reports of the linear value csv_dbm takes the logarithm of, d = avg / rate / samples:
+ * s = d at a bin's first report, s += alpha * (d - s) afterwards, all in IEEE doubles
+ * without contraction; a report of a hop without samples leaves s alone and prints d.
+ * The duplicated last column repeats the smoothed last bin.  `avg` / `samples` are
+ * never smoothed.
  */
 RTLSDR_GPU_API int rtlsdr_gpu_scan_collect(rtlsdr_gpu_scan_t *h, int hop, int64_t *avg, int *samples, double *db);
 

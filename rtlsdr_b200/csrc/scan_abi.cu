@@ -83,6 +83,7 @@ struct rtlsdr_gpu_scan {
 	int2 *d_twb = nullptr;          /* large path: round-B twiddles re-ordered [se][plow][ilow] */
 	uint16_t *d_win = nullptr;
 	double *d_db = nullptr;
+	double *d_iir = nullptr;        /* -s iir smoothing state [tune_count][db_count - 1] */
 	int *d_samples = nullptr;
 	int *h_samples_pinned = nullptr;
 	std::vector<int> samples;
@@ -141,6 +142,12 @@ struct rtlsdr_gpu_scan {
 	int timing_every = 1;   /* bracket every k-th transform with events (events between kernels
 	                         * prevent programmatic dependent launch, so benchmarks sample) */
 	uint64_t timing_count = 0;
+
+	/* debug / A-B switches, read from the environment ONCE at init (never on the launch path):
+	 * RTLSDR_GPU_BOXCAR_STREAM = 0|1|2|3|5 forces the narrow-scan kernel variant,
+	 * RTLSDR_GPU_NO_FUSED_BOXCAR / RTLSDR_GPU_NO_HB_STREAM fall back to the staged kernels */
+	int dbg_boxcar_mode = -1;
+	bool dbg_no_fused_boxcar = false, dbg_no_hb_stream = false;
 
 	std::string last_error;
 };
@@ -346,6 +353,9 @@ int build_desc(rtlsdr_gpu_scan *h, const std::vector<long long> &offs, const std
 		s_offs[p] = offs[i];
 		s_hops[p] = hops[i];
 	}
+	segs.clear();
+	if (h->path == PATH_SMALL_U8 || h->path == PATH_RMS || h->path == PATH_LARGE)
+		return 0; /* these kernels walk the hop-sorted reads themselves (equal runs per CTA / per-read work) */
 	/* the decimating path runs in kDecimChunks chunks, each should still fill the GPU */
 	const bool big_decim = h->path == PATH_SMALL_DECIM && (size_t)n * (size_t)h->cfg.buf_len >= kDecimOverlapBytes;
 	const int target = std::max(1, h->num_sms * h->ctas_per_sm) * (big_decim ? kDecimChunks : 1);
@@ -378,7 +388,6 @@ int build_desc(rtlsdr_gpu_scan *h, const std::vector<long long> &offs, const std
 		}
 		chunk = best_chunk;
 	}
-	segs.clear();
 	for (int hp = 0; hp < tc; hp++) {
 		int lo = count[hp], hi = count[hp + 1];
 		int cnt = hi - lo;
@@ -430,11 +439,12 @@ template <int L, bool PEAK, bool IN16>
 int launch_small_t(rtlsdr_gpu_scan *h, const SmallParams &prm)
 {
 	auto kern = scan_small_kernel<L, PEAK, IN16>;
-	/* RTLSDR_GPU_DEBUG_SMEM_PAD: occupancy experiments only (extra bytes -> fewer CTAs per SM) */
-	static const int pad = getenv("RTLSDR_GPU_DEBUG_SMEM_PAD") ? atoi(getenv("RTLSDR_GPU_DEBUG_SMEM_PAD")) : 0;
-	const int smem = SmallSmem<L>::bytes + pad;
+	const int smem = SmallSmem<L>::bytes;
 	CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-	const int grid = std::min(prm.n_segs, h->num_sms * 8);
+	/* u8 reads: one resident wave of persistent CTAs, each with an equal share of the working sets;
+	 * decimated images: one CTA per segment */
+	const int grid = IN16 ? std::min(prm.n_segs, h->num_sms * 8)
+			      : (int)std::min<long long>(2ll * prm.n_entries, (long long)h->num_sms * h->ctas_per_sm);
 	if (int rc = launch_after_epilogue(h, kern, grid, kThreads, smem, prm, !IN16))
 		return rc;
 	return check_launch(h, "scan_small_kernel");
@@ -576,7 +586,6 @@ int launch_sym_boxcar_t(rtlsdr_gpu_scan *h, const FusedBoxcarParams &prm_in)
 template <int L>
 int stream_boxcar_mode(const rtlsdr_gpu_scan *h)
 {
-	const char *force = getenv("RTLSDR_GPU_BOXCAR_STREAM");
 	const int ds = h->cfg.downsample;
 	/* measured on B200 (profiles/r01l_stream_modes.txt, r01n_stream_modes.txt): up to 512 bins and, at 1024 bins,
 	 * below ds ~ 24 the symmetric worker kernel wins (N = 256: +25 %, N = 512: +8..16 %); the three-role kernel
@@ -589,8 +598,8 @@ int stream_boxcar_mode(const rtlsdr_gpu_scan *h)
 		mode = 5;
 	else
 		mode = ds < kStreamOneFftGroupDs ? 3 : 1;
-	if (force)
-		mode = atoi(force);
+	if (h->dbg_boxcar_mode >= 0)
+		mode = h->dbg_boxcar_mode;
 	if (mode == 5 && sym_boxcar_slots<L>(ds) < 3)
 		mode = 1;
 	if (mode == 1 && stream_boxcar_slots<L, 1>(ds) < 4)
@@ -644,7 +653,7 @@ bool fused_boxcar_ok(const rtlsdr_gpu_scan *h)
 {
 	const int ds = h->cfg.downsample;
 	return h->cfg.boxcar && ds >= 2 && ds <= 64 && h->cfg.bin_e >= 8 && h->cfg.bin_e <= 12 && h->n_blocks == 1 &&
-	       h->cfg.buf_len == 2 * h->N * ds && !getenv("RTLSDR_GPU_NO_FUSED_BOXCAR");
+	       h->cfg.buf_len == 2 * h->N * ds && !h->dbg_no_fused_boxcar;
 }
 
 /*
@@ -742,7 +751,7 @@ int run_decimators(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_o
 		tile = std::min(tile, M);
 		/* P <= 5: the register-streaming kernel computes final samples >= 16, the tile kernel only
 		 * the eased-in head [0, 16) of every read (RTLSDR_GPU_NO_HB_STREAM=1: tile kernel for all) */
-		const bool stream = passes <= kHbStreamMaxPasses && M >= 2 * kHbStreamHead && !getenv("RTLSDR_GPU_NO_HB_STREAM");
+		const bool stream = passes <= kHbStreamMaxPasses && M >= 2 * kHbStreamHead && !h->dbg_no_hb_stream;
 		if (stream)
 			tile = kHbStreamHead;
 		p.tile = tile;
@@ -899,8 +908,8 @@ int launch_batch(rtlsdr_gpu_scan *h, const uint8_t *base, const uint8_t *d_desc,
 		memset(&p, 0, sizeof(p));
 		p.base = base;
 		p.read_off = d_offs;
-		p.segs = d_segs;
-		p.n_segs = n_segs;
+		p.hop_of = d_hops;
+		p.n_entries = n_reads;
 		p.avg = h->d_avg;
 		p.samples = h->d_smp64;
 		p.samples_per_read = h->samples_per_read;
@@ -1118,6 +1127,7 @@ void free_all(rtlsdr_gpu_scan *h)
 	cudaFree(h->d_twc);
 	cudaFree(h->d_win);
 	cudaFree(h->d_db);
+	cudaFree(h->d_iir);
 	cudaFree(h->d_samples);
 	cudaFree(h->d_scratch);
 	cudaFree(h->d_bulk);
@@ -1187,6 +1197,8 @@ int run_epilogue(rtlsdr_gpu_scan *h, int hop0, int nhops, double *db, long long 
 	p.i2 = h->db_i2;
 	p.rate = h->cfg.rate;
 	p.hop0 = hop0;
+	p.iir = h->d_iir;
+	p.iir_alpha = h->cfg.iir_alpha;
 	const int span = std::max(h->db_count, avg_out ? h->N : 0);
 	dim3 grid((span + 255) / 256, nhops);
 	epilogue_kernel<<<grid, 256, 0, h->stream>>>(p);
@@ -1265,12 +1277,18 @@ void rtlsdr_gpu_scan_host_free(void *p)
 		cudaFreeHost(p);
 }
 
-int rtlsdr_gpu_scan_init(const rtlsdr_gpu_scan_cfg_t *cfg, rtlsdr_gpu_scan_t **out)
+int rtlsdr_gpu_scan_init(const rtlsdr_gpu_scan_cfg_t *cfg_in, rtlsdr_gpu_scan_t **out)
 {
-	if (!cfg || !out)
+	if (!cfg_in || !out)
 		return RTLSDR_GPU_ERR_NULL;
 	*out = nullptr;
-	if (cfg->struct_size != sizeof(rtlsdr_gpu_scan_cfg_t))
+	if (cfg_in->struct_size != sizeof(rtlsdr_gpu_scan_cfg_t) && cfg_in->struct_size != RTLSDR_GPU_SCAN_CFG_V1_SIZE)
+		return RTLSDR_GPU_ERR_CONFIG;
+	rtlsdr_gpu_scan_cfg_t full;
+	memset(&full, 0, sizeof(full));
+	memcpy(&full, cfg_in, cfg_in->struct_size); /* fields a shorter (older) struct lacks stay 0 */
+	const rtlsdr_gpu_scan_cfg_t *cfg = &full;
+	if (!(cfg->iir_alpha >= 0.0 && cfg->iir_alpha <= 1.0))
 		return RTLSDR_GPU_ERR_CONFIG;
 	if (cfg->tune_count <= 0 || cfg->tune_count > 3000 /* MAX_TUNES, rtl_power.c:113 */ ||
 	    cfg->bin_e < 0 || cfg->bin_e > 21 /* rtl_power.c:483 */ || cfg->downsample < 1 ||
@@ -1309,6 +1327,16 @@ int rtlsdr_gpu_scan_init(const rtlsdr_gpu_scan_cfg_t *cfg, rtlsdr_gpu_scan_t **o
 	if (!h)
 		return RTLSDR_GPU_ERR_NOMEM;
 	h->cfg = *cfg;
+	if (const char *f = getenv("RTLSDR_GPU_BOXCAR_STREAM")) {
+		const int m = atoi(f);
+		if (m != 0 && m != 1 && m != 2 && m != 3 && m != 5) {
+			delete h;
+			return RTLSDR_GPU_ERR_CONFIG; /* not a kernel variant */
+		}
+		h->dbg_boxcar_mode = m;
+	}
+	h->dbg_no_fused_boxcar = getenv("RTLSDR_GPU_NO_FUSED_BOXCAR") != nullptr;
+	h->dbg_no_hb_stream = getenv("RTLSDR_GPU_NO_HB_STREAM") != nullptr;
 	h->cfg.window_coefs = nullptr;
 	h->cfg.sinewave = nullptr;
 	h->N = N;
@@ -1378,6 +1406,16 @@ int rtlsdr_gpu_scan_init(const rtlsdr_gpu_scan_cfg_t *cfg, rtlsdr_gpu_scan_t **o
 			break;
 		if (cudaMemsetAsync(h->d_avg, 0, avg_bytes, h->stream) != cudaSuccess)
 			break;
+		if (cfg->iir_alpha > 0.0) {
+			/* smoothing state of the printed bins, NaN (all bits set) = no report yet */
+			const size_t ib = (size_t)cfg->tune_count * (size_t)(h->db_count - 1) * sizeof(double);
+			if (cudaMalloc(&h->d_iir, ib) != cudaSuccess) {
+				rc = RTLSDR_GPU_ERR_NOMEM;
+				break;
+			}
+			if (cudaMemsetAsync(h->d_iir, 0xFF, ib, h->stream) != cudaSuccess)
+				break;
+		}
 		if (cfg->flags & RTLSDR_GPU_FLAG_LEVEL_STATS) {
 			const size_t lb = (size_t)cfg->tune_count * 2 * sizeof(unsigned long long);
 			if (cudaMalloc(&h->d_level, lb) != cudaSuccess) {
@@ -1638,21 +1676,9 @@ int rtlsdr_gpu_scan_submit_device(rtlsdr_gpu_scan_t *h, int hop_first, int hop_c
 	return submit_regular(h, hop_first, hop_count, passes, dev_buf, pass_stride, hop_stride);
 }
 
-int rtlsdr_gpu_scan_submit_batch(rtlsdr_gpu_scan_t *h, int hop_first, int hop_count, int passes,
-				 const uint8_t *buf, int64_t pass_stride, int64_t hop_stride)
+/* device landing area of submit_batch / submit_reads (grown on demand) + the copy stream and its events */
+static int bulk_prepare(rtlsdr_gpu_scan_t *h, size_t extent)
 {
-	if (!h || !buf)
-		return RTLSDR_GPU_ERR_NULL;
-	if ((pass_stride & 15) || (hop_stride & 15) || ((uintptr_t)buf & 15))
-		return RTLSDR_GPU_ERR_ALIGN;
-	if (hop_first < 0 || hop_count <= 0 || hop_first + hop_count > h->cfg.tune_count)
-		return RTLSDR_GPU_ERR_HOP;
-	if (passes <= 0 || pass_stride < 0 || hop_stride < 0)
-		return RTLSDR_GPU_ERR_CONFIG;
-	CU(cudaSetDevice(h->cfg.device));
-	const size_t B = (size_t)h->cfg.buf_len;
-	const size_t pass_extent = (size_t)(hop_count - 1) * (size_t)hop_stride + B;
-	const size_t extent = (size_t)(passes - 1) * (size_t)pass_stride + pass_extent;
 	if (h->bulk_bytes < extent) {
 		CU(cudaStreamSynchronize(h->stream));
 		if (h->copy_stream)
@@ -1678,11 +1704,32 @@ int rtlsdr_gpu_scan_submit_batch(rtlsdr_gpu_scan_t *h, int hop_first, int hop_co
 	int rc = flush_ring(h);
 	if (rc)
 		return rc;
+	if (h->bulk_used)
+		CU(cudaStreamWaitEvent(h->copy_stream, h->bulk_free, 0)); /* previous batch's kernels are done with d_bulk */
+	return 0;
+}
+
+int rtlsdr_gpu_scan_submit_batch(rtlsdr_gpu_scan_t *h, int hop_first, int hop_count, int passes,
+				 const uint8_t *buf, int64_t pass_stride, int64_t hop_stride)
+{
+	if (!h || !buf)
+		return RTLSDR_GPU_ERR_NULL;
+	if ((pass_stride & 15) || (hop_stride & 15) || ((uintptr_t)buf & 15))
+		return RTLSDR_GPU_ERR_ALIGN;
+	if (hop_first < 0 || hop_count <= 0 || hop_first + hop_count > h->cfg.tune_count)
+		return RTLSDR_GPU_ERR_HOP;
+	if (passes <= 0 || pass_stride < 0 || hop_stride < 0)
+		return RTLSDR_GPU_ERR_CONFIG;
+	CU(cudaSetDevice(h->cfg.device));
+	const size_t B = (size_t)h->cfg.buf_len;
+	const size_t pass_extent = (size_t)(hop_count - 1) * (size_t)hop_stride + B;
+	const size_t extent = (size_t)(passes - 1) * (size_t)pass_stride + pass_extent;
+	int rc = bulk_prepare(h, extent);
+	if (rc)
+		return rc;
 	/* Chunks of whole passes: chunk c+1 crosses PCIe while chunk c is transformed.  Passes must
 	 * not interleave in memory for that (pass_stride covers one pass), else one chunk. */
 	int chunks = (passes >= 2 * kBatchChunks && (size_t)pass_stride >= pass_extent) ? kBatchChunks : 1;
-	if (h->bulk_used)
-		CU(cudaStreamWaitEvent(h->copy_stream, h->bulk_free, 0)); /* previous batch's kernels are done with d_bulk */
 	for (int c = 0; c < chunks; c++) {
 		const int p0 = (int)((long long)passes * c / chunks), p1 = (int)((long long)passes * (c + 1) / chunks);
 		const size_t off = (size_t)p0 * (size_t)pass_stride;
@@ -1698,6 +1745,49 @@ int rtlsdr_gpu_scan_submit_batch(rtlsdr_gpu_scan_t *h, int hop_first, int hop_co
 		rc = submit_regular(h, hop_first, hop_count, p1 - p0, h->d_bulk + (size_t)p0 * (size_t)pass_stride,
 				    pass_stride, hop_stride);
 		if (rc)
+			return rc;
+	}
+	CU(cudaEventRecord(h->bulk_free, h->stream));
+	h->bulk_used = true;
+	return 0;
+}
+
+int rtlsdr_gpu_scan_submit_reads(rtlsdr_gpu_scan_t *h, int n_reads, const int32_t *hops, const uint8_t *buf, int64_t stride)
+{
+	if (!h || !buf || !hops)
+		return RTLSDR_GPU_ERR_NULL;
+	if ((stride & 15) || ((uintptr_t)buf & 15))
+		return RTLSDR_GPU_ERR_ALIGN;
+	if (n_reads <= 0 || stride < (int64_t)h->cfg.buf_len)
+		return RTLSDR_GPU_ERR_CONFIG;
+	for (int i = 0; i < n_reads; i++)
+		if (hops[i] < 0 || hops[i] >= h->cfg.tune_count)
+			return RTLSDR_GPU_ERR_HOP;
+	CU(cudaSetDevice(h->cfg.device));
+	const size_t B = (size_t)h->cfg.buf_len;
+	int rc = bulk_prepare(h, (size_t)(n_reads - 1) * (size_t)stride + B);
+	if (rc)
+		return rc;
+	/* chunks of consecutive reads: chunk c+1 crosses PCIe while chunk c is transformed */
+	const int chunks = n_reads >= 64 * kBatchChunks ? kBatchChunks : 1;
+	for (int c = 0; c < chunks; c++) {
+		const int r0 = (int)((long long)n_reads * c / chunks), r1 = (int)((long long)n_reads * (c + 1) / chunks);
+		const size_t off = (size_t)r0 * (size_t)stride, bytes = (size_t)(r1 - r0 - 1) * (size_t)stride + B;
+		CU(cudaMemcpyAsync(h->d_bulk + off, buf + off, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+		CU(cudaEventRecord(h->chunk_ready[c], h->copy_stream));
+		h->h2d += bytes;
+	}
+	std::vector<long long> offs;
+	std::vector<int> hp;
+	for (int c = 0; c < chunks; c++) {
+		const int r0 = (int)((long long)n_reads * c / chunks), r1 = (int)((long long)n_reads * (c + 1) / chunks);
+		offs.resize((size_t)(r1 - r0));
+		hp.assign(hops + r0, hops + r1);
+		for (int i = r0; i < r1; i++)
+			offs[(size_t)(i - r0)] = (long long)i * (long long)stride;
+		h->last_was_epilogue = false;
+		CU(cudaStreamWaitEvent(h->stream, h->chunk_ready[c], 0));
+		if ((rc = process_batch(h, h->d_bulk, offs, hp)))
 			return rc;
 	}
 	CU(cudaEventRecord(h->bulk_free, h->stream));

@@ -313,8 +313,10 @@ struct SmallParams {
 	const long long *read_off;  /* byte offset of entry e from base; NULL = regular */
 	long long regular_stride;   /* read_off == NULL: entry e at (e - entry_base) * regular_stride */
 	int entry_base;             /* first entry of this launch (IN16 images / dc_sums are relative to it) */
-	const int4 *segs;           /* (hop, first entry, entry count, -) */
+	const int4 *segs;           /* IN16: (hop, first entry, entry count, -) */
 	int n_segs;
+	const int *hop_of;          /* u8 reads: hop of entry e, entries sorted by hop */
+	int n_entries;              /* u8 reads: entries of this launch */
 	long long *avg;             /* [tune_count << L] */
 	long long *samples;         /* [tune_count] tunes[i].samples (rtl_power.c:717) */
 	int samples_per_read;
@@ -369,6 +371,123 @@ SCAN_DEV int dc_average(long long sum, int length)
 	return (int)(int16_t)(sum / (long long)length);
 }
 
+/* ---- pieces shared by the two loops of scan_small_kernel ---------------- */
+
+/* byte sums of I and Q over one staged 16 KiB read -> the constants (127 + int16 average) that the front end
+ * subtracts from the raw bytes: remove_dc over the WHOLE read (rtl_power.c:581-596, 692-693), divisors B and B-1 */
+SCAN_DEV void u8_read_dc(const uint8_t *st, int *red, int t, int &kI, int &kQ)
+{
+	unsigned sI = 0, sQ = 0;
+#pragma unroll
+	for (int i = 0; i < kStageBytes / (kThreads * 16); ++i) {
+		const uint4 q = *(const uint4 *)(st + (i * kThreads + t) * 16);
+		sI = __dp4a(q.x, 0x00010001u, sI);
+		sQ = __dp4a(q.x, 0x01000100u, sQ);
+		sI = __dp4a(q.y, 0x00010001u, sI);
+		sQ = __dp4a(q.y, 0x01000100u, sQ);
+		sI = __dp4a(q.z, 0x00010001u, sI);
+		sQ = __dp4a(q.z, 0x01000100u, sQ);
+		sI = __dp4a(q.w, 0x00010001u, sI);
+		sQ = __dp4a(q.w, 0x01000100u, sQ);
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		sI += __shfl_xor_sync(0xffffffffu, sI, o);
+		sQ += __shfl_xor_sync(0xffffffffu, sQ, o);
+	}
+	if ((t & 31) == 0) {
+		red[(t >> 5) * 2 + 0] = (int)sI;
+		red[(t >> 5) * 2 + 1] = (int)sQ;
+	}
+	__syncthreads();
+	int tI = 0, tQ = 0;
+#pragma unroll
+	for (int w = 0; w < kThreads / 32; ++w) {
+		tI += red[w * 2];
+		tQ += red[w * 2 + 1];
+	}
+	/* sum of (b - 127); int16 average, truncating division (rtl_power.c:589) */
+	kI = 127 + (int)(int16_t)((tI - 127 * (kStageBytes / 2)) / kStageBytes);
+	kQ = 127 + (int)(int16_t)((tQ - 127 * (kStageBytes / 2)) / (kStageBytes - 1));
+}
+
+/* sample index (inside its FFT block / inside the working set) that feeds register r */
+template <int L>
+SCAN_DEV void front_index(int r, int t, int trev, int blkbase, int &nblk, int &n)
+{
+	constexpr int N = 1 << L;
+	if constexpr (L >= 4) {
+		nblk = (brev4(r) << (L - 4)) + trev;
+		n = blkbase + nblk;
+	} else {
+		nblk = brev_bits((unsigned)(r & (N - 1)), L);
+		n = (t << 4) + (r & ~(N - 1)) + nblk;
+	}
+}
+
+/* u8 -> int16 minus (127 + DC), window, bit-reversed placement (rtl_power.c:666-668, 594, 697-706) */
+template <int L>
+SCAN_DEV void front_u8(X2 (&x)[kPts], const uint8_t *st, int ws, int kI, int kQ, const uint16_t *wins, int t, int trev,
+		       int blkbase)
+{
+#pragma unroll
+	for (int r = 0; r < kPts; ++r) {
+		int nblk, n;
+		front_index<L>(r, t, trev, blkbase, nblk, n);
+		const int wv = wins[nblk];
+		const unsigned raw = ((const uint16_t *)st)[ws * kWS + n];
+		x[r].re = (((int)(raw & 0xFFu) - kI) * wv) << 16;
+		x[r].im = (((int)(raw >> 8) - kQ) * wv) << 16;
+	}
+}
+
+/* one hop's sums / peaks of this CTA -> tunes[hop].avg (64-bit RED); `bins` = N x u64 of shared memory that no
+ * thread is using (only touched when N < 4096, where several registers of the CTA share a bin) */
+template <int L, bool PEAK>
+SCAN_DEV void flush_bins(unsigned long long (&acc)[kPts], long long *out, unsigned long long *bins, int t)
+{
+	constexpr int N = 1 << L;
+	if constexpr (L == 12) {
+#pragma unroll
+		for (int r = 0; r < kPts; ++r) {
+			const int bin = last_pos<L>(t, r) & (N - 1);
+			if constexpr (PEAK)
+				atomicMax(out + bin, (long long)acc[r]);
+			else
+				atomicAdd((unsigned long long *)(out + bin), acc[r]);
+		}
+	} else {
+		__syncthreads();
+		for (int i = t; i < N; i += kThreads)
+			bins[i] = 0ull;
+		__syncthreads();
+#pragma unroll
+		for (int r = 0; r < kPts; ++r) {
+			const int bin = last_pos<L>(t, r) & (N - 1);
+			if constexpr (PEAK)
+				atomicMax(bins + bin, acc[r]);
+			else
+				atomicAdd(bins + bin, acc[r]);
+		}
+		__syncthreads();
+		for (int i = t; i < N; i += kThreads) {
+			if constexpr (PEAK)
+				atomicMax(out + i, (long long)bins[i]);
+			else
+				atomicAdd((unsigned long long *)(out + i), bins[i]);
+		}
+		__syncthreads();
+	}
+}
+
+/*
+ * u8 reads (IN16 = false): the launch's hop-sorted reads are cut into gridDim.x contiguous runs of equal
+ * length, counted in 4096-sample working sets (half reads), so every CTA does the same amount of work whatever
+ * the hop count; a CTA walks its run once, keeps the next read in flight across hop boundaries, and flushes
+ * its register accumulators whenever the hop changes.  A run may begin or end in the middle of a read: that CTA
+ * still stages the whole read (remove_dc needs all of it) and transforms only its half.
+ * decimated images (IN16 = true): segment list, one CTA per segment (the decimating paths).
+ */
 template <int L, bool PEAK, bool IN16>
 __global__ void __launch_bounds__(kThreads, 2)
 scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
@@ -408,15 +527,86 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 	if constexpr (L >= 4)
 		blkbase = (t >> (L - 4)) << L;
 
-	constexpr int kWsPerUnit = IN16 ? 1 : 2; /* a 16 KiB slot = 8192 u8 pairs or 4096 c16 */
 	int flip = 0;
 
+	if constexpr (!IN16) {
+		const long long total_ws = 2ll * prm.n_entries;
+		const long long ws_lo = total_ws * blockIdx.x / gridDim.x, ws_hi = total_ws * (blockIdx.x + 1) / gridDim.x;
+		if (ws_lo >= ws_hi)
+			return;
+		const int e_lo = (int)(ws_lo >> 1), e_hi = (int)((ws_hi + 1) >> 1); /* reads [e_lo, e_hi) are touched */
+
+		unsigned long long acc[kPts];
+#pragma unroll
+		for (int r = 0; r < kPts; ++r)
+			acc[r] = 0ull;
+		int hop = prm.hop_of[e_lo], hop_ws = 0;
+		bool waited = false;
+
+		{
+			const uint8_t *src = prm.base + prm.read_off[e_lo];
+#pragma unroll
+			for (int i = 0; i < kStageBytes / (kThreads * 16); ++i)
+				cp_async16(stage + (i * kThreads + t) * 16, src + (i * kThreads + t) * 16);
+			cp_async_commit();
+		}
+		for (int e = e_lo; e < e_hi; ++e) {
+			const int u = e - e_lo;
+			cp_async_wait_all();
+			__syncthreads(); /* slot u&1 landed; slot (u+1)&1 no longer read */
+			int next_hop = -1;
+			if (e + 1 < e_hi) {
+				const uint8_t *src = prm.base + prm.read_off[e + 1];
+				uint8_t *dst = stage + ((u + 1) & 1) * kStageBytes;
+#pragma unroll
+				for (int i = 0; i < kStageBytes / (kThreads * 16); ++i)
+					cp_async16(dst + (i * kThreads + t) * 16, src + (i * kThreads + t) * 16);
+				cp_async_commit();
+				next_hop = prm.hop_of[e + 1];
+			}
+			const uint8_t *st = stage + (u & 1) * kStageBytes;
+			int kI, kQ;
+			u8_read_dc(st, red, t, kI, kQ);
+
+			/* this CTA's working sets of the read: both, except at the two ends of its run */
+			const int ws0 = (2ll * e < ws_lo) ? 1 : 0, ws1 = (2ll * e + 2 > ws_hi) ? 1 : 2;
+#pragma unroll 1
+			for (int ws = ws0; ws < ws1; ++ws) {
+				X2 x[kPts];
+				front_u8<L>(x, st, ws, kI, kQ, wins, t, trev, blkbase);
+				engine_fft_db<L>(x, xch, flip, t, tw, BlockBar(), t0);
+				/* ---- |X|^2 (rtl_power.c:636-640, 708-716) ---- */
+#pragma unroll
+				for (int r = 0; r < kPts; ++r)
+					accumulate_power<PEAK>(acc[r], x[r].re >> 16, x[r].im >> 16);
+			}
+			hop_ws += ws1 - ws0;
+
+			if (next_hop != hop) {
+				/* everything above only read this launch's inputs; the accumulators may still be in use
+				 * by the report epilogue of the previous interval (programmatic dependent launch) */
+				if (!waited)
+					pdl_wait();
+				waited = true;
+				if (t == 0) /* tunes[hop].samples += ds per FFT block (rtl_power.c:717) */
+					atomicAdd((unsigned long long *)(prm.samples + hop),
+						  (unsigned long long)((long long)hop_ws * (prm.samples_per_read / 2)));
+				/* N < 4096: the transpose buffers are idle here and serve as the shared bin array */
+				flush_bins<L, PEAK>(acc, prm.avg + ((long long)hop << L), (unsigned long long *)xch, t);
+#pragma unroll
+				for (int r = 0; r < kPts; ++r)
+					acc[r] = 0ull;
+				hop = next_hop;
+				hop_ws = 0;
+			}
+		}
+	} else {
 	for (int seg = blockIdx.x; seg < prm.n_segs; seg += gridDim.x) {
 		const int4 sg = prm.segs[seg];
 		const int hop = sg.x, first = sg.y;
-		/* IN16: the segment's images form one contiguous run of blocks, cut into 4096-sample units */
-		const int seg_blocks = IN16 ? sg.z * prm.blocks_padded : 0;
-		const int units = IN16 ? (int)(((long long)seg_blocks * N + kWS - 1) / kWS) : sg.z;
+		/* the segment's images form one contiguous run of blocks, cut into 4096-sample units */
+		const int seg_blocks = sg.z * prm.blocks_padded;
+		const int units = (int)(((long long)seg_blocks * N + kWS - 1) / kWS);
 
 		unsigned long long acc[kPts];
 #pragma unroll
@@ -436,12 +626,7 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 			cp_async_wait_all();
 			__syncthreads(); /* slot u&1 landed; slot (u+1)&1 no longer read */
 			if (u + 1 < units) {
-				long long o;
-				if (IN16)
-					o = entry_offset(prm, first) + (long long)(u + 1) * kStageBytes;
-				else
-					o = entry_offset(prm, first + u + 1);
-				const uint8_t *src = prm.base + o;
+				const uint8_t *src = prm.base + entry_offset(prm, first) + (long long)(u + 1) * kStageBytes;
 				uint8_t *dst = stage + ((u + 1) & 1) * kStageBytes;
 #pragma unroll
 				for (int i = 0; i < kStageBytes / (kThreads * 16); ++i)
@@ -452,165 +637,72 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 
 			/* ---- DC term of the whole read (rtl_power.c:692-693) ---- */
 			int limI = kWS, limQ = kWS, kI, kQ;
-			if constexpr (!IN16) {
-				unsigned sI = 0, sQ = 0;
-#pragma unroll
-				for (int i = 0; i < kStageBytes / (kThreads * 16); ++i) {
-					const uint4 q = *(const uint4 *)(st + (i * kThreads + t) * 16);
-					sI = __dp4a(q.x, 0x00010001u, sI);
-					sQ = __dp4a(q.x, 0x01000100u, sQ);
-					sI = __dp4a(q.y, 0x00010001u, sI);
-					sQ = __dp4a(q.y, 0x01000100u, sQ);
-					sI = __dp4a(q.z, 0x00010001u, sI);
-					sQ = __dp4a(q.z, 0x01000100u, sQ);
-					sI = __dp4a(q.w, 0x00010001u, sI);
-					sQ = __dp4a(q.w, 0x01000100u, sQ);
-				}
-#pragma unroll
-				for (int o = 16; o > 0; o >>= 1) {
-					sI += __shfl_xor_sync(0xffffffffu, sI, o);
-					sQ += __shfl_xor_sync(0xffffffffu, sQ, o);
-				}
-				if ((t & 31) == 0) {
-					red[(t >> 5) * 2 + 0] = (int)sI;
-					red[(t >> 5) * 2 + 1] = (int)sQ;
-				}
-				__syncthreads();
-				int tI = 0, tQ = 0;
-#pragma unroll
-				for (int w = 0; w < kThreads / 32; ++w) {
-					tI += red[w * 2];
-					tQ += red[w * 2 + 1];
-				}
-				/* sum of (b - 127); int16 average, truncating division (rtl_power.c:589) */
-				kI = 127 + (int)(int16_t)((tI - 127 * (kStageBytes / 2)) / kStageBytes);
-				kQ = 127 + (int)(int16_t)((tQ - 127 * (kStageBytes / 2)) / (kStageBytes - 1));
+			/* working-set block b is block gb = u * (4096/N) + b of the segment */
+			if constexpr (L >= 4) {
+				const int gb = u * (kWS / N) + (t >> (L - 4));
+				const int rd = gb / prm.blocks_padded, bir = gb - rd * prm.blocks_padded;
+				const bool live = gb < seg_blocks && bir < prm.n_blocks;
+				const int e = first + (live ? rd : 0) - prm.entry_base;
+				kI = __ldg(prm.dc_ave + 2 * e);
+				kQ = __ldg(prm.dc_ave + 2 * e + 1);
+				/* remove_dc covers int16 indices < l_len of the read (rtl_power.c:692-693) */
+				limI = live ? ((prm.l_len + 1) >> 1) - bir * N : 0;
+				limQ = live ? (prm.l_len >> 1) - bir * N : 0;
 			} else {
-				/* working-set block b is block gb = u * (4096/N) + b of the segment */
-				if constexpr (L >= 4) {
-					const int gb = u * (kWS / N) + (t >> (L - 4));
-					const int rd = gb / prm.blocks_padded, bir = gb - rd * prm.blocks_padded;
-					const bool live = gb < seg_blocks && bir < prm.n_blocks;
-					const int e = first + (live ? rd : 0) - prm.entry_base;
-					kI = __ldg(prm.dc_ave + 2 * e);
-					kQ = __ldg(prm.dc_ave + 2 * e + 1);
-					/* remove_dc covers int16 indices < l_len of the read (rtl_power.c:692-693) */
-					limI = live ? ((prm.l_len + 1) >> 1) - bir * N : 0;
-					limQ = live ? (prm.l_len >> 1) - bir * N : 0;
-				} else {
-					kI = kQ = 0; /* per element below */
-				}
+				kI = kQ = 0; /* per element below */
 			}
 
-#pragma unroll 1
-			for (int ws = 0; ws < kWsPerUnit; ++ws) {
-				X2 x[kPts];
-				/* ---- convert, remove DC, window, bit-reversed placement ---- */
+			X2 x[kPts];
+			/* ---- remove DC, window, bit-reversed placement ---- */
 #pragma unroll
-				for (int r = 0; r < kPts; ++r) {
-					int nblk, n; /* sample index inside its block / inside the working set */
-					if constexpr (L >= 4) {
-						nblk = (brev4(r) << (L - 4)) + trev;
-						n = blkbase + nblk;
-					} else {
-						nblk = brev_bits((unsigned)(r & (N - 1)), L);
-						n = (t << 4) + (r & ~(N - 1)) + nblk;
+			for (int r = 0; r < kPts; ++r) {
+				int nblk, n; /* sample index inside its block / inside the working set */
+				front_index<L>(r, t, trev, blkbase, nblk, n);
+				const int wv = wins[nblk];
+				const c16 raw = ((const c16 *)st)[n];
+				int re = c16_re(raw), im = c16_im(raw);
+				if constexpr (L >= 4) {
+					if (nblk < limI)
+						re -= kI;
+					if (nblk < limQ)
+						im -= kQ;
+				} else {
+					/* several blocks per thread: look the read up per element */
+					const int gb = u * (kWS / N) + (n >> L);
+					const int rd = gb / prm.blocks_padded, bir = gb - rd * prm.blocks_padded;
+					if (gb < seg_blocks && bir < prm.n_blocks) {
+						const int e = first + rd - prm.entry_base;
+						const int k = bir * N + nblk;
+						if (2 * k < prm.l_len)
+							re -= __ldg(prm.dc_ave + 2 * e);
+						if (2 * k + 1 < prm.l_len)
+							im -= __ldg(prm.dc_ave + 2 * e + 1);
 					}
-					const int wv = wins[nblk];
-					int re, im;
-					if constexpr (!IN16) {
-						const unsigned raw = ((const uint16_t *)st)[ws * kWS + n];
-						re = ((int)(raw & 0xFFu) - kI) * wv;
-						im = ((int)(raw >> 8) - kQ) * wv;
-					} else {
-						const c16 raw = ((const c16 *)st)[n];
-						re = c16_re(raw);
-						im = c16_im(raw);
-						if constexpr (L >= 4) {
-							if (nblk < limI)
-								re -= kI;
-							if (nblk < limQ)
-								im -= kQ;
-						} else {
-							/* several blocks per thread: look the read up per element */
-							const int gb = u * (kWS / N) + (n >> L);
-							const int rd = gb / prm.blocks_padded, bir = gb - rd * prm.blocks_padded;
-							if (gb < seg_blocks && bir < prm.n_blocks) {
-								const int e = first + rd - prm.entry_base;
-								const int k = bir * N + nblk;
-								if (2 * k < prm.l_len)
-									re -= __ldg(prm.dc_ave + 2 * e);
-								if (2 * k + 1 < prm.l_len)
-									im -= __ldg(prm.dc_ave + 2 * e + 1);
-							}
-						}
-						re *= wv;
-						im *= wv;
-					}
-					x[r].re = re << 16;
-					x[r].im = im << 16;
 				}
+				x[r].re = (re * wv) << 16;
+				x[r].im = (im * wv) << 16;
+			}
 
-				engine_fft_db<L>(x, xch, flip, t, tw, BlockBar(), t0);
+			engine_fft_db<L>(x, xch, flip, t, tw, BlockBar(), t0);
 
-				/* ---- |X|^2 (rtl_power.c:636-640, 708-716) ---- */
+			/* ---- |X|^2 (rtl_power.c:636-640, 708-716) ---- */
 #pragma unroll
-				for (int r = 0; r < kPts; ++r) {
-					const int re = x[r].re >> 16, im = x[r].im >> 16;
-					bool ok = true;
-					if constexpr (IN16) {
-						const int gb = u * (kWS / N) + (last_pos<L>(t, r) >> L);
-						ok = gb < seg_blocks;
-						if (prm.blocks_padded != prm.n_blocks)
-							ok = ok && (gb % prm.blocks_padded) < prm.n_blocks;
-					}
-					if (ok)
-						accumulate_power<PEAK>(acc[r], re, im);
-				}
+			for (int r = 0; r < kPts; ++r) {
+				const int gb = u * (kWS / N) + (last_pos<L>(t, r) >> L);
+				bool ok = gb < seg_blocks;
+				if (prm.blocks_padded != prm.n_blocks)
+					ok = ok && (gb % prm.blocks_padded) < prm.n_blocks;
+				if (ok)
+					accumulate_power<PEAK>(acc[r], x[r].re >> 16, x[r].im >> 16);
 			}
 		}
 
-		/* everything above only read this launch's inputs; the accumulators may still be in use
-		 * by the report epilogue of the previous interval (programmatic dependent launch) */
 		pdl_wait();
 		if (t == 0)
 			atomicAdd((unsigned long long *)(prm.samples + hop), (unsigned long long)((long long)sg.z * prm.samples_per_read));
-
-		/* ---- flush this segment's sums ---- */
-		long long *out = prm.avg + ((long long)hop << L);
-		if constexpr (L == 12) {
-#pragma unroll
-			for (int r = 0; r < kPts; ++r) {
-				const int bin = last_pos<L>(t, r) & (N - 1);
-				if constexpr (PEAK)
-					atomicMax(out + bin, (long long)acc[r]);
-				else
-					atomicAdd((unsigned long long *)(out + bin), acc[r]);
-			}
-		} else {
-			/* several registers of the CTA share a bin: combine in shared first */
-			unsigned long long *bins = (unsigned long long *)stage;
-			__syncthreads();
-			for (int i = t; i < N; i += kThreads)
-				bins[i] = 0ull;
-			__syncthreads();
-#pragma unroll
-			for (int r = 0; r < kPts; ++r) {
-				const int bin = last_pos<L>(t, r) & (N - 1);
-				if constexpr (PEAK)
-					atomicMax(bins + bin, acc[r]);
-				else
-					atomicAdd(bins + bin, acc[r]);
-			}
-			__syncthreads();
-			for (int i = t; i < N; i += kThreads) {
-				if constexpr (PEAK)
-					atomicMax(out + i, (long long)bins[i]);
-				else
-					atomicAdd((unsigned long long *)(out + i), bins[i]);
-			}
-			__syncthreads();
-		}
+		/* ---- flush this segment's sums (the staging area is idle: no prefetch is pending) ---- */
+		flush_bins<L, PEAK>(acc, prm.avg + ((long long)hop << L), (unsigned long long *)stage, t);
+	}
 	}
 }
 
@@ -1368,8 +1460,10 @@ dc_finalize_kernel(const SCAN_GRID_CONSTANT DcFinalizeParams prm)
 struct FusedBoxcarParams {
 	const uint8_t *base;        /* u8 reads of 2 * N * ds bytes (one FFT block per read) */
 	const long long *read_off;
-	const int4 *segs;           /* (hop, first entry, entry count, -) */
+	const int4 *segs;           /* IN16: (hop, first entry, entry count, -) */
 	int n_segs;
+	const int *hop_of;          /* u8 reads: hop of entry e, entries sorted by hop */
+	int n_entries;              /* u8 reads: entries of this launch */
 	int ds;
 	int slots;                  /* staging ring depth, 2..4 chunks of 512 * ds bytes */
 	long long *avg;
@@ -2341,6 +2435,8 @@ struct EpilogueParams {
 	unsigned *done;           /* optional [hops]: blocks finished per hop; the last one zeroes the hop */
 	long long *avg_rw;        /* same memory as avg when `done` is set */
 	long long *samples_rw;
+	double *iir;              /* optional [hops][db_count - 1] smoothing state (-s iir), NaN = no report yet */
+	double iir_alpha;
 };
 
 /* one launch per report: dB row, raw-bin copy and sample count of every hop */
@@ -2372,7 +2468,26 @@ epilogue_kernel(const SCAN_GRID_CONSTANT EpilogueParams prm)
 		d = __ddiv_rn(__ddiv_rn((double)v, rate), smp);
 	else
 		d = __ddiv_rn((double)v, __dmul_rn(rate, smp));
-	prm.db[(long long)blockIdx.y * count + k] = 10 * log10(d);
+	if (!prm.iir) {
+		prm.db[(long long)blockIdx.y * count + k] = 10 * log10(d);
+	} else if (k < count - 1) {
+		/* -s iir (parsed, never implemented by the reference, rtl_power.c:820-825 and its TODO list :29-36):
+		 * exponential smoothing ACROSS reports of the linear value csv_dbm takes the logarithm of,
+		 *   s = d for a bin's first report, s += alpha * (d - s) afterwards (reports without samples skip it);
+		 * the duplicated last column (rtl_power.c:755-760) prints the same smoothed bin again */
+		double *st = prm.iir + (long long)hop * (count - 1) + k;
+		double sm = *st;
+		if (smp != 0.0) {
+			sm = (sm != sm) ? d : __dadd_rn(sm, __dmul_rn(prm.iir_alpha, __dadd_rn(d, -sm)));
+			*st = sm;
+		} else {
+			sm = d;
+		}
+		const double o = 10 * log10(sm);
+		prm.db[(long long)blockIdx.y * count + k] = o;
+		if (k == count - 2)
+			prm.db[(long long)blockIdx.y * count + k + 1] = o;
+	}
 	}
 	/* read-and-zero (rtl_power.c:761-764): the last block of a hop to finish clears its
 	 * bins and sample counter, so no separate memset has to follow the report */

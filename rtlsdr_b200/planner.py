@@ -37,6 +37,12 @@ def host_library():
             fn.restype = ctypes.c_double
         L.synth_generate.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t]
+        L.synth_generate_cube.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p,
+                                          ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int]
+        L.synth_generate_cube.restype = None
+        L.synth_fnv1a_int64.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64]
+        L.synth_fnv1a_int64.restype = ctypes.c_uint64
         _HOST = L
     return _HOST
 
@@ -90,3 +96,25 @@ def plan_scan(freq_range, crop=0.0, fir=None):
     return Plan(c.tune_count, c.bin_e, c.buf_len, c.downsample, c.downsample_passes, c.rate, c.crop,
                 boxcar, 0 if fir is None else int(fir), c.bw_seen, c.bin_size,
                 [c.freq[i] for i in range(c.tune_count)], c)
+
+
+FNV_OFFSET = 14695981039346656037
+
+
+def fnv1a_int64(words, h=FNV_OFFSET):
+    """FNV-1a over int64 words in natural (hop-major) order: the hash of SURVEY.md 8(c)'s known-answer rows"""
+    import numpy as np
+    a = np.ascontiguousarray(words, dtype=np.int64)
+    return int(host_library().synth_fnv1a_int64(a.ctypes.data, a.size, ctypes.c_uint64(h)))
+
+
+def synth_cube(out_ptr, mode, seed, param, tune_count, hop_first, hop_count, pass_first, passes, buf_len,
+               pass_stride=None, hop_stride=None, threads=None):
+    """Fill [passes, hop_count, buf_len] (or the given strides) at out_ptr with the synthetic source's bytes
+    for reads (pass_first + p, hop_first + k): a pure function of (mode, seed, hop, pass)."""
+    hop_stride = buf_len if hop_stride is None else hop_stride
+    pass_stride = hop_count * hop_stride if pass_stride is None else pass_stride
+    threads = threads or min(32, os.cpu_count() or 1)
+    host_library().synth_generate_cube(mode, ctypes.c_uint64(seed), param, tune_count, hop_first, hop_count,
+                                       ctypes.c_uint64(pass_first), ctypes.c_uint64(passes), out_ptr,
+                                       pass_stride, hop_stride, buf_len, threads)

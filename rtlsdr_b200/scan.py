@@ -22,7 +22,7 @@ class _Cfg(ctypes.Structure):
                 ("comp_fir_size", ctypes.c_int32), ("peak_hold", ctypes.c_int32),
                 ("rate", ctypes.c_int32), ("crop", ctypes.c_double),
                 ("window_coefs", ctypes.c_void_p), ("sinewave", ctypes.c_void_p),
-                ("ring_bytes", ctypes.c_uint32), ("flags", ctypes.c_uint32)]
+                ("ring_bytes", ctypes.c_uint32), ("flags", ctypes.c_uint32), ("iir_alpha", ctypes.c_double)]
 
 
 def lib_path():
@@ -47,6 +47,7 @@ def load_library():
     L.rtlsdr_gpu_scan_submit.argtypes = [vp, i, vp, ctypes.c_uint32]
     L.rtlsdr_gpu_scan_submit_batch.argtypes = [vp, i, i, i, vp, i64, i64]
     L.rtlsdr_gpu_scan_submit_device.argtypes = [vp, i, i, i, vp, i64, i64]
+    L.rtlsdr_gpu_scan_submit_reads.argtypes = [vp, i, vp, vp, i64]
     L.rtlsdr_gpu_scan_flush.argtypes = [vp]
     L.rtlsdr_gpu_scan_sync.argtypes = [vp]
     L.rtlsdr_gpu_scan_collect.argtypes = [vp, i, vp, vp, vp]
@@ -124,7 +125,7 @@ class GpuScan:
 
     def __init__(self, tune_count, bin_e, buf_len, downsample=1, downsample_passes=0, boxcar=1,
                  comp_fir_size=0, peak_hold=0, rate=2400000, crop=0.0, window_coefs=None,
-                 sinewave=None, device=0, ring_bytes=0, level_stats=False):
+                 sinewave=None, device=0, ring_bytes=0, level_stats=False, iir_alpha=0.0):
         self.lib = load_library()
         self.tune_count, self.bin_e, self.buf_len = tune_count, bin_e, buf_len
         self.n = 1 << bin_e
@@ -145,6 +146,7 @@ class GpuScan:
             cfg.sinewave = self._s.ctypes.data
         cfg.ring_bytes = ring_bytes
         cfg.flags = 1 if level_stats else 0  # RTLSDR_GPU_FLAG_LEVEL_STATS
+        cfg.iir_alpha = iir_alpha            # -s iir smoothing of the dB rows across reports (0 = off)
         self.h = ctypes.c_void_p()
         rc = self.lib.rtlsdr_gpu_scan_init(ctypes.byref(cfg), ctypes.byref(self.h))
         if rc:
@@ -174,6 +176,12 @@ class GpuScan:
     def submit_batch(self, hop_first, hop_count, passes, host_ptr, pass_stride, hop_stride):
         self._check(self.lib.rtlsdr_gpu_scan_submit_batch(self.h, hop_first, hop_count, passes, host_ptr,
                                                           pass_stride, hop_stride), "submit_batch")
+
+    def submit_reads(self, hops, host_ptr, stride=None):
+        """hop visits in any order: read i (buf_len bytes at host_ptr + i * stride, pinned memory) belongs to hops[i]"""
+        hp = np.ascontiguousarray(hops, dtype=np.int32)
+        self._check(self.lib.rtlsdr_gpu_scan_submit_reads(self.h, hp.size, hp.ctypes.data, host_ptr,
+                                                          self.buf_len if stride is None else stride), "submit_reads")
 
     def submit_device(self, hop_first, hop_count, passes, dev_ptr, pass_stride, hop_stride):
         self._check(self.lib.rtlsdr_gpu_scan_submit_device(self.h, hop_first, hop_count, passes, dev_ptr,

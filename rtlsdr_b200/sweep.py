@@ -4,17 +4,28 @@ Frequency hops are independent (reference src/rtl_power.c:650-719: tunes[i] are
 disjoint), so hops are dealt to ranks in contiguous ranges and every rank runs
 its own rtlsdr_gpu_scan handle; there is no collective on the data path.  Once
 per integration interval the per-hop spectra (int64 bins, dB doubles, sample
-counts) are gathered to rank 0 with ONE gather, and rank 0 prints the rows in
-hop order like the reference's report loop (rtl_power.c:995-1000).
+counts) reach rank 0 with ONE exchange, and rank 0 prints the rows in hop order
+like the reference's report loop (rtl_power.c:995-1000).
 
 One process per GPU; torch.distributed is only the plumbing (NCCL over NVLink
 on the GPU box, gloo in the CPU tests).
 
-On a box with NVLink peer access the gather needs no collective at all: the report
-epilogue (rtlsdr_gpu_scan_collect_device) writes wherever it is pointed, so every
-rank points it at its slot of rank 0's buffer (torch symmetric memory peer mapping)
-and one symmetric-memory barrier per interval tells rank 0 that the slots are
-complete (RTLSDR_B200_NCCL_GATHER=1 keeps the NCCL gather).
+Three forms of the per-interval exchange, chosen once for all ranks:
+  peer   every rank's report epilogue (rtlsdr_gpu_scan_collect_device) stores
+         straight into its slot of rank 0's buffer through an NVLink peer mapping
+         (torch symmetric memory); one symmetric-memory barrier per interval on a
+         second stream tells rank 0 that all slots are complete.  No copy, no
+         collective kernel.
+  nccl   ONE torch.distributed.gather (grouped send/receive) per interval on a
+         second stream (RTLSDR_B200_NCCL_GATHER=1, or no peer access).
+  host   gloo / CPU tensors (tests; also CUDA ranks without NCCL: the report is
+         staged through host memory).
+
+Ordering rules this class owns: the handle's stream never rewrites a
+report buffer before the exchange that consumed it has finished
+(`before_collect`), and rank 0 copies a gathered report out before any rank may
+overwrite it (the exchange of interval j+1 is ordered behind that copy on rank 0's
+second stream, and every rank's epilogue j+2 waits for exchange j+1).
 """
 import os
 from dataclasses import dataclass
@@ -23,6 +34,8 @@ from typing import List, Optional
 import numpy as np
 import torch
 import torch.distributed as dist
+
+SLOTS = 2  # report buffers: interval j+1 is transformed while interval j is exchanged
 
 
 def shard_hops(tune_count: int, world: int, rank: int) -> range:
@@ -44,104 +57,200 @@ class IntervalReport:
 
 
 class SpectrumGather:
-    """Packs one rank's interval result into a single int64 buffer
-    [avg | db (bit pattern) | samples] padded to the largest shard, and gathers all
-    ranks' buffers to rank 0 with one collective call per interval."""
+    """One rank's side of the per-interval exchange.
 
-    def __init__(self, tune_count, n_bins, db_count, world, rank, device):
+    A report buffer is `words` int64 words: [avg hmax*N | db hmax*db_count (bit patterns) |
+    samples hmax x int32, padded to 8 bytes], hmax = the largest shard.  Use per interval j
+    (k = j % SLOTS):
+        before_collect(k, stream); collect_device(*pointers(k)); publish(k, stream)
+        ... later, rank 0: fetch(k)  (needs publish(..., to_host=True))
+    """
+
+    def __init__(self, tune_count, n_bins, db_count, world, rank, device, mode=None):
         self.tune_count, self.n, self.db_count = tune_count, n_bins, db_count
         self.world, self.rank = world, rank
+        self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
         self.hmax = max_hops_per_rank(tune_count, world)
-        self.words = self.hmax * (n_bins + db_count + 1)
+        self.smp_words = (self.hmax + 1) // 2
+        self.words = self.hmax * (n_bins + db_count) + self.smp_words
         self.my_hops = shard_hops(tune_count, world, rank)
-        self.peer = self._try_peer(torch.device(device)) if world > 1 else None
-        if self.peer is not None:
-            # this rank's slot of rank 0's buffer, mapped into this process over NVLink
-            self.send = self.peer[2][rank * self.words:(rank + 1) * self.words]
-            self.recv = None
+        self.peer = None
+        if mode is None:
+            mode = self._pick_mode()
+        if mode == "peer" and not self._setup_peer():
+            mode = "nccl"
+        self.mode = mode
+        self.last_exchange = None
+        if self.cuda:
+            self.comm = torch.cuda.Stream(device=self.device)
+            self.ready = [torch.cuda.Event() for _ in range(SLOTS)]
+            self.gathered = [torch.cuda.Event() for _ in range(SLOTS)]
+        if mode == "peer":
+            buf = self.peer[0]
+            self.send = [buf[(k * world + rank) * self.words:(k * world + rank + 1) * self.words] for k in range(SLOTS)]
+            self.recv = ([buf[k * world * self.words:(k + 1) * world * self.words].view(world, self.words)
+                          for k in range(SLOTS)] if rank == 0 else None)
         else:
-            self.send = torch.zeros(self.words, dtype=torch.int64, device=device)
-            self.recv = ([torch.zeros(self.words, dtype=torch.int64, device=device) for _ in range(world)]
-                         if rank == 0 and world > 1 else None)
+            dev = self.device
+            self.send = [torch.zeros(self.words, dtype=torch.int64, device=dev) for _ in range(SLOTS)]
+            rdev = torch.device("cpu") if mode == "host" else dev
+            self.recv = ([torch.zeros(world, self.words, dtype=torch.int64, device=rdev) for _ in range(SLOTS)]
+                         if rank == 0 else None)
+        if mode == "host" and self.cuda:
+            self.stage = [torch.zeros(self.words, dtype=torch.int64).pin_memory() for _ in range(SLOTS)]
+        # rank 0: pinned landing area of a gathered report
+        self.host = None
+        if rank == 0 and self.cuda and mode != "host":
+            self.host = [torch.zeros(world, self.words, dtype=torch.int64).pin_memory() for _ in range(SLOTS)]
 
-    def _try_peer(self, device):
-        """(local buffer, symmetric-memory handle, rank 0's buffer as seen from here), or None; all ranks agree"""
-        ok, peer = 0, None
-        if device.type == "cuda" and not os.environ.get("RTLSDR_B200_NCCL_GATHER"):
-            try:
-                import torch.distributed._symmetric_memory as symm
-                buf = symm.empty(self.world * self.words, dtype=torch.int64, device=device)
-                buf.zero_()
-                hdl = symm.rendezvous(buf, dist.group.WORLD)
-                root = hdl.get_buffer(0, (self.world * self.words,), torch.int64)
-                peer, ok = (buf, hdl, root), 1
-            except Exception:  # noqa: BLE001 -- any failure means: use the collective
-                peer = None
-        if device.type != "cuda":
-            return None  # (gloo tests: every rank takes this branch, no agreement round needed)
-        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+    # ---- setup ----------------------------------------------------------------
+
+    def _pick_mode(self):
+        if self.world == 1:
+            return "nccl" if self.cuda else "host"   # no exchange; "nccl" = device buffers
+        if not self.cuda or dist.get_backend() != "nccl":
+            return "host"
+        return "nccl" if os.environ.get("RTLSDR_B200_NCCL_GATHER") else "peer"
+
+    def _agree(self, ok):
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        return peer if int(flag.item()) == 1 else None
+        return int(flag.item()) == 1
 
-    # views into the send buffer, sized for THIS rank's hop count
-    def views(self):
-        h = len(self.my_hops)
-        a = self.send[: self.hmax * self.n].view(self.hmax, self.n)[:h]
-        o = self.hmax * self.n
-        d = self.send[o: o + self.hmax * self.db_count].view(torch.float64).view(self.hmax, self.db_count)[:h]
-        o += self.hmax * self.db_count
-        s = self.send[o: o + self.hmax][:h]
-        return a, d, s
+    def _setup_peer(self):
+        """Symmetric-memory buffer on every rank (rank 0's is the destination).  The rendezvous is a
+        collective, so the ranks first agree that everybody can reach it (import + allocation), and
+        agree again on its outcome; any failure anywhere -> every rank takes the NCCL gather."""
+        symm = buf = None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            # only rank 0's copy is ever written, but the allocation is symmetric by construction
+            buf = symm.empty(SLOTS * self.world * self.words, dtype=torch.int64, device=self.device)
+            buf.zero_()
+            ok = True
+        except Exception:  # noqa: BLE001
+            ok = False
+        if not self._agree(ok):
+            return False
+        hdl = None
+        try:
+            hdl = symm.rendezvous(buf, dist.group.WORLD)
+            root = int(hdl.buffer_ptrs[0])
+            ok = True
+        except Exception:  # noqa: BLE001
+            ok = False
+        if not self._agree(ok):
+            return False
+        self.peer = (buf, hdl, root)
+        return True
 
-    def pointers(self):
-        """device addresses for rtlsdr_gpu_scan_collect_device(avg, samples(int32), db)"""
-        base = self.send.data_ptr()
+    # ---- per interval -----------------------------------------------------------
+
+    def pointers(self, k=0):
+        """device addresses for rtlsdr_gpu_scan_collect_device(avg, samples(int32), db) of report buffer k:
+        this rank's slot of rank 0's buffer in peer mode, the local send buffer otherwise"""
+        if self.mode == "peer":
+            base = self.peer[2] + (k * self.world + self.rank) * self.words * 8
+        else:
+            base = self.send[k].data_ptr()
         p_db = base + self.hmax * self.n * 8
         p_smp = p_db + self.hmax * self.db_count * 8
         return base, p_smp, p_db
 
-    def samples_are_int32(self):
-        """collect_device writes int32 sample counts; widen them in place to int64 words."""
+    def views(self, k=0):
+        """(avg [h, N] int64, db [h, db_count] float64, samples [h] int32) views of the LOCAL send buffer k
+        sized for this rank's hop count (host mode / tests fill these instead of a GPU epilogue)"""
         h = len(self.my_hops)
-        o = self.hmax * (self.n + self.db_count)
-        raw = self.send[o: o + self.hmax].view(torch.int32)
-        vals = raw[:h].clone().to(torch.int64)
-        self.send[o: o + self.hmax].zero_()
-        self.send[o: o + h] = vals
+        s = self.send[k]
+        a = s[: self.hmax * self.n].view(self.hmax, self.n)[:h]
+        o = self.hmax * self.n
+        d = s[o: o + self.hmax * self.db_count].view(torch.float64).view(self.hmax, self.db_count)[:h]
+        o += self.hmax * self.db_count
+        c = s[o: o + self.smp_words].view(torch.int32)[:h]
+        return a, d, c
 
-    def gather(self) -> Optional[IntervalReport]:
-        if self.peer is not None:
-            buf, hdl, _ = self.peer
-            hdl.barrier(channel=0)          # every rank's epilogue has stored into rank 0's buffer
-            if self.rank != 0:
-                hdl.barrier(channel=1)      # rank 0 has read it: the slot may be rewritten
-                return None
-            host = buf.cpu()                # synchronises with the barrier above
-            hdl.barrier(channel=1)
-            bufs = [host[r * self.words:(r + 1) * self.words] for r in range(self.world)]
-        elif self.world > 1:
-            dist.gather(self.send, self.recv, dst=0)
-            if self.rank != 0:
-                return None
-            bufs = self.recv
+    def before_collect(self, k, stream=None):
+        """Call before the epilogue writes report buffer k: the handle's stream waits for the most recent
+        exchange (which, on rank 0, is ordered behind the copy-out of the exchange before it)."""
+        if self.cuda and self.last_exchange is not None and self.world > 1:
+            (stream or torch.cuda.current_stream()).wait_event(self.last_exchange)
+
+    def publish(self, k, stream=None, to_host=False):
+        """Report buffer k is complete once everything enqueued so far on `stream` has run: exchange it on the
+        second stream (asynchronous on CUDA).  to_host: rank 0 also copies the gathered report to pinned memory."""
+        if not self.cuda:
+            if self.world > 1:
+                dist.gather(self.send[k], list(self.recv[k].unbind(0)) if self.rank == 0 else None, dst=0)
+            elif self.rank == 0:
+                self.recv[k][0].copy_(self.send[k])
+            return
+        stream = stream or torch.cuda.current_stream()
+        self.ready[k].record(stream)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self.ready[k])
+            if self.world == 1:
+                src = self.send[k].view(1, self.words)
+            elif self.mode == "peer":
+                self.peer[1].barrier(channel=k)     # every rank's epilogue has stored into rank 0's buffer
+                src = self.recv[k] if self.rank == 0 else None
+            elif self.mode == "nccl":
+                dist.gather(self.send[k], list(self.recv[k].unbind(0)) if self.rank == 0 else None, dst=0)
+                src = self.recv[k] if self.rank == 0 else None
+            else:  # host staged (gloo with CUDA ranks)
+                self.stage[k].copy_(self.send[k], non_blocking=True)
+                self.comm.synchronize()
+                dist.gather(self.stage[k], list(self.recv[k].unbind(0)) if self.rank == 0 else None, dst=0)
+                src = None
+            if to_host and self.rank == 0 and src is not None:
+                self.host[k].copy_(src, non_blocking=True)
+            self.gathered[k].record(self.comm)
+        self.last_exchange = self.gathered[k]
+
+    def drain(self, stream=None):
+        """make `stream` wait for every exchange issued so far"""
+        if self.cuda:
+            (stream or torch.cuda.current_stream()).wait_stream(self.comm)
+
+    def fetch(self, k) -> Optional[IntervalReport]:
+        """rank 0: the gathered report of buffer k (blocks until its exchange and copy-out are done)"""
+        if self.cuda:
+            self.gathered[k].synchronize()
+        if self.rank != 0:
+            return None
+        if self.mode == "host" or not self.cuda:
+            bufs = self.recv[k].numpy()
         else:
-            bufs = [self.send]
+            bufs = self.host[k].numpy()
+        return self.unpack(bufs)
+
+    def unpack(self, bufs) -> IntervalReport:
+        """bufs: int64 [world, words] -> rows in hop order"""
         avg = np.zeros((self.tune_count, self.n), dtype=np.int64)
         db = np.zeros((self.tune_count, self.db_count), dtype=np.float64)
         smp = np.zeros(self.tune_count, dtype=np.int32)
-        for r, buf in enumerate(bufs):
+        for r in range(self.world):
             hops = shard_hops(self.tune_count, self.world, r)
-            if len(hops) == 0:
-                continue
-            b = buf.cpu().numpy()
             h = len(hops)
+            if h == 0:
+                continue
+            b = bufs[r]
             avg[hops.start: hops.stop] = b[: self.hmax * self.n].reshape(self.hmax, self.n)[:h]
             o = self.hmax * self.n
             db[hops.start: hops.stop] = b[o: o + self.hmax * self.db_count].view(np.float64).reshape(
                 self.hmax, self.db_count)[:h]
             o += self.hmax * self.db_count
-            smp[hops.start: hops.stop] = b[o: o + h].astype(np.int32)
+            smp[hops.start: hops.stop] = b[o: o + self.smp_words].view(np.int32)[:h]
         return IntervalReport(avg, db, smp)
+
+    def describe(self):
+        return {"peer": "every rank's report epilogue stores its int64 bins + dB + counts straight into rank 0's "
+                        "buffer over NVLink (symmetric-memory peer mapping); one symmetric-memory barrier per "
+                        "interval on a second stream",
+                "nccl": "one NCCL gather of int64 bins + dB + counts per interval, on a second stream, overlapped "
+                        "with the next interval's transform",
+                "host": "reports staged through host memory and gathered with torch.distributed (gloo)"}[self.mode] \
+            if self.world > 1 else "none (one rank)"
 
 
 def format_rows(plan, report: IntervalReport, stamp: str) -> List[str]:

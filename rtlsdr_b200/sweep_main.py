@@ -10,6 +10,8 @@ bins + dB rows + sample counts reach rank 0 -- written by every rank's report ep
 into rank 0's buffer over NVLink (symmetric-memory peer mapping, one barrier per interval), or by
 ONE NCCL gather where peer mapping is unavailable / RTLSDR_B200_NCCL_GATHER=1 -- and rank 0 prints
 the reference's CSV rows in hop order (rtl_power.c:995-1000).  With N = 1 no process group is created.
+Hop order inside a rank's shard can be randomised (--random-hops SEED, the reference's TODO list
+rtl_power.c:29-36): the bins are order independent (int64 sums / maxima, rtl_power.c:708-716).
 """
 import argparse
 import ctypes
@@ -32,6 +34,11 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--param", type=int, default=0)
     ap.add_argument("--stamp", default="2026-01-01, 00:00:00", help="fixed 'date, time' prefix of the rows")
+    ap.add_argument("--random-hops", type=int, default=None, metavar="SEED",
+                    help="visit the hops of every sweep in a random order (results do not depend on it)")
+    ap.add_argument("--backend", default="nccl", choices=["nccl", "gloo"],
+                    help="gloo: reports are staged through host memory (e.g. several ranks on one GPU in tests)")
+    ap.add_argument("--device", type=int, default=None, help="CUDA device of this rank (default: LOCAL_RANK)")
     ap.add_argument("-o", dest="out", default="-")
     args = ap.parse_args(argv)
 
@@ -39,17 +46,20 @@ def main(argv=None):
     import torch.distributed as dist
 
     from . import scan as rs
-    from .planner import host_library, plan_scan
+    from .planner import host_library, plan_scan, synth_cube
     from .sweep import SpectrumGather, format_rows, shard_hops
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0")) if args.device is None else args.device
     if not torch.cuda.is_available():
         raise SystemExit("sweep_main: no CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if args.backend == "nccl":
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("gloo")
 
     host = host_library()
     crop = host.rp_atofp(args.crop.encode())
@@ -65,33 +75,57 @@ def main(argv=None):
         window = rs.window_coefs(args.window, n) if pd["bin_e"] else None
         g = rs.GpuScan.from_plan(pd, window_coefs=window, device=local, hops=list(mine))
     db_count = g.db_count if g else plan.db_count
-    gather = SpectrumGather(tc, n, db_count, world, rank, torch.device("cuda", local))
+    gather = SpectrumGather(tc, n, db_count, world, rank, torch.device("cuda", local),
+                            mode=("host" if args.backend == "gloo" and world > 1 else None))
     if rank == 0 and world > 1:
-        print("sweep_main: interval reports " + ("are written by every rank straight into rank 0's buffer (NVLink peer "
-              "mapping, one symmetric-memory barrier per interval)" if gather.peer is not None else
-              "are gathered with one NCCL gather per interval"), file=sys.stderr)
+        print("sweep_main: interval reports: " + gather.describe(), file=sys.stderr)
     stream = torch.cuda.ExternalStream(g.get_stream()) if g else torch.cuda.current_stream()
-    pinned = rs.PinnedBuffer(max(1, args.sweeps * len(mine) * b)) if g else None
+    # Two pinned input cubes alternate: rtlsdr_gpu_scan_submit_batch() returns while its host-to-device copies
+    # are still queued, and `buf` must stay untouched until an event recorded on the handle's stream after the
+    # call has completed (include/rtlsdr_gpu_scan.h) -- `consumed[k]` below.
+    pinned = [rs.PinnedBuffer(max(1, args.sweeps * len(mine) * b)) for _ in range(2)] if g else None
+    consumed = [None, None]
 
+    rng = np.random.default_rng(args.random_hops + 7919 * rank) if args.random_hops is not None else None
     rows_out = []
-    for interval in range(args.intervals):
-        if g:
-            cube = pinned.view(np.uint8, (args.sweeps, len(mine), b))
-            for s in range(args.sweeps):
-                sweep_index = interval * args.sweeps + s
-                for k, hop in enumerate(mine):
-                    host.synth_generate(mode, ctypes.c_uint64(args.seed), args.param, tc, hop,
-                                        ctypes.c_uint64(sweep_index), cube[s, k].ctypes.data, ctypes.c_size_t(b))
-            g.submit_batch(0, len(mine), args.sweeps, pinned.ptr, len(mine) * b, b)
-            p_avg, p_smp, p_db = gather.pointers()
-            g.collect_device(p_avg, p_smp, p_db)
-            with torch.cuda.stream(stream):
-                gather.samples_are_int32()
-        # one collective per interval; the current stream must see the report first
-        torch.cuda.current_stream().wait_stream(stream)
-        report = gather.gather()
+    pending = None          # exchange buffer of the interval whose report has not been printed yet
+
+    def print_pending():
+        report = gather.fetch(pending)
         if rank == 0:
-            rows_out += format_rows(plan, report, args.stamp)
+            rows_out.extend(format_rows(plan, report, args.stamp))
+
+    for interval in range(args.intervals):
+        k = interval & 1
+        if g:
+            if consumed[k] is not None:
+                consumed[k].synchronize()
+            if rng is None:
+                synth_cube(pinned[k].ptr, mode, args.seed, args.param, tc, mine.start, len(mine),
+                           interval * args.sweeps, args.sweeps, b)
+                g.submit_batch(0, len(mine), args.sweeps, pinned[k].ptr, len(mine) * b, b)
+            else:
+                # randomised hopping: every sweep visits this rank's hops in its own random order
+                cube = pinned[k].view(np.uint8, (args.sweeps, len(mine), b))
+                order = np.stack([rng.permutation(len(mine)) for _ in range(args.sweeps)]).astype(np.int32)
+                for s_ in range(args.sweeps):
+                    for j, lh in enumerate(order[s_]):
+                        host.synth_generate(mode, ctypes.c_uint64(args.seed), args.param, tc, mine.start + int(lh),
+                                            ctypes.c_uint64(interval * args.sweeps + s_), cube[s_, j].ctypes.data,
+                                            ctypes.c_size_t(b))
+                g.submit_reads(order.ravel(), pinned[k].ptr, b)
+            gather.before_collect(k, stream)
+            g.collect_device(*gather.pointers(k))
+            consumed[k] = torch.cuda.Event()
+            consumed[k].record(stream)
+        # one exchange per interval (asynchronous, second stream); the previous interval's rows are
+        # printed while this one is on the GPU
+        gather.publish(k, stream, to_host=True)
+        if pending is not None:
+            print_pending()
+        pending = k
+    if pending is not None:
+        print_pending()
     if rank == 0:
         text = "".join(rows_out)
         if args.out == "-":

@@ -224,6 +224,7 @@ static inline int __dp2a_lo(int a, int b, int c) { return emu_dp2a(a, b, c, 0); 
 static inline int __dp2a_hi(int a, int b, int c) { return emu_dp2a(a, b, c, 2); }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
 
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v)

@@ -18,6 +18,7 @@ namespace {
 template <int L, bool PEAK, bool IN16>
 void run_small_t(const SmallParams &prm)
 {
+	/* u8 reads: prm.n_segs carries the grid size (CTAs share the reads in equal runs) */
 	cuda_emu::launch(dim3(prm.n_segs), dim3(kThreads), SmallSmem<L>::bytes,
 			 [&]() { scan_small_kernel<L, PEAK, IN16>(prm); });
 }
@@ -71,9 +72,9 @@ void fill_tw0(PassTw &tw0, const int2 *tw, int L)
 
 extern "C" {
 
-/* u8 path: reads [n_reads][16384], segs [n_segs][4] = (hop, first, count, 0) */
-void emu_small_u8(int L, int peak, const uint8_t *reads, int n_reads, const int *segs, int n_segs,
-		  const int *tw /* [N/2][2] */, const uint16_t *win, long long *avg)
+/* u8 path: reads [n_reads][16384] sorted by hop, hop_of [n_reads]; `grid` CTAs share the working sets in equal runs */
+void emu_small_u8(int L, int peak, const uint8_t *reads, int n_reads, const int *hop_of, int grid,
+		  const int *tw /* [N/2][2] */, const uint16_t *win, long long *avg, long long *samples)
 {
 	std::vector<long long> offs(n_reads);
 	for (int i = 0; i < n_reads; i++)
@@ -82,12 +83,12 @@ void emu_small_u8(int L, int peak, const uint8_t *reads, int n_reads, const int 
 	memset(&p, 0, sizeof(p));
 	p.base = reads;
 	p.read_off = offs.data();
-	p.segs = (const int4 *)segs;
-	p.n_segs = n_segs;
-	std::vector<long long> smp(4096, 0);
+	p.hop_of = hop_of;
+	p.n_entries = n_reads;
+	p.n_segs = grid; /* run_small_t launches n_segs CTAs */
 	p.avg = avg;
-	p.samples = smp.data();
-	p.samples_per_read = 1;
+	p.samples = samples;
+	p.samples_per_read = kStageBytes / (2 << L); /* FFT blocks per read (ds = 1) */
 	p.tw = (const int2 *)tw;
 	std::vector<int2> twc = compact_tw(p.tw, L);
 	p.twc = twc.data();
@@ -292,6 +293,7 @@ void emu_rms(const uint8_t *reads, int n_reads, int buf_len, const int *hop_of, 
 void emu_epilogue(const long long *avg, const int *samples, double *db, int bin_e, int i1, int i2, int rate, int hops)
 {
 	EpilogueParams p;
+	memset(&p, 0, sizeof(p));
 	std::vector<long long> smp(hops);
 	std::vector<long long> avg_copy((size_t)hops << bin_e, -1);
 	std::vector<int> smp_copy(hops, -1);

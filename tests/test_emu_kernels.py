@@ -67,13 +67,19 @@ def test_small_u8_kernel(emu, port_oracle, bin_e):
         reads, hops = make_reads(port_oracle.lib, plan, 3, SYNTH_BIASED, seed=bin_e, param=10)
         reads[1, :] = 255
         reads[2, :] = 0
-        want, _, _ = expected(port_oracle, plan, win, reads, hops)
-        sreads, _, segs = sort_by_hop(reads, hops, 2)
+        want, want_smp, _ = expected(port_oracle, plan, win, reads, hops)
+        sreads, shops, _ = sort_by_hop(reads, hops, 2)
+        shops = np.ascontiguousarray(shops, dtype=np.int32)
         tw = twiddles(port_oracle.sine_table(bin_e), bin_e)
         w16 = (win & 0xFFFF).astype(np.uint16)
-        avg = np.zeros((2, n), dtype=np.int64)
-        emu.emu_small_u8(bin_e, peak, vp(sreads), len(sreads), vp(segs), len(segs), vp(tw), vp(w16), vp(avg))
-        assert np.array_equal(avg, want), (bin_e, peak)
+        # the CTAs share the 12 working sets (half reads) in equal runs: 1 CTA, runs that cut reads in the
+        # middle (5, 7 CTAs), one working set per CTA, and more CTAs than work
+        for grid in ((1, 5, 12) if bin_e < 12 else (1, 2, 5, 7, 12, 15)):
+            avg = np.zeros((2, n), dtype=np.int64)
+            smp = np.zeros(2, dtype=np.int64)
+            emu.emu_small_u8(bin_e, peak, vp(sreads), len(sreads), vp(shops), grid, vp(tw), vp(w16), vp(avg), vp(smp))
+            assert np.array_equal(avg, want), (bin_e, peak, grid)
+            assert np.array_equal(smp, want_smp), (bin_e, peak, grid)
 
 
 @pytest.mark.parametrize("freq,window,fir,peak", [

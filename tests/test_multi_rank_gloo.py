@@ -55,22 +55,33 @@ def _worker(rank, world, port, tune_count, bin_e, out_path):
         sub = dict(plan)
         avg, smp, db = expected(port_o, sub, w, reads[sel], hops[sel])
         g = SpectrumGather(tune_count, n, db.shape[1], world, rank, "cpu")
-        a, d, s = g.views()
-        a.copy_(torch.from_numpy(avg[mine.start: mine.stop]))
-        d.copy_(torch.from_numpy(db[mine.start: mine.stop]))
-        s.copy_(torch.from_numpy(smp[mine.start: mine.stop].astype(np.int64)))
-        rep = g.gather()
+        assert g.mode == "host"
+        full = expected(port_o, plan, w, reads, hops)
+        ok = True
+        # three intervals through the two alternating report buffers; interval j scales the bins by j + 1 so that
+        # a stale or swapped buffer cannot go unnoticed
+        for j in range(3):
+            k = j & 1
+            a, d, s = g.views(k)
+            a.copy_(torch.from_numpy(avg[mine.start: mine.stop] * (j + 1)))
+            d.copy_(torch.from_numpy(db[mine.start: mine.stop] + j))
+            s.copy_(torch.from_numpy(smp[mine.start: mine.stop].astype(np.int32) + j))
+            g.before_collect(k)
+            g.publish(k, to_host=True)
+            rep = g.fetch(k)
+            if rank == 0:
+                ok = ok and (np.array_equal(rep.avg, full[0] * (j + 1)) and np.array_equal(rep.samples, full[1] + j)
+                             and np.array_equal(rep.db, full[2] + j, equal_nan=True))
+            else:
+                assert rep is None
         if rank == 0:
-            full = expected(port_o, plan, w, reads, hops)
-            ok = (np.array_equal(rep.avg, full[0]) and np.array_equal(rep.samples, full[1])
-                  and np.array_equal(rep.db, full[2], equal_nan=True))
             with open(out_path, "w") as f:
                 f.write("ok" if ok else "mismatch")
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("tune_count", [2, 5])
+@pytest.mark.parametrize("tune_count", [1, 2, 5])
 def test_gather_world_size_2(tmp_path, tune_count):
     out = tmp_path / "result.txt"
     port = _free_port()
