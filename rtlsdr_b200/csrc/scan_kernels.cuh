@@ -32,6 +32,20 @@
 #pragma once
 #include "scan_compat.cuh"
 
+/* Micro-variants of the transform kernel, all measured on B200 (profiles/r02d_small_kernel_ab.txt, config 5):
+ * window coefficients in registers +0.4 %, IDP.4A front end +0.8 %, packed "b" operands after a transpose +0.5 %,
+ * together +1.9 %.  (Tried and measured slower: 16-byte transpose stores -1.2 %, DC partial sums hoisted in front of
+ * the per-read barrier -0.5 %, IMAD.HI products: ptxas splits the chained form.)  tools/ab_run.sh builds both sides. */
+#ifndef RSCAN_WIN_REGS
+#define RSCAN_WIN_REGS 1
+#endif
+#ifndef RSCAN_FRONT_IDP
+#define RSCAN_FRONT_IDP 1
+#endif
+#ifndef RSCAN_PACKED_B
+#define RSCAN_PACKED_B 1
+#endif
+
 namespace rscan {
 
 typedef uint32_t c16; /* packed complex int16: re = bits 0..15, im = bits 16..31 */
@@ -95,6 +109,34 @@ SCAN_DEV X2 x_unpack(c16 v)
 SCAN_DEV c16 x_pack(X2 x)
 {
 	return __byte_perm((uint32_t)x.re, (uint32_t)x.im, 0x7632); /* one PRMT: bytes 2,3 of re | bytes 2,3 of im */
+}
+
+/* sign-extended low / high half of a packed value: one PRMT (sign-replicating selector) / one shift */
+SCAN_DEV int c16_re_fast(c16 v)
+{
+#ifdef SCAN_EMU
+	return (int)(int16_t)(uint16_t)(v & 0xFFFFu);
+#else
+	int r;
+	asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(r) : "r"(v));
+	return r;
+#endif
+}
+
+SCAN_DEV void butterfly_x(X2 &a, X2 &b, int wr, int wi);
+
+/* the same butterfly when the lower ("b") element is still PACKED (first stage after a transpose):
+ * its components are extracted straight from the packed word, the X-form unpack is skipped */
+SCAN_DEV void butterfly_x_packed_b(X2 &a, X2 &b, c16 vb, int wr, int wi)
+{
+	const int br = c16_re_fast(vb), bi = ((int)vb) >> 16;
+	const int tr = ((wr * br + 16384) >> 15) - ((wi * bi + 16384) >> 15);
+	const int ti = ((wr * bi + 16384) >> 15) + ((wi * br + 16384) >> 15);
+	const int hr = a.re >> 1, hi = a.im >> 1;
+	b.re = hr - tr * 65536;
+	b.im = hi - ti * 65536;
+	a.re = hr + tr * 65536;
+	a.im = hi + ti * 65536;
 }
 
 SCAN_DEV void butterfly_x(X2 &a, X2 &b, int wr, int wi)
@@ -178,7 +220,7 @@ SCAN_DEV int brev_bits(unsigned v, int bits)
  * (true for every table sine_table() builds; checked by the host at init).
  */
 template <int K, int LE, class TW>
-SCAN_DEV void run_pass(X2 (&x)[kPts], int t, const TW &tw)
+SCAN_DEV void run_pass(X2 (&x)[kPts], int t, const TW &tw, const c16 *packed = nullptr)
 {
 	constexpr int s0 = 4 * K;
 	constexpr int ns = (LE - s0) < 4 ? (LE - s0) : 4;
@@ -189,7 +231,9 @@ SCAN_DEV void run_pass(X2 (&x)[kPts], int t, const TW &tw)
 			if ((r & (1 << b)) == 0) {
 				const int2 w = tw.template get<K>(s0 + b, pos<K>(t, r));
 				const int g = r & ((1 << b) - 1);
-				if (K == 0 && TW::kTrivial && g == 0)
+				if (RSCAN_PACKED_B && K > 0 && b == 0 && packed) /* x[r | 1] has not been unpacked: take it from the packed word */
+					butterfly_x_packed_b(x[r], x[r | 1], packed[r | 1], w.x, w.y);
+				else if (K == 0 && TW::kTrivial && g == 0)
 					butterfly_x_re(x[r], x[r | (1 << b)], w.x);
 				else if (K == 0 && TW::kTrivial && b > 0 && g == (1 << (b - 1)))
 					butterfly_x_im(x[r], x[r | (1 << b)], w.y);
@@ -229,6 +273,23 @@ SCAN_DEV void exchange(X2 (&x)[kPts], c16 *xch, int tw_, int t, const BAR &bar =
 #pragma unroll
 	for (int r = 0; r < kPts; ++r)
 		x[r] = x_unpack(xch[xch_idx(pos<KB>(t, r))]);
+}
+
+/* Transpose whose odd registers stay packed in `pk` (they are the "b" elements of the next pass's first stage,
+ * butterfly_x_packed_b extracts them without the X-form unpack); even registers are unpacked as usual. */
+template <int KA, int KB, class BAR>
+SCAN_DEV void exchange_pk(X2 (&x)[kPts], c16 (&pk)[kPts], c16 *xch, int tw_, int t, const BAR &bar)
+{
+#pragma unroll
+	for (int r = 0; r < kPts; ++r)
+		xch[xch_idx(pos<KA>(tw_, r))] = x_pack(x[r]);
+	bar.sync();
+#pragma unroll
+	for (int r = 0; r < kPts; ++r) {
+		pk[r] = xch[xch_idx(pos<KB>(t, r))];
+		if (!RSCAN_PACKED_B || (r & 1) == 0)
+			x[r] = x_unpack(pk[r]);
+	}
 }
 
 /*
@@ -282,15 +343,16 @@ SCAN_DEV void engine_fft_db(X2 (&x)[kPts], c16 *xch2, int &flip, int t, const TW
 	if (t0 < 0)
 		t0 = t; /* natural front end: the registers hold positions 16t + r */
 	run_pass<0, LE>(x, t0, tw);
+	c16 pk[kPts];
 	if constexpr (LE > 4) {
-		exchange<0, 1, false, BAR>(x, xch2 + flip * kXchWords, t0, t, bar);
+		exchange_pk<0, 1, BAR>(x, pk, xch2 + flip * kXchWords, t0, t, bar);
 		flip ^= 1;
-		run_pass<1, LE>(x, t, tw);
+		run_pass<1, LE>(x, t, tw, pk);
 	}
 	if constexpr (LE > 8) {
-		exchange<1, 2, false, BAR>(x, xch2 + flip * kXchWords, t, t, bar);
+		exchange_pk<1, 2, BAR>(x, pk, xch2 + flip * kXchWords, t, t, bar);
 		flip ^= 1;
-		run_pass<2, LE>(x, t, tw);
+		run_pass<2, LE>(x, t, tw, pk);
 	}
 }
 
@@ -426,18 +488,46 @@ SCAN_DEV void front_index(int r, int t, int trev, int blkbase, int &nblk, int &n
 }
 
 /* u8 -> int16 minus (127 + DC), window, bit-reversed placement (rtl_power.c:666-668, 594, 697-706) */
+
+/* 4096 bins: a thread multiplies by the same 16 window coefficients in every working set (one FFT block per
+ * working set, nblk depends on (t, r) only), so they live in 8 registers, two 16-bit coefficients each */
+constexpr int kWinRegs = kPts / 2;
+
 template <int L>
+SCAN_DEV void load_window_regs(unsigned (&wreg)[kWinRegs], const uint16_t *wins, int t, int trev, int blkbase)
+{
+#pragma unroll
+	for (int j = 0; j < kWinRegs; ++j) {
+		int nblk0, nblk1, n;
+		front_index<L>(2 * j, t, trev, blkbase, nblk0, n);
+		front_index<L>(2 * j + 1, t, trev, blkbase, nblk1, n);
+		wreg[j] = (unsigned)wins[nblk0] | ((unsigned)wins[nblk1] << 16);
+	}
+}
+
+template <int L, bool WREG = false>
 SCAN_DEV void front_u8(X2 (&x)[kPts], const uint8_t *st, int ws, int kI, int kQ, const uint16_t *wins, int t, int trev,
-		       int blkbase)
+		       int blkbase, const unsigned *wreg = nullptr)
 {
 #pragma unroll
 	for (int r = 0; r < kPts; ++r) {
 		int nblk, n;
 		front_index<L>(r, t, trev, blkbase, nblk, n);
-		const int wv = wins[nblk];
+		/* (byte - k) in one IDP.4A each, times the window coefficient already moved to the high half:
+		 * the int16 truncation of the product (rtl_power.c:701, 705) is the natural mod-2^32 wrap */
+		unsigned wx;
+		if constexpr (WREG)
+			wx = (r & 1) ? (wreg[r >> 1] & 0xFFFF0000u) : (wreg[r >> 1] << 16);
+		else
+			wx = (unsigned)wins[nblk] << 16;
 		const unsigned raw = ((const uint16_t *)st)[ws * kWS + n];
-		x[r].re = (((int)(raw & 0xFFu) - kI) * wv) << 16;
-		x[r].im = (((int)(raw >> 8) - kQ) * wv) << 16;
+#if RSCAN_FRONT_IDP
+		x[r].re = (int)(__dp4a(raw, 0x00000001u, (unsigned)-kI) * wx);
+		x[r].im = (int)(__dp4a(raw, 0x00000100u, (unsigned)-kQ) * wx);
+#else
+		x[r].re = (int)((unsigned)((int)(raw & 0xFFu) - kI) * wx);
+		x[r].im = (int)((unsigned)((int)(raw >> 8) - kQ) * wx);
+#endif
 	}
 }
 
@@ -530,8 +620,17 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 	int flip = 0;
 
 	if constexpr (!IN16) {
+		/* runs are cut at half reads only when a CTA has several reads to amortise the read it shares with
+		 * its neighbour (both stage it and sum its DC term); short launches are cut at whole reads */
 		const long long total_ws = 2ll * prm.n_entries;
-		const long long ws_lo = total_ws * blockIdx.x / gridDim.x, ws_hi = total_ws * (blockIdx.x + 1) / gridDim.x;
+		long long ws_lo, ws_hi;
+		if (total_ws >= 8ll * gridDim.x) {
+			ws_lo = total_ws * blockIdx.x / gridDim.x;
+			ws_hi = total_ws * (blockIdx.x + 1) / gridDim.x;
+		} else {
+			ws_lo = 2 * ((long long)prm.n_entries * blockIdx.x / gridDim.x);
+			ws_hi = 2 * ((long long)prm.n_entries * (blockIdx.x + 1) / gridDim.x);
+		}
 		if (ws_lo >= ws_hi)
 			return;
 		const int e_lo = (int)(ws_lo >> 1), e_hi = (int)((ws_hi + 1) >> 1); /* reads [e_lo, e_hi) are touched */
@@ -549,6 +648,13 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 			for (int i = 0; i < kStageBytes / (kThreads * 16); ++i)
 				cp_async16(stage + (i * kThreads + t) * 16, src + (i * kThreads + t) * 16);
 			cp_async_commit();
+		}
+		constexpr bool kWinRegsOn = RSCAN_WIN_REGS && L == 12;
+		unsigned wreg[kWinRegs];
+		if constexpr (kWinRegsOn) {
+			cp_async_wait_all(); /* the tables have landed too (same thread's copies are not enough: barrier) */
+			__syncthreads();
+			load_window_regs<L>(wreg, wins, t, trev, blkbase);
 		}
 		for (int e = e_lo; e < e_hi; ++e) {
 			const int u = e - e_lo;
@@ -573,7 +679,7 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 #pragma unroll 1
 			for (int ws = ws0; ws < ws1; ++ws) {
 				X2 x[kPts];
-				front_u8<L>(x, st, ws, kI, kQ, wins, t, trev, blkbase);
+				front_u8<L, kWinRegsOn>(x, st, ws, kI, kQ, wins, t, trev, blkbase, wreg);
 				engine_fft_db<L>(x, xch, flip, t, tw, BlockBar(), t0);
 				/* ---- |X|^2 (rtl_power.c:636-640, 708-716) ---- */
 #pragma unroll

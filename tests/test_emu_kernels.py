@@ -72,14 +72,36 @@ def test_small_u8_kernel(emu, port_oracle, bin_e):
         shops = np.ascontiguousarray(shops, dtype=np.int32)
         tw = twiddles(port_oracle.sine_table(bin_e), bin_e)
         w16 = (win & 0xFFFF).astype(np.uint16)
-        # the CTAs share the 12 working sets (half reads) in equal runs: 1 CTA, runs that cut reads in the
-        # middle (5, 7 CTAs), one working set per CTA, and more CTAs than work
-        for grid in ((1, 5, 12) if bin_e < 12 else (1, 2, 5, 7, 12, 15)):
+        # the CTAs share the 6 reads in equal runs (cut at whole reads in so short a launch): 1 CTA, uneven
+        # runs (4, 5 CTAs), one read per CTA, and more CTAs than reads
+        for grid in ((1, 5) if bin_e < 12 else (1, 2, 4, 5, 6, 9)):
             avg = np.zeros((2, n), dtype=np.int64)
             smp = np.zeros(2, dtype=np.int64)
             emu.emu_small_u8(bin_e, peak, vp(sreads), len(sreads), vp(shops), grid, vp(tw), vp(w16), vp(avg), vp(smp))
             assert np.array_equal(avg, want), (bin_e, peak, grid)
             assert np.array_equal(smp, want_smp), (bin_e, peak, grid)
+
+
+@pytest.mark.parametrize("bin_e,peak", [(12, 0), (10, 1), (7, 0)])
+def test_small_u8_kernel_half_read_cuts(emu, port_oracle, bin_e, peak):
+    """launches with >= 4 reads per CTA are cut at half reads: 9 reads of 3 hops on 2 CTAs = 9 working sets
+    each, the cut falls in the middle of read 4 (both CTAs stage it and take its DC term, each transforms
+    its half); the first CTA's run covers a hop boundary, the second starts mid-hop"""
+    n = 1 << bin_e
+    plan = plan_dict(bin_e, peak_hold=peak, tune_count=3)
+    win = port_oracle.window_coefs("blackman", n)
+    reads, hops = make_reads(port_oracle.lib, plan, 3, SYNTH_BIASED, seed=40 + bin_e, param=-12)
+    reads[4, ::3] = 255
+    want, want_smp, _ = expected(port_oracle, plan, win, reads, hops)
+    sreads, shops, _ = sort_by_hop(reads, hops, 3)
+    shops = np.ascontiguousarray(shops, dtype=np.int32)
+    tw = twiddles(port_oracle.sine_table(bin_e), bin_e)
+    w16 = (win & 0xFFFF).astype(np.uint16)
+    avg = np.zeros((3, n), dtype=np.int64)
+    smp = np.zeros(3, dtype=np.int64)
+    emu.emu_small_u8(bin_e, peak, vp(sreads), len(sreads), vp(shops), 2, vp(tw), vp(w16), vp(avg), vp(smp))
+    assert np.array_equal(avg, want)
+    assert np.array_equal(smp, want_smp)
 
 
 @pytest.mark.parametrize("freq,window,fir,peak", [
