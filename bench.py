@@ -81,7 +81,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "10",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._pump, daemon=True)
             self.th.start()
@@ -229,7 +229,8 @@ class Dist:
         self.torch.cuda.synchronize()
 
     def max(self, v):
-        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        dev = "cuda" if self.dist.is_initialized() and self.dist.get_backend() == "nccl" else "cpu"
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=dev)
         if self.world > 1:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
@@ -321,11 +322,14 @@ def time_device(D, sw, steps, warmup, min_ms=MIN_TIMED_MS, sampler=None):
     k_ms, k_n = sw.g.kernel_time()
     sw.g.set_timing(0)
     if sampler:
-        # nvidia-smi ticks every 20 ms: keep the same load running, untimed, until a few clock samples exist
+        # nvidia-smi ticks every 10 ms: keep the same kernels running on THIS rank, untimed and WITHOUT the
+        # exchange (a collective that the other ranks do not join would never complete), until a few clock
+        # samples exist
         t_end = time.perf_counter() + 1.0
         while len(sampler.rows) < 4 and time.perf_counter() < t_end:
-            for i in range(4):
-                sw.step_device(i0 + i)
+            for _ in range(4):
+                sw.g.submit_device(0, sw.h, sw.sweeps, sw.dev_in.data_ptr(), sw.h * sw.b, sw.b)
+                sw.g.collect_device(*sw.gather.pointers(0))
             torch.cuda.synchronize()
     return (total_ms / (rounds * steps), rounds * steps, k_ms / max(k_n, 1), k_n,
             s1["kernel_launches"] - s0["kernel_launches"])
@@ -468,15 +472,21 @@ def run_gpu(args):
     D = Dist(torch, dist)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the GPU arm has no CPU fallback")
+    one_gpu = bool(os.environ.get("BENCH_GLOO_ONE_GPU"))   # tests: every rank on cuda:0, reports exchanged through gloo
+    if one_gpu:
+        D.local = 0
     torch.cuda.set_device(D.local)
     pin = pin_to_gpu_numa(D.local)            # before any pinned allocation
     if D.world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", D.local))
+        if one_gpu:
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", D.local))
     rs.load_library()
     peak, peak_src = read_peaks()
 
     # ---- headline: BASELINE configs[4], hops sharded over the ranks ----
-    sw = ShardedSweep(D, rs, RANGE, CROP, WINDOW, FIR, SWEEPS)
+    sw = ShardedSweep(D, rs, RANGE, CROP, WINDOW, FIR, args.sweeps)
     verify = verify_sharded(D, sw, KAT_P1)
     sampler = ClockSampler(D.local) if D.rank == 0 else None
     ms_step, timed_steps, k_ms, k_n, launches = time_device(D, sw, args.steps, args.warmup, sampler=sampler)
@@ -485,7 +495,7 @@ def run_gpu(args):
     e2e_s = time_e2e(D, sw, e2e_steps, args.warmup)
 
     # ---- second sharded workload: BASELINE configs[2] (623 hops do not divide evenly) ----
-    sw3 = ShardedSweep(D, rs, RANGE3, 0.0, "rectangle", FIR3, SWEEPS3)
+    sw3 = ShardedSweep(D, rs, RANGE3, 0.0, "rectangle", FIR3, max(1, SWEEPS3 * args.sweeps // SWEEPS))
     verify3 = verify_sharded(D, sw3, KAT3_P1, full_interval=False)
     ms3, steps3, k3_ms, _, _ = time_device(D, sw3, max(4, min(args.steps, 20)), 3)
     comp3 = None
@@ -511,8 +521,10 @@ def run_gpu(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "timed_steps": timed_steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int16/int64 fixed point", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "cli": f"-f {RANGE}", "hops": sw.tc, "bins": sw.n,
-                       "sweeps_per_step": SWEEPS, "reads_per_step": SWEEPS * sw.tc, "bytes_per_step": sw.bytes_all,
+            "config": {"workload": WORKLOAD if sw.sweeps == SWEEPS else
+                       f"REDUCED TEST SIZE ({sw.sweeps} sweeps per step, not a benchmark result) of {WORKLOAD}",
+                       "cli": f"-f {RANGE}", "hops": sw.tc, "bins": sw.n,
+                       "sweeps_per_step": sw.sweeps, "reads_per_step": sw.sweeps * sw.tc, "bytes_per_step": sw.bytes_all,
                        "hops_per_gpu": [len(shard_hops(sw.tc, D.world, r)) for r in range(D.world)],
                        "input": "synthetic source xorshift stream, bytes a pure function of (hop, sweep): "
                                 "identical job at every N",
@@ -616,6 +628,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    ap.add_argument("--sweeps", type=int, default=SWEEPS,
+                    help="sweeps per step (default = the benchmark's 256; tests shrink it, the line says so)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-companions", action="store_true", help="skip the other-configuration measurements")
     args = ap.parse_args()

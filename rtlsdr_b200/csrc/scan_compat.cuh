@@ -165,6 +165,21 @@ SCAN_DEV void bulk_copy_g2s(void *smem_dst, const void *gmem_src, unsigned bytes
 {
 #ifdef SCAN_EMU
 	::cuda_emu::bulk_copy(smem_dst, gmem_src, bytes, bar);
+#elif defined(RSCAN_RACECHECK_COPY)
+	/* Debug build for compute-sanitizer racecheck (tools/racecheck_stream.sh), never shipped: racecheck does not
+	 * model the async proxy's writes completing through complete_tx, so it flags every staged read of the real
+	 * build.  Here the SAME producer lane moves the chunk with ordinary loads / stores and then performs the
+	 * complete_tx on the SAME barrier itself: the full / empty protocol and every consumer are unchanged, only
+	 * the copy engine is one the tool understands. */
+	{
+		const uint4 *s = (const uint4 *)gmem_src;
+		uint4 *d = (uint4 *)smem_dst;
+		for (unsigned i = 0; i < bytes / 16; ++i)
+			d[i] = s[i];
+		__threadfence_block();
+		unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+		asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(b), "r"(bytes) : "memory");
+	}
 #else
 	unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
 	unsigned b = (unsigned)__cvta_generic_to_shared(bar);

@@ -269,3 +269,63 @@ def test_kat_rows_through_host_cube(scan_mod):
         pinned.free()
         assert fnv_c(avg) == want == fnv1a_int64(avg)
         assert (smp == 2).all()
+
+
+@pytest.mark.parametrize("bin_e,reads_n,peak", [(17, 150, 0), (17, 77, 1), (15, 300, 0), (18, 40, 0), (13, 700, 1)])
+def test_large_path_many_reads_shuffled_hops(scan_mod, port_oracle, bin_e, reads_n, peak):
+    """large-FFT path on one batch of many hop visits in shuffled order (submit_reads): unequal hop sizes, hop
+    changes inside round C's 16-read runs, sums / peaks of repeated reads"""
+    n = 1 << bin_e
+    tc = 3
+    plan = plan_dict(bin_e, buf_len=2 * n, peak_hold=peak, tune_count=tc, crop=0.25)
+    w = port_oracle.window_coefs("blackman-harris", n)
+    rng = np.random.default_rng(bin_e + reads_n)
+    # a handful of distinct reads, repeated (the oracle's time goes with the number of DISTINCT reads below)
+    base_reads, _ = make_reads(port_oracle.lib, dict(plan, tune_count=1), 6, SYNTH_BIASED, seed=bin_e, param=27)
+    base_reads[1, ::5] = 255
+    pick = rng.integers(0, len(base_reads), reads_n)
+    hops = np.sort(rng.integers(0, tc, reads_n)).astype(np.int32)     # unequal hop sizes, hop changes mid-CTA
+    # expected: per hop, sum / max over its reads of the per-read spectrum
+    one = {}
+    for j in range(len(base_reads)):
+        a, _, _ = expected(port_oracle, dict(plan, tune_count=1), w, base_reads[j:j + 1], np.zeros(1, np.int32))
+        one[j] = a[0]
+    want = np.zeros((tc, n), dtype=np.int64)
+    smp = np.zeros(tc, dtype=np.int32)
+    for j, h in zip(pick, hops):
+        want[h] = np.maximum(want[h], one[j]) if peak else want[h] + one[j]
+        smp[h] += 1
+    # ONE batch of reads_n hop visits in shuffled order (submit_reads): the library sorts them by hop and walks
+    # them chunk by chunk
+    order = rng.permutation(reads_n)
+    pinned = scan_mod.PinnedBuffer(reads_n * 2 * n)
+    pinned.view(np.uint8, (reads_n, 2 * n))[:] = base_reads[pick[order]]
+    g = scan_mod.GpuScan.from_plan(plan, window_coefs=w)
+    g.submit_reads(hops[order], pinned.ptr)
+    avg, got_smp, _ = g.collect_all(want_db=False)
+    g.close()
+    pinned.free()
+    assert np.array_equal(avg, want)
+    assert np.array_equal(got_smp, smp)
+
+
+def test_bench_two_ranks_on_one_gpu(scan_mod, tmp_path):
+    """bench.py's multi-rank control flow (hop sharding, verification against the known answer and the 1-rank run,
+    timed rounds, host-buffer leg, second sharded workload) with two ranks sharing cuda:0 and gloo as the
+    exchange (BENCH_GLOO_ONE_GPU=1) at a reduced size: every collective must be entered by both ranks."""
+    import json
+    env = dict(os.environ, BENCH_GLOO_ONE_GPU="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29400 + os.getpid() % 500), os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "4",
+           "--warmup", "3", "--sweeps", "8", "--no-cpu", "--no-companions"]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=420)
+    assert r.returncode == 0, r.stderr[-3000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["n_gpus"] == 2 and line["scaling"] == "strong"
+    assert line["config"]["hops_per_gpu"] == [256, 256]
+    v = line["verify"]
+    assert v["ok"] and v["kat_ok"] and v["interval_ok"] and v["kat_fnv"] == "7b1c7343a9686225"
+    assert v["interval_ranks"] == 2 and v["interval_fnv"] == v["interval_fnv_check"]
+    c3 = line["companions"][0]
+    assert c3["verify"]["ok"] and c3["hops_per_gpu"] == [312, 311]
+    assert line["value"] > 0 and line["e2e"]["value"] > 0 and line["gpu_launches"] >= 4

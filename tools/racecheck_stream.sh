@@ -1,0 +1,36 @@
+#!/bin/bash
+# compute-sanitizer racecheck of the warp-specialised narrow-scan kernels (scan_boxcar_stream_kernel modes 1/2/3,
+# scan_boxcar_sym_kernel mode 5) -- ADVICE r1 / VERDICT r1 "argued exemption":
+#   1. debug build (-DRSCAN_RACECHECK_COPY, build/racecheck/): the producer lane moves every chunk with ordinary
+#      loads/stores and then performs the complete_tx on the same full[] barrier itself; protocol and consumers are
+#      unchanged.  racecheck understands this hand-off -> the log must be CLEAN.
+#   2. production build (cp.async.bulk through the async proxy): racecheck does not model the async proxy's writes
+#      completing via complete_tx and flags the staged reads -> kept next to the clean log, counted.
+# usage: tools/racecheck_stream.sh TAG
+TAG=${1:-r02}
+mkdir -p gpurun_out build/racecheck
+DBG=build/racecheck/librtlsdr_gpu_scan_racecopy.so
+if [ ! -f $DBG ]; then
+  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden -shared \
+       -DRSCAN_RACECHECK_COPY -o $DBG rtlsdr_b200/csrc/scan_abi.cu
+fi
+K="boxcar_stream_kernel_forced and (10-28 or 12-16 or 8-13)"
+RTLSDR_GPU_SCAN_LIB=$PWD/$DBG timeout 1500 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_parity.py -x -q -k "$K" \
+    > gpurun_out/${TAG}_racecheck_debugcopy.txt 2>&1
+echo "== debug-copy build"; tail -4 gpurun_out/${TAG}_racecheck_debugcopy.txt | cut -c1-200
+RTLSDR_GPU_SCAN_LIB=$PWD/$DBG timeout 900 compute-sanitizer --tool synccheck python -m pytest tests/test_gpu_parity.py -x -q -k "$K" \
+    > gpurun_out/${TAG}_synccheck_debugcopy.txt 2>&1
+echo "== debug-copy build, synccheck"; tail -3 gpurun_out/${TAG}_synccheck_debugcopy.txt | cut -c1-200
+timeout 900 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_parity.py -x -q -k "boxcar_stream_kernel_forced and 10-28 and (5-0 or 1-0)" \
+    > gpurun_out/${TAG}_racecheck_production.txt 2>&1
+echo "== production build"; grep -c "Race reported" gpurun_out/${TAG}_racecheck_production.txt; tail -3 gpurun_out/${TAG}_racecheck_production.txt | cut -c1-200
+# the production log is huge: keep the head and the summary
+(head -40 gpurun_out/${TAG}_racecheck_production.txt; echo ...; tail -5 gpurun_out/${TAG}_racecheck_production.txt) > gpurun_out/${TAG}_racecheck_production_short.txt
+rm -f gpurun_out/${TAG}_racecheck_production.txt
+# new kernels of this round
+timeout 900 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_round2.py -x -q -k "equal_run or large_path or submit_reads or iir" \
+    > gpurun_out/${TAG}_memcheck_round2.txt 2>&1
+echo "== memcheck round-2 kernels"; tail -3 gpurun_out/${TAG}_memcheck_round2.txt | cut -c1-200
+timeout 900 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_round2.py -x -q -k "equal_run or (large_path and 17-77)" \
+    > gpurun_out/${TAG}_racecheck_round2.txt 2>&1
+echo "== racecheck round-2 kernels"; tail -3 gpurun_out/${TAG}_racecheck_round2.txt | cut -c1-200
