@@ -254,8 +254,11 @@ class ShardedSweep:
         self.mine = shard_hops(self.tc, D.world, D.rank)
         self.h = len(self.mine)
         self.window = rs.window_coefs(window, self.n) if pd["bin_e"] else None
-        self.g = rs.GpuScan.from_plan(pd, window_coefs=self.window, device=D.local, hops=list(self.mine))
+        # async_report: the report epilogue of interval k runs on the handle's report stream while the handle's own
+        # stream already transforms interval k+1 into the second accumulator set
+        self.g = rs.GpuScan.from_plan(pd, window_coefs=self.window, device=D.local, hops=list(self.mine), async_report=True)
         self.stream = torch.cuda.ExternalStream(self.g.get_stream())
+        self.rstream = torch.cuda.ExternalStream(self.g.get_report_stream())
         self.gather = SpectrumGather(self.tc, self.n, self.g.db_count, D.world, D.rank, torch.device("cuda", D.local))
         self.bytes_rank = sweeps * self.h * self.b
         self.bytes_all = sweeps * self.tc * self.b
@@ -269,13 +272,13 @@ class ShardedSweep:
     def step_device(self, i, sweeps=None, to_host=False):
         k = i & 1
         self.g.submit_device(0, self.h, sweeps or self.sweeps, self.dev_in.data_ptr(), self.h * self.b, self.b)
-        self.finish(self.g, self.stream, k, to_host)
+        self.finish(self.g, self.rstream, k, to_host)
 
-    def finish(self, g, stream, k, to_host):
-        """report epilogue into exchange buffer k + the exchange (asynchronous)"""
-        self.gather.before_collect(k, stream)
+    def finish(self, g, rstream, k, to_host):
+        """report epilogue into exchange buffer k (on the handle's report stream) + the exchange (asynchronous)"""
+        self.gather.before_collect(k, rstream)
         g.collect_device(*self.gather.pointers(k))
-        self.gather.publish(k, stream, to_host=to_host)
+        self.gather.publish(k, rstream, to_host=to_host)
 
     def report(self, k):
         """rank 0: IntervalReport of exchange buffer k; every rank blocks until the exchange is done"""
@@ -294,6 +297,7 @@ def time_device(D, sw, steps, warmup, min_ms=MIN_TIMED_MS, sampler=None):
     torch = D.torch
     for i in range(warmup):
         sw.step_device(i)
+    sw.stream.wait_stream(sw.rstream)
     sw.gather.drain(sw.stream)
     D.barrier()
     sw.g.kernel_time()      # arm / reset the per-kernel timers
@@ -309,7 +313,8 @@ def time_device(D, sw, steps, warmup, min_ms=MIN_TIMED_MS, sampler=None):
         e0.record(sw.stream)
         for i in range(steps):
             sw.step_device(i0 + i)
-        sw.gather.drain(sw.stream)          # the last exchanges are inside the timed region
+        sw.stream.wait_stream(sw.rstream)   # the last reports ...
+        sw.gather.drain(sw.stream)          # ... and exchanges are inside the timed region
         e1.record(sw.stream)
         D.barrier()
         ms = D.max(e0.elapsed_time(e1))
@@ -388,9 +393,9 @@ def time_e2e(D, sw, steps, warmup):
     so interval i+1 crosses PCIe while interval i is transformed and exchanged (what a continuously
     running rtl_power does).  Wall clock between barriers, max over ranks."""
     torch, rs = D.torch, sw.rs
-    g2 = rs.GpuScan.from_plan(sw.pd, window_coefs=sw.window, device=D.local, hops=list(sw.mine))
+    g2 = rs.GpuScan.from_plan(sw.pd, window_coefs=sw.window, device=D.local, hops=list(sw.mine), async_report=True)
     sw.extra.append(g2)
-    handles = [(sw.g, sw.stream), (g2, torch.cuda.ExternalStream(g2.get_stream()))]
+    handles = [(sw.g, sw.rstream), (g2, torch.cuda.ExternalStream(g2.get_report_stream()))]
 
     def submit(i):
         handles[i & 1][0].submit_batch(0, sw.h, sw.sweeps, sw.pinned.ptr, sw.h * sw.b, sw.b)

@@ -105,6 +105,13 @@ typedef struct rtlsdr_gpu_scan_cfg {
 /* cfg.flags: also count, per hop, the byte statistics librtlsdr's soft AGC looks at
  * (src/librtlsdr.c:3288-3306); read them with rtlsdr_gpu_scan_level_stats() */
 #define RTLSDR_GPU_FLAG_LEVEL_STATS 1u
+/* cfg.flags: rtlsdr_gpu_scan_collect_device() becomes asynchronous to the handle's stream: a second accumulator
+ * set is allocated, the report of the current set runs on a separate stream
+ * (rtlsdr_gpu_scan_get_report_stream()) behind everything submitted so far, and the next submits accumulate
+ * into the other set at once -- back-to-back integration intervals with the report off the transform's
+ * critical path (what rtl_power does between two reports, rtl_power.c:989-1003, without stalling the scanner).
+ * The caller orders its use of the report buffers against the REPORT stream.  Host collects are unchanged. */
+#define RTLSDR_GPU_FLAG_ASYNC_REPORT 2u
 
 /* ---- lifecycle --------------------------------------------------------- */
 
@@ -209,6 +216,24 @@ RTLSDR_GPU_API int rtlsdr_gpu_scan_collect_device(rtlsdr_gpu_scan_t *h, void *de
 RTLSDR_GPU_API int rtlsdr_gpu_scan_level_stats(rtlsdr_gpu_scan_t *h, int hop, uint64_t *overload,
 		uint64_t *high_level, uint64_t *bytes);
 
+/* ---- multi-GPU report hand-off ----------------------------------------- */
+
+/*
+ * With rtlsdr_gpu_scan_collect_device() every GPU's report epilogue can store straight into ONE GPU's memory
+ * (NVLink peer mapping).  These two calls are the rest of the "gather": a 32-bit flag per (buffer, writer),
+ * stored with system-scope release semantics by a one-thread kernel on `cuda_stream` (behind the epilogue), and a
+ * wait for `count` consecutive flags to reach `value` (wrap-safe compare) by a kernel whose threads sleep between
+ * polls, so it takes no issue slots from the transform kernels it runs beside.  The wait gives up after
+ * timeout_ms (0 = 10 s) and then sets *dev_timed_out (may be NULL) instead of hanging the GPU.  Both launch on the
+ * CURRENT device; flags may live in peer-mapped memory.  No reference counterpart (the reference has one device).
+ * Caution (CUDA lazy module loading): while a wait is pending, the FIRST launch of any kernel the process has not
+ * used yet may block until the wait ends; these two load each other before launching, callers should have run
+ * whatever else the waited-for work needs (e.g. one submit + collect_device) at least once beforehand.
+ */
+RTLSDR_GPU_API int rtlsdr_gpu_scan_flag_signal(void *cuda_stream, void *dev_flag, uint32_t value);
+RTLSDR_GPU_API int rtlsdr_gpu_scan_flag_wait(void *cuda_stream, const void *dev_flags, int count, uint32_t value,
+		uint32_t timeout_ms, void *dev_timed_out);
+
 /* ---- helpers ----------------------------------------------------------- */
 
 /* Number of doubles per hop that collect() writes to `db` (= i2 - i1 + 2). */
@@ -222,6 +247,9 @@ RTLSDR_GPU_API int rtlsdr_gpu_scan_set_stream(rtlsdr_gpu_scan_t *h, void *cuda_s
 /* The stream the handle currently launches on (cudaStream_t as void*), e.g. to record events on it
  * or to make other streams wait for it. */
 RTLSDR_GPU_API void *rtlsdr_gpu_scan_get_stream(rtlsdr_gpu_scan_t *h);
+/* The stream rtlsdr_gpu_scan_collect_device() puts its report on: the handle's stream, or the separate report
+ * stream of RTLSDR_GPU_FLAG_ASYNC_REPORT. */
+RTLSDR_GPU_API void *rtlsdr_gpu_scan_get_report_stream(rtlsdr_gpu_scan_t *h);
 /* Host table builders using the reference's expressions: Sinewave
  * (rtl_power.c:247-261; out[(1<<bin_e)*3/4]) and window_coefs for a -w name
  * (rtl_power.c:329-408, 826-843, 985-988; out[n]).  window returns -1 for an

@@ -75,6 +75,14 @@ struct rtlsdr_gpu_scan {
 
 	long long *d_avg = nullptr;     /* [tune_count * N] bins, then [tune_count] sample counters */
 	long long *d_smp64 = nullptr;   /* = d_avg + tune_count * N */
+	/* RTLSDR_GPU_FLAG_ASYNC_REPORT: a second accumulator set.  collect_device() reports the current set on
+	 * report_stream and flips, so the handle's stream runs transform kernels back to back (d_avg / d_smp64
+	 * always point at the set the NEXT submits accumulate into) */
+	long long *d_avg_other = nullptr;
+	cudaStream_t report_stream = nullptr;
+	cudaEvent_t ev_scan = nullptr, ev_report[2] = { nullptr, nullptr };
+	bool report_pending[2] = { false, false };
+	int cur_acc = 0;
 	unsigned *d_done = nullptr;     /* [tune_count] epilogue tickets (fused read-and-zero) */
 	unsigned long long *d_level = nullptr; /* [tune_count][2] soft-AGC byte counts (optional) */
 	std::vector<uint64_t> level_bytes;
@@ -147,6 +155,7 @@ struct rtlsdr_gpu_scan {
 	 * RTLSDR_GPU_BOXCAR_STREAM = 0|1|2|3|5 forces the narrow-scan kernel variant,
 	 * RTLSDR_GPU_NO_FUSED_BOXCAR / RTLSDR_GPU_NO_HB_STREAM fall back to the staged kernels */
 	int dbg_boxcar_mode = -1;
+	int dbg_stagger_ns = 0;
 	bool dbg_no_fused_boxcar = false, dbg_no_hb_stream = false;
 
 	std::string last_error;
@@ -910,6 +919,7 @@ int launch_batch(rtlsdr_gpu_scan *h, const uint8_t *base, const uint8_t *d_desc,
 		p.read_off = d_offs;
 		p.hop_of = d_hops;
 		p.n_entries = n_reads;
+		p.stagger_ns = h->dbg_stagger_ns;
 		p.avg = h->d_avg;
 		p.samples = h->d_smp64;
 		p.samples_per_read = h->samples_per_read;
@@ -1119,7 +1129,17 @@ void free_all(rtlsdr_gpu_scan *h)
 	cudaSetDevice(h->cfg.device);
 	if (h->stream)
 		cudaStreamSynchronize(h->stream);
+	if (h->report_stream)
+		cudaStreamSynchronize(h->report_stream);
 	cudaFree(h->d_avg);
+	cudaFree(h->d_avg_other);
+	if (h->report_stream)
+		cudaStreamDestroy(h->report_stream);
+	if (h->ev_scan)
+		cudaEventDestroy(h->ev_scan);
+	for (int i = 0; i < 2; i++)
+		if (h->ev_report[i])
+			cudaEventDestroy(h->ev_report[i]);
 	cudaFree(h->d_tw);
 	cudaFree(h->d_level);
 	cudaFree(h->d_done);
@@ -1336,6 +1356,8 @@ int rtlsdr_gpu_scan_init(const rtlsdr_gpu_scan_cfg_t *cfg_in, rtlsdr_gpu_scan_t 
 		h->dbg_boxcar_mode = m;
 	}
 	h->dbg_no_fused_boxcar = getenv("RTLSDR_GPU_NO_FUSED_BOXCAR") != nullptr;
+	if (const char *f = getenv("RTLSDR_GPU_STAGGER_NS"))
+		h->dbg_stagger_ns = atoi(f);
 	h->dbg_no_hb_stream = getenv("RTLSDR_GPU_NO_HB_STREAM") != nullptr;
 	h->cfg.window_coefs = nullptr;
 	h->cfg.sinewave = nullptr;
@@ -1398,6 +1420,18 @@ int rtlsdr_gpu_scan_init(const rtlsdr_gpu_scan_cfg_t *cfg_in, rtlsdr_gpu_scan_t 
 			break;
 		}
 		h->d_smp64 = h->d_avg + (size_t)cfg->tune_count * N;
+		if (cfg->flags & RTLSDR_GPU_FLAG_ASYNC_REPORT) {
+			if (cudaMalloc(&h->d_avg_other, avg_bytes) != cudaSuccess) {
+				rc = RTLSDR_GPU_ERR_NOMEM;
+				break;
+			}
+			if (cudaMemsetAsync(h->d_avg_other, 0, avg_bytes, h->stream) != cudaSuccess ||
+			    cudaStreamCreateWithFlags(&h->report_stream, cudaStreamNonBlocking) != cudaSuccess ||
+			    cudaEventCreateWithFlags(&h->ev_scan, cudaEventDisableTiming) != cudaSuccess ||
+			    cudaEventCreateWithFlags(&h->ev_report[0], cudaEventDisableTiming) != cudaSuccess ||
+			    cudaEventCreateWithFlags(&h->ev_report[1], cudaEventDisableTiming) != cudaSuccess)
+				break;
+		}
 		if (cudaMalloc(&h->d_done, (size_t)cfg->tune_count * sizeof(unsigned)) != cudaSuccess) {
 			rc = RTLSDR_GPU_ERR_NOMEM;
 			break;
@@ -1533,6 +1567,13 @@ void rtlsdr_gpu_scan_close(rtlsdr_gpu_scan_t *h)
 void *rtlsdr_gpu_scan_get_stream(rtlsdr_gpu_scan_t *h)
 {
 	return h ? (void *)h->stream : nullptr;
+}
+
+void *rtlsdr_gpu_scan_get_report_stream(rtlsdr_gpu_scan_t *h)
+{
+	if (!h)
+		return nullptr;
+	return (void *)((h->report_stream && !h->d_level) ? h->report_stream : h->stream);
 }
 
 int rtlsdr_gpu_scan_set_stream(rtlsdr_gpu_scan_t *h, void *cuda_stream)
@@ -1795,6 +1836,49 @@ int rtlsdr_gpu_scan_submit_reads(rtlsdr_gpu_scan_t *h, int n_reads, const int32_
 	return 0;
 }
 
+/* CUDA loads kernels lazily, and the first launch of a not-yet-loaded kernel can block until the kernels already
+ * running on the device have finished -- among them, possibly, the very flag_wait_kernel that this launch is
+ * meant to release.  Both kernels are therefore loaded (cudaFuncGetAttributes) before either is launched. */
+static int flag_kernels_loaded()
+{
+	cudaFuncAttributes attr;
+	if (cudaFuncGetAttributes(&attr, flag_signal_kernel) != cudaSuccess ||
+	    cudaFuncGetAttributes(&attr, flag_wait_kernel) != cudaSuccess) {
+		cudaGetLastError();
+		return RTLSDR_GPU_ERR_CUDA;
+	}
+	return 0;
+}
+
+int rtlsdr_gpu_scan_flag_signal(void *cuda_stream, void *dev_flag, uint32_t value)
+{
+	if (!dev_flag)
+		return RTLSDR_GPU_ERR_NULL;
+	if ((uintptr_t)dev_flag & 3)
+		return RTLSDR_GPU_ERR_ALIGN;
+	if (int rc = flag_kernels_loaded())
+		return rc;
+	flag_signal_kernel<<<1, 1, 0, (cudaStream_t)cuda_stream>>>((unsigned *)dev_flag, value);
+	return cudaGetLastError() == cudaSuccess ? 0 : RTLSDR_GPU_ERR_CUDA;
+}
+
+int rtlsdr_gpu_scan_flag_wait(void *cuda_stream, const void *dev_flags, int count, uint32_t value, uint32_t timeout_ms,
+			      void *dev_timed_out)
+{
+	if (!dev_flags)
+		return RTLSDR_GPU_ERR_NULL;
+	if (((uintptr_t)dev_flags & 3) || ((uintptr_t)dev_timed_out & 3))
+		return RTLSDR_GPU_ERR_ALIGN;
+	if (count <= 0 || count > 1024)
+		return RTLSDR_GPU_ERR_CONFIG;
+	if (int rc = flag_kernels_loaded())
+		return rc;
+	const unsigned long long ns = (unsigned long long)(timeout_ms ? timeout_ms : 10000u) * 1000000ull;
+	flag_wait_kernel<<<1, (count + 31) & ~31, 0, (cudaStream_t)cuda_stream>>>((const unsigned *)dev_flags, count, value, ns,
+										    (unsigned *)dev_timed_out);
+	return cudaGetLastError() == cudaSuccess ? 0 : RTLSDR_GPU_ERR_CUDA;
+}
+
 int rtlsdr_gpu_scan_db_count(const rtlsdr_gpu_scan_t *h)
 {
 	return h ? h->db_count : RTLSDR_GPU_ERR_NULL;
@@ -1868,6 +1952,32 @@ int rtlsdr_gpu_scan_collect_device(rtlsdr_gpu_scan_t *h, void *dev_avg, void *de
 	 * caller's buffers (e.g. the NCCL send buffer), one memset clears the state */
 	/* up to 8192 bins the last epilogue block of a hop also zeroes it (no memset launch) */
 	const bool fused_zero = N <= 8192;
+	if (h->report_stream && !h->d_level) {
+		/* asynchronous report: the epilogue of THIS accumulator set runs on report_stream behind everything
+		 * submitted so far, the handle's stream moves on to the other set at once */
+		cudaStream_t main_stream = h->stream;
+		CU(cudaEventRecord(h->ev_scan, main_stream));
+		CU(cudaStreamWaitEvent(h->report_stream, h->ev_scan, 0));
+		h->stream = h->report_stream;
+		rc = run_epilogue(h, 0, (int)tc, (double *)dev_db, (long long *)dev_avg, (int *)dev_samples, fused_zero);
+		if (!rc && !fused_zero) {
+			if (cudaMemsetAsync(h->d_avg, 0, (tc * N + tc) * sizeof(long long), h->report_stream) != cudaSuccess)
+				rc = RTLSDR_GPU_ERR_CUDA;
+		}
+		h->stream = main_stream;
+		h->last_was_epilogue = false;
+		if (rc)
+			return rc;
+		CU(cudaEventRecord(h->ev_report[h->cur_acc], h->report_stream));
+		h->report_pending[h->cur_acc] = true;
+		std::swap(h->d_avg, h->d_avg_other);
+		h->d_smp64 = h->d_avg + tc * N;
+		h->cur_acc ^= 1;
+		if (h->report_pending[h->cur_acc]) /* the set the next submits use: its last report (two collects ago) is done */
+			CU(cudaStreamWaitEvent(main_stream, h->ev_report[h->cur_acc], 0));
+		std::fill(h->samples.begin(), h->samples.end(), 0);
+		return 0;
+	}
 	if ((rc = run_epilogue(h, 0, (int)tc, (double *)dev_db, (long long *)dev_avg, (int *)dev_samples, fused_zero)))
 		return rc;
 	if (!fused_zero) {

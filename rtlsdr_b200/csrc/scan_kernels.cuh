@@ -379,6 +379,7 @@ struct SmallParams {
 	int n_segs;
 	const int *hop_of;          /* u8 reads: hop of entry e, entries sorted by hop */
 	int n_entries;              /* u8 reads: entries of this launch */
+	int stagger_ns;             /* u8 reads: start delay of the second resident wave half (see the kernel) */
 	long long *avg;             /* [tune_count << L] */
 	long long *samples;         /* [tune_count] tunes[i].samples (rtl_power.c:717) */
 	int samples_per_read;
@@ -633,6 +634,14 @@ scan_small_kernel(const SCAN_GRID_CONSTANT SmallParams prm)
 		}
 		if (ws_lo >= ws_hi)
 			return;
+#ifndef SCAN_EMU
+		/* The two CTAs of an SM start in lockstep (same phase of every working set: both in the front end, both at
+		 * a barrier ...) and only drift into complementary phases after many working sets; delaying the second
+		 * half of the grid (CTA b and b + gridDim/2 share an SM under round-robin placement) by about half a
+		 * working set de-phases them from the start.  Only worth it for short launches. */
+		if (prm.stagger_ns > 0 && blockIdx.x >= gridDim.x / 2)
+			__nanosleep((unsigned)prm.stagger_ns);
+#endif
 		const int e_lo = (int)(ws_lo >> 1), e_hi = (int)((ws_hi + 1) >> 1); /* reads [e_lo, e_hi) are touched */
 
 		unsigned long long acc[kPts];
@@ -1570,6 +1579,7 @@ struct FusedBoxcarParams {
 	int n_segs;
 	const int *hop_of;          /* u8 reads: hop of entry e, entries sorted by hop */
 	int n_entries;              /* u8 reads: entries of this launch */
+	int stagger_ns;             /* u8 reads: start delay of the second resident wave half (see the kernel) */
 	int ds;
 	int slots;                  /* staging ring depth, 2..4 chunks of 512 * ds bytes */
 	long long *avg;
@@ -2614,6 +2624,61 @@ epilogue_kernel(const SCAN_GRID_CONSTANT EpilogueParams prm)
 			}
 		}
 	}
+}
+
+/* ======================================================================== *
+ *  Device-side flags for the per-interval report exchange (multi-GPU)       *
+ * ======================================================================== */
+
+/*
+ * The report epilogue of every rank stores straight into rank 0's memory (NVLink peer mapping).  What is left of
+ * a "gather" is telling rank 0 that a slot is complete and telling the writers that rank 0 has consumed it: one
+ * 32-bit flag per (buffer, rank), written with a system-scope release store by a one-thread kernel behind the
+ * epilogue, and awaited by a kernel whose threads SLEEP between polls -- a waiter that spins (or a collective's
+ * CTAs) takes issue slots from the transform CTAs of the SM it lands on, and with the transform's static
+ * equal-run schedule one slowed SM delays the whole launch (measured at 8 GPUs: transform 545 us per interval
+ * with a spinning barrier kernel, 513 us without).
+ */
+__global__ void flag_signal_kernel(unsigned *flag, unsigned value)
+{
+#ifdef SCAN_EMU
+	*flag = value;
+#else
+	__threadfence_system();
+	asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+#endif
+}
+
+/* thread i waits until flags[i] - value >= 0 (wrap-safe); gives up after about `timeout_ns` and reports it */
+__global__ void flag_wait_kernel(const unsigned *flags, int count, unsigned value, unsigned long long timeout_ns,
+				 unsigned *timed_out)
+{
+	const int i = threadIdx.x;
+	if (i >= count)
+		return;
+#ifdef SCAN_EMU
+	(void)flags; (void)value; (void)timeout_ns; (void)timed_out;
+#else
+	unsigned long long t0;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+	unsigned sleep_ns = 64;
+	for (;;) {
+		unsigned v;
+		asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
+		if ((int)(v - value) >= 0)
+			break;
+		__nanosleep(sleep_ns);
+		if (sleep_ns < 2048)
+			sleep_ns *= 2;
+		unsigned long long t1;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+		if (t1 - t0 > timeout_ns) {
+			if (timed_out)
+				atomicExch(timed_out, 1u);
+			break;
+		}
+	}
+#endif
 }
 
 } // namespace rscan

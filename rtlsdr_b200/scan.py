@@ -48,6 +48,8 @@ def load_library():
     L.rtlsdr_gpu_scan_submit_batch.argtypes = [vp, i, i, i, vp, i64, i64]
     L.rtlsdr_gpu_scan_submit_device.argtypes = [vp, i, i, i, vp, i64, i64]
     L.rtlsdr_gpu_scan_submit_reads.argtypes = [vp, i, vp, vp, i64]
+    L.rtlsdr_gpu_scan_flag_signal.argtypes = [vp, vp, ctypes.c_uint32]
+    L.rtlsdr_gpu_scan_flag_wait.argtypes = [vp, vp, i, ctypes.c_uint32, ctypes.c_uint32, vp]
     L.rtlsdr_gpu_scan_flush.argtypes = [vp]
     L.rtlsdr_gpu_scan_sync.argtypes = [vp]
     L.rtlsdr_gpu_scan_collect.argtypes = [vp, i, vp, vp, vp]
@@ -61,6 +63,8 @@ def load_library():
     L.rtlsdr_gpu_scan_set_stream.argtypes = [vp, vp]
     L.rtlsdr_gpu_scan_get_stream.argtypes = [vp]
     L.rtlsdr_gpu_scan_get_stream.restype = vp
+    L.rtlsdr_gpu_scan_get_report_stream.argtypes = [vp]
+    L.rtlsdr_gpu_scan_get_report_stream.restype = vp
     L.rtlsdr_gpu_scan_sine_table.argtypes = [i, vp]
     L.rtlsdr_gpu_scan_sine_table.restype = None
     L.rtlsdr_gpu_scan_window.argtypes = [ctypes.c_char_p, i, vp]
@@ -87,6 +91,20 @@ def sine_table(bin_e):
     out = np.zeros(max((1 << bin_e) * 3 // 4, 1), dtype=np.int16)
     load_library().rtlsdr_gpu_scan_sine_table(bin_e, out.ctypes.data_as(ctypes.c_void_p))
     return out[: (1 << bin_e) * 3 // 4]
+
+
+def flag_signal(cuda_stream, dev_flag, value):
+    """one-thread kernel on `cuda_stream`: *dev_flag = value with system-scope release (may be peer memory)"""
+    rc = load_library().rtlsdr_gpu_scan_flag_signal(cuda_stream, dev_flag, value & 0xFFFFFFFF)
+    if rc:
+        raise ScanError(rc, "flag_signal")
+
+
+def flag_wait(cuda_stream, dev_flags, count, value, timeout_ms=0, dev_timed_out=None):
+    """kernel on `cuda_stream` that sleeps until dev_flags[0..count) have all reached `value`"""
+    rc = load_library().rtlsdr_gpu_scan_flag_wait(cuda_stream, dev_flags, count, value & 0xFFFFFFFF, timeout_ms, dev_timed_out)
+    if rc:
+        raise ScanError(rc, "flag_wait")
 
 
 class PinnedBuffer:
@@ -125,7 +143,7 @@ class GpuScan:
 
     def __init__(self, tune_count, bin_e, buf_len, downsample=1, downsample_passes=0, boxcar=1,
                  comp_fir_size=0, peak_hold=0, rate=2400000, crop=0.0, window_coefs=None,
-                 sinewave=None, device=0, ring_bytes=0, level_stats=False, iir_alpha=0.0):
+                 sinewave=None, device=0, ring_bytes=0, level_stats=False, iir_alpha=0.0, async_report=False):
         self.lib = load_library()
         self.tune_count, self.bin_e, self.buf_len = tune_count, bin_e, buf_len
         self.n = 1 << bin_e
@@ -145,7 +163,7 @@ class GpuScan:
             self._s = np.ascontiguousarray(sinewave, dtype=np.int16)
             cfg.sinewave = self._s.ctypes.data
         cfg.ring_bytes = ring_bytes
-        cfg.flags = 1 if level_stats else 0  # RTLSDR_GPU_FLAG_LEVEL_STATS
+        cfg.flags = (1 if level_stats else 0) | (2 if async_report else 0)  # RTLSDR_GPU_FLAG_LEVEL_STATS / _ASYNC_REPORT
         cfg.iir_alpha = iir_alpha            # -s iir smoothing of the dB rows across reports (0 = off)
         self.h = ctypes.c_void_p()
         rc = self.lib.rtlsdr_gpu_scan_init(ctypes.byref(cfg), ctypes.byref(self.h))
@@ -230,6 +248,10 @@ class GpuScan:
     def get_stream(self):
         """raw cudaStream_t of the handle (wrap with torch.cuda.ExternalStream to record events on it)"""
         return self.lib.rtlsdr_gpu_scan_get_stream(self.h)
+
+    def get_report_stream(self):
+        """raw cudaStream_t collect_device() reports on (the handle's stream unless async_report=True)"""
+        return self.lib.rtlsdr_gpu_scan_get_report_stream(self.h)
 
     def stats(self):
         k, a, b = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()

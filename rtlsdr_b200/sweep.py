@@ -13,19 +13,27 @@ on the GPU box, gloo in the CPU tests).
 Three forms of the per-interval exchange, chosen once for all ranks:
   peer   every rank's report epilogue (rtlsdr_gpu_scan_collect_device) stores
          straight into its slot of rank 0's buffer through an NVLink peer mapping
-         (torch symmetric memory); one symmetric-memory barrier per interval on a
-         second stream tells rank 0 that all slots are complete.  No copy, no
-         collective kernel.
+         (torch symmetric memory).  No copy, no collective kernel: a one-thread
+         kernel behind the epilogue raises the rank's "slot complete" flag in rank
+         0's memory, rank 0 waits for all flags on a second stream with a kernel
+         whose threads sleep between polls, (copies the report out,) and raises
+         an "interval consumed" flag in every rank's memory, which a rank awaits
+         before it rewrites that buffer two intervals later
+         (rtlsdr_gpu_scan_flag_signal / _flag_wait).  A spinning barrier kernel or a
+         collective's CTAs would take issue slots from the transform kernel on the
+         SM they land on, and with its static equal-run schedule one slowed SM
+         delays the whole launch (measured at 8 GPUs: 545 vs 513 us per interval).
   nccl   ONE torch.distributed.gather (grouped send/receive) per interval on a
          second stream (RTLSDR_B200_NCCL_GATHER=1, or no peer access).
   host   gloo / CPU tensors (tests; also CUDA ranks without NCCL: the report is
          staged through host memory).
 
-Ordering rules this class owns: the handle's stream never rewrites a
-report buffer before the exchange that consumed it has finished
-(`before_collect`), and rank 0 copies a gathered report out before any rank may
-overwrite it (the exchange of interval j+1 is ordered behind that copy on rank 0's
-second stream, and every rank's epilogue j+2 waits for exchange j+1).
+Ordering rules this class owns: a rank never rewrites a report buffer
+before the exchange that consumed it has finished (`before_collect`), and rank 0
+copies a gathered report out before any rank may overwrite it (peer: the
+"interval consumed" flag is raised behind that copy; nccl / host: the exchange of
+interval j+1 is ordered behind the copy on rank 0's second stream, and every rank's
+epilogue j+2 waits for exchange j+1).
 """
 import os
 from dataclasses import dataclass
@@ -76,6 +84,10 @@ class SpectrumGather:
         self.words = self.hmax * (n_bins + db_count) + self.smp_words
         self.my_hops = shard_hops(tune_count, world, rank)
         self.peer = None
+        # peer mode: int32 flags behind the report buffers of the symmetric allocation:
+        # [SLOTS][world] "slot complete" (used in rank 0's copy), [SLOTS] "interval consumed" (every rank's own copy), [1] time-out
+        self.flag_words = (SLOTS * world + SLOTS + 2 + 1) // 2
+        self.seq = [0] * SLOTS
         if mode is None:
             mode = self._pick_mode()
         if mode == "peer" and not self._setup_peer():
@@ -126,8 +138,9 @@ class SpectrumGather:
         try:
             import torch.distributed._symmetric_memory as symm
             # only rank 0's copy is ever written, but the allocation is symmetric by construction
-            buf = symm.empty(SLOTS * self.world * self.words, dtype=torch.int64, device=self.device)
+            buf = symm.empty(SLOTS * self.world * self.words + self.flag_words, dtype=torch.int64, device=self.device)
             buf.zero_()
+            torch.cuda.synchronize(self.device)   # flags are zero before any peer can raise one
             ok = True
         except Exception:  # noqa: BLE001
             ok = False
@@ -137,6 +150,7 @@ class SpectrumGather:
         try:
             hdl = symm.rendezvous(buf, dist.group.WORLD)
             root = int(hdl.buffer_ptrs[0])
+            self.peer_ptrs = [int(p) for p in hdl.buffer_ptrs]
             ok = True
         except Exception:  # noqa: BLE001
             ok = False
@@ -170,11 +184,25 @@ class SpectrumGather:
         c = s[o: o + self.smp_words].view(torch.int32)[:h]
         return a, d, c
 
+    def _flag_addr(self, owner, index):
+        """device address (as seen from this rank) of int32 flag `index` in rank `owner`'s symmetric buffer"""
+        return self.peer_ptrs[owner] + SLOTS * self.world * self.words * 8 + 4 * index
+
     def before_collect(self, k, stream=None):
-        """Call before the epilogue writes report buffer k: the handle's stream waits for the most recent
-        exchange (which, on rank 0, is ordered behind the copy-out of the exchange before it)."""
-        if self.cuda and self.last_exchange is not None and self.world > 1:
-            (stream or torch.cuda.current_stream()).wait_event(self.last_exchange)
+        """Call before the epilogue writes report buffer k (on the stream the epilogue will run on).
+        peer: that stream waits until rank 0 has consumed the buffer's previous content (its "interval consumed"
+        flag, raised behind rank 0's copy-out).  Otherwise: it waits for the most recent exchange (which, on rank
+        0, is ordered behind the copy-out of the exchange before it)."""
+        if not self.cuda or self.world == 1:
+            return
+        stream = stream or torch.cuda.current_stream()
+        if self.mode == "peer":
+            if self.seq[k] > 0:
+                from .scan import flag_wait
+                flag_wait(stream.cuda_stream, self._flag_addr(self.rank, SLOTS * self.world + k), 1, self.seq[k],
+                          0, self._flag_addr(self.rank, SLOTS * self.world + SLOTS))
+        elif self.last_exchange is not None:
+            stream.wait_event(self.last_exchange)
 
     def publish(self, k, stream=None, to_host=False):
         """Report buffer k is complete once everything enqueued so far on `stream` has run: exchange it on the
@@ -186,14 +214,31 @@ class SpectrumGather:
                 self.recv[k][0].copy_(self.send[k])
             return
         stream = stream or torch.cuda.current_stream()
+        if self.mode == "peer" and self.world > 1:
+            from .scan import flag_signal, flag_wait
+            self.seq[k] += 1
+            seq = self.seq[k]
+            # "my slot of buffer k is complete": into rank 0's memory, behind this rank's epilogue
+            flag_signal(stream.cuda_stream, self._flag_addr(0, k * self.world + self.rank), seq)
+            if self.rank != 0:
+                self.gathered[k].record(stream)
+                self.last_exchange = self.gathered[k]
+                return
+            with torch.cuda.stream(self.comm):
+                flag_wait(self.comm.cuda_stream, self._flag_addr(0, k * self.world), self.world, seq, 0,
+                          self._flag_addr(0, SLOTS * self.world + SLOTS))
+                if to_host:
+                    self.host[k].copy_(self.recv[k], non_blocking=True)
+                for r in range(self.world):   # "interval consumed": the slot may be rewritten
+                    flag_signal(self.comm.cuda_stream, self._flag_addr(r, SLOTS * self.world + k), seq)
+                self.gathered[k].record(self.comm)
+            self.last_exchange = self.gathered[k]
+            return
         self.ready[k].record(stream)
         with torch.cuda.stream(self.comm):
             self.comm.wait_event(self.ready[k])
             if self.world == 1:
                 src = self.send[k].view(1, self.words)
-            elif self.mode == "peer":
-                self.peer[1].barrier(channel=k)     # every rank's epilogue has stored into rank 0's buffer
-                src = self.recv[k] if self.rank == 0 else None
             elif self.mode == "nccl":
                 dist.gather(self.send[k], list(self.recv[k].unbind(0)) if self.rank == 0 else None, dst=0)
                 src = self.recv[k] if self.rank == 0 else None
@@ -218,6 +263,10 @@ class SpectrumGather:
             self.gathered[k].synchronize()
         if self.rank != 0:
             return None
+        if self.mode == "peer" and self.world > 1:
+            flags = self.peer[0][SLOTS * self.world * self.words:].view(torch.int32)
+            if int(flags[SLOTS * self.world + SLOTS].item()) != 0:
+                raise RuntimeError("SpectrumGather: a rank's report did not arrive within the flag wait's time-out")
         if self.mode == "host" or not self.cuda:
             bufs = self.recv[k].numpy()
         else:
@@ -245,8 +294,9 @@ class SpectrumGather:
 
     def describe(self):
         return {"peer": "every rank's report epilogue stores its int64 bins + dB + counts straight into rank 0's "
-                        "buffer over NVLink (symmetric-memory peer mapping); one symmetric-memory barrier per "
-                        "interval on a second stream",
+                        "buffer over NVLink (symmetric-memory peer mapping); per interval one 'slot complete' flag per "
+                        "rank and one 'consumed' flag back, raised by one-thread kernels and awaited by a sleeping "
+                        "kernel on a second stream (no collective, no spinning CTA beside the transform)",
                 "nccl": "one NCCL gather of int64 bins + dB + counts per interval, on a second stream, overlapped "
                         "with the next interval's transform",
                 "host": "reports staged through host memory and gathered with torch.distributed (gloo)"}[self.mode] \

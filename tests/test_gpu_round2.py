@@ -329,3 +329,74 @@ def test_bench_two_ranks_on_one_gpu(scan_mod, tmp_path):
     c3 = line["companions"][0]
     assert c3["verify"]["ok"] and c3["hops_per_gpu"] == [312, 311]
     assert line["value"] > 0 and line["e2e"]["value"] > 0 and line["gpu_launches"] >= 4
+
+
+@pytest.mark.parametrize("bin_e,peak", [(12, 0), (10, 1), (14, 0), (0, 0)])
+def test_async_report_back_to_back_intervals(scan_mod, port_oracle, bin_e, peak):
+    """RTLSDR_GPU_FLAG_ASYNC_REPORT: collect_device() reports on the handle's report stream and flips to the second
+    accumulator set; five intervals are queued back to back without any host synchronisation, every report must
+    equal the oracle's for ITS interval (no leakage between the two sets, read-and-zero intact), and a host
+    collect afterwards sees only what was submitted after the last device collect"""
+    import torch
+    n = 1 << bin_e
+    tc = 3
+    buf_len = max(16384, 2 * n)
+    plan = plan_dict(bin_e, buf_len=buf_len, peak_hold=peak, tune_count=tc, crop=0.2 if bin_e else 0.0, rate=1000000 if not bin_e else 2400000)
+    w = port_oracle.window_coefs("hamming", n) if bin_e else None
+    g = scan_mod.GpuScan.from_plan(plan, window_coefs=w, async_report=True)
+    assert g.get_report_stream() != g.get_stream()
+    keep, outs, wants = [], [], []
+    for it in range(5):
+        reads, hops = make_reads(port_oracle.lib, plan, 2 + it, SYNTH_BIASED, seed=100 + it, param=9 * it - 20)
+        wants.append(expected(port_oracle, plan, w if bin_e else np.zeros(1, np.int32), reads, hops))
+        dev = torch.from_numpy(reads).cuda()
+        keep.append(dev)
+        o_avg = torch.full((tc, n), -1, dtype=torch.int64, device="cuda")
+        o_smp = torch.full((tc,), -1, dtype=torch.int32, device="cuda")
+        o_db = torch.zeros((tc, g.db_count), dtype=torch.float64, device="cuda")
+        outs.append((o_avg, o_smp, o_db))
+        torch.cuda.synchronize()          # inputs / outputs exist before the handle's streams touch them
+        g.submit_device(0, tc, 2 + it, dev.data_ptr(), tc * buf_len, buf_len)
+        g.collect_device(o_avg.data_ptr(), o_smp.data_ptr(), o_db.data_ptr())
+    # something submitted after the last device collect, reported by a HOST collect
+    reads, hops = make_reads(port_oracle.lib, plan, 2, SYNTH_BIASED, seed=200, param=3)
+    for r, h in zip(reads, hops):
+        g.submit(int(h), r)
+    tail = g.collect_all()
+    torch.cuda.synchronize()
+    for it, (want, (o_avg, o_smp, o_db)) in enumerate(zip(wants, outs)):
+        assert np.array_equal(o_avg.cpu().numpy(), want[0]), it
+        assert np.array_equal(o_smp.cpu().numpy(), want[1]), it
+        assert db_close(o_db.cpu().numpy(), want[2]), it
+    want_tail = expected(port_oracle, plan, w if bin_e else np.zeros(1, np.int32), reads, hops)
+    assert np.array_equal(tail[0], want_tail[0]) and np.array_equal(tail[1], want_tail[1]) and db_close(tail[2], want_tail[2])
+    g.close()
+
+
+def test_flag_signal_and_sleeping_wait(scan_mod):
+    """the report hand-off kernels: a wait on stream A completes only after both flags were raised on stream B
+    (wrap-safe compare), and a wait that is never satisfied gives up after its time-out and says so"""
+    import time
+    import torch
+    flags = torch.zeros(4, dtype=torch.int32, device="cuda")
+    marker = torch.zeros(1, dtype=torch.int32, device="cuda")
+    a, b = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    scan_mod.flag_wait(a.cuda_stream, flags.data_ptr(), 2, 5, 5000, flags.data_ptr() + 12)
+    with torch.cuda.stream(a):
+        marker.fill_(1)
+    scan_mod.flag_signal(b.cuda_stream, flags.data_ptr(), 5)
+    b.synchronize()
+    time.sleep(0.05)
+    assert not a.query()                      # flag 1 still missing: the waiter sleeps, the marker is unset
+    scan_mod.flag_signal(b.cuda_stream, flags.data_ptr() + 4, 7)   # 7 >= 5
+    a.synchronize()
+    assert int(marker.item()) == 1 and flags.tolist() == [5, 7, 0, 0]
+    # time-out: nobody raises flag 2
+    t0 = time.perf_counter()
+    scan_mod.flag_wait(a.cuda_stream, flags.data_ptr() + 8, 1, 1, 60, flags.data_ptr() + 12)
+    a.synchronize()
+    assert 0.04 < time.perf_counter() - t0 < 2.0
+    assert flags.tolist() == [5, 7, 0, 1]
+    with pytest.raises(scan_mod.ScanError):
+        scan_mod.flag_wait(a.cuda_stream, flags.data_ptr() + 1, 1, 1)      # misaligned

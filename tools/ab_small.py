@@ -15,6 +15,8 @@ from rtlsdr_b200.planner import plan_scan  # noqa: E402
 CONFIGS = {
     "cfg5": ("24M:1457.6M:700", 0.0, "rectangle", None, 0, 256),
     "cfg5s": ("24M:1457.6M:700", 0.0, "rectangle", None, 0, 32),     # one GPU's share at N = 8
+    "cfg5n8": ("24M:203.2M:700", 0.0, "rectangle", None, 0, 256),     # exactly one GPU's share at N = 8: 64 hops x 256 sweeps
+    "cfg5n4": ("24M:382.4M:700", 0.0, "rectangle", None, 0, 256),     # one GPU's share at N = 4
     "cfg2": ("88M:108M:1k", 0.2, "hamming", None, 0, 377),
     "cfg3": ("24M:1766M:1k", 0.0, "rectangle", 9, 0, 64),
     "cfg1": ("100M:102.4M:2400", 0.0, "rectangle", None, 0, 293),
@@ -22,11 +24,17 @@ CONFIGS = {
     "box28": ("100M:100.1M:100", 0.0, "rectangle", None, 0, 8192),
     "f9": ("100M:100.1M:100", 0.0, "blackman", 9, 0, 8192),
     "rms": ("100M:110M:1M", 0.0, "rectangle", None, 0, 4096),
+    "rms1k": ("100M:110M:1M", 0.0, "rectangle", None, 0, 1024),
+    "rms16k": ("100M:110M:1M", 0.0, "rectangle", None, 0, 16384),
+    "box28x4": ("100M:100.1M:100", 0.0, "rectangle", None, 0, 32768),
 }
 
 
 def run(name):
-    freq, crop, window, fir, peak, passes = CONFIGS[name]
+    base, _, override = name.partition(":")          # "cfg5:32" = config 5 with 32 sweeps per step
+    freq, crop, window, fir, peak, passes = CONFIGS[base]
+    if override:
+        passes = int(override)
     pd = plan_scan(freq, crop, fir).as_dict()
     pd["peak_hold"] = peak
     tc, b, n = pd["tune_count"], pd["buf_len"], 1 << pd["bin_e"]

@@ -8,8 +8,8 @@ TAG=${1:-r02}; N=${2:-2}
 mkdir -p gpurun_out
 O=gpurun_out/${TAG}
 A="-f 24M:300M:1k -c 20% -w hamming --sweeps 4 --intervals 3"
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-python -m rtlsdr_b200.sweep_main $A -o ${O}_sweep_n1.csv
+TR="timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+timeout 150 python -m rtlsdr_b200.sweep_main $A -o ${O}_sweep_n1.csv
 $TR --master-port 29521 -m rtlsdr_b200.sweep_main $A -o ${O}_sweep_peer.csv 2> ${O}_sweep_peer.err
 RTLSDR_B200_NCCL_GATHER=1 $TR --master-port 29522 -m rtlsdr_b200.sweep_main $A -o ${O}_sweep_nccl.csv 2> ${O}_sweep_nccl.err
 $TR --master-port 29523 -m rtlsdr_b200.sweep_main $A --random-hops 3 -o ${O}_sweep_shuffled.csv 2> ${O}_sweep_shuffled.err
