@@ -240,10 +240,10 @@ class ShardedSweep:
     """One hop-sharded rtl_power scan: this rank's handle, its share of the synthetic input (pinned host
     copy + device-resident copy) and the per-interval exchange to rank 0."""
 
-    def __init__(self, D, rs, rng, crop, window, fir, sweeps, peak=0):
+    def __init__(self, D, rs, rng, crop, window, fir, sweeps, peak=0, sizes=None, device_copy=True):
         import numpy as np
         from rtlsdr_b200.planner import plan_scan, synth_cube
-        from rtlsdr_b200.sweep import SpectrumGather, shard_hops
+        from rtlsdr_b200.sweep import SpectrumGather, shard_ranges
         torch = D.torch
         self.D, self.rs, self.np = D, rs, np
         self.plan = plan_scan(rng, crop, fir)
@@ -251,7 +251,8 @@ class ShardedSweep:
         pd["peak_hold"] = peak
         self.pd, self.sweeps = pd, sweeps
         self.tc, self.b, self.n = pd["tune_count"], pd["buf_len"], 1 << pd["bin_e"]
-        self.mine = shard_hops(self.tc, D.world, D.rank)
+        self.sizes = [len(r) for r in shard_ranges(self.tc, D.world, sizes)]
+        self.mine = shard_ranges(self.tc, D.world, sizes)[D.rank]
         self.h = len(self.mine)
         self.window = rs.window_coefs(window, self.n) if pd["bin_e"] else None
         # async_report: the report epilogue of interval k runs on the handle's report stream while the handle's own
@@ -259,14 +260,17 @@ class ShardedSweep:
         self.g = rs.GpuScan.from_plan(pd, window_coefs=self.window, device=D.local, hops=list(self.mine), async_report=True)
         self.stream = torch.cuda.ExternalStream(self.g.get_stream())
         self.rstream = torch.cuda.ExternalStream(self.g.get_report_stream())
-        self.gather = SpectrumGather(self.tc, self.n, self.g.db_count, D.world, D.rank, torch.device("cuda", D.local))
+        self.gather = SpectrumGather(self.tc, self.n, self.g.db_count, D.world, D.rank, torch.device("cuda", D.local),
+                                     sizes=sizes)
         self.bytes_rank = sweeps * self.h * self.b
         self.bytes_all = sweeps * self.tc * self.b
         # input: bytes of read (sweep p, hop) from the synthetic source, [sweeps, my hops, buf_len]
         self.pinned = rs.PinnedBuffer(self.bytes_rank)
         synth_cube(self.pinned.ptr, SYNTH_XORSHIFT, 0, 0, self.tc, self.mine.start, self.h, 0, sweeps, self.b)
-        self.dev_in = torch.empty(self.bytes_rank, dtype=torch.uint8, device="cuda")
-        self.dev_in.copy_(torch.from_numpy(self.pinned.array), non_blocking=False)
+        self.dev_in = None
+        if device_copy:
+            self.dev_in = torch.empty(self.bytes_rank, dtype=torch.uint8, device="cuda")
+            self.dev_in.copy_(torch.from_numpy(self.pinned.array), non_blocking=False)
         self.extra = []     # second handle of the host-buffer leg
 
     def step_device(self, i, sweeps=None, to_host=False):
@@ -420,7 +424,36 @@ def time_e2e(D, sw, steps, warmup):
     if D.rank == 0:
         assert int(rep.samples[0]) == 2 * sw.sweeps and int(rep.samples[-1]) == 2 * sw.sweeps, \
             "e2e report does not cover one whole interval"
-    return dt
+    return dt, rep
+
+
+def probe_h2d(D):
+    """host-to-device GB/s of every rank's GPU with ALL ranks copying at the same time (pinned memory, CUDA events):
+    the GPUs of one box do not all see the same host bandwidth (profiles/r02i_pcie_topo_8gpu.json)"""
+    torch = D.torch
+    nbytes = 128 << 20
+    host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    dev = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        dev.copy_(host, non_blocking=True)
+    st.synchronize()
+    D.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(st):
+        e0.record(st)
+        for _ in range(6):
+            dev.copy_(host, non_blocking=True)
+        e1.record(st)
+    st.synchronize()
+    gbs = 6 * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    if D.world == 1:
+        return [gbs]
+    dev_t = "cuda" if D.dist.get_backend() == "nccl" else "cpu"
+    mine = torch.tensor([gbs], dtype=torch.float64, device=dev_t)
+    every = [torch.zeros(1, dtype=torch.float64, device=dev_t) for _ in range(D.world)]
+    D.dist.all_gather(every, mine)
+    return [float(t.item()) for t in every]
 
 
 def companion(rs, plan_scan, torch, name, freq, crop, window, fir, peak, passes, steps, peak_gbs):
@@ -496,8 +529,26 @@ def run_gpu(args):
     sampler = ClockSampler(D.local) if D.rank == 0 else None
     ms_step, timed_steps, k_ms, k_n, launches = time_device(D, sw, args.steps, args.warmup, sampler=sampler)
     clocks = sampler.stop() if sampler else None
+    # ---- end to end from host buffers: hop shares proportional to each GPU's host-to-device bandwidth ----
     e2e_steps = max(4, min(args.steps, 24))
-    e2e_s = time_e2e(D, sw, e2e_steps, args.warmup)
+    h2d = probe_h2d(D)
+    forced = os.environ.get("BENCH_E2E_WEIGHTS")           # tests
+    weights = [float(x) for x in forced.split(",")] if forced else h2d
+    sw_e2e, e2e_shares = sw, "equal"
+    if D.world > 1 and len(weights) == D.world and max(weights) > 1.1 * min(weights):
+        from rtlsdr_b200.sweep import weighted_sizes
+        sizes = weighted_sizes(sw.tc, weights)
+        sw_e2e = ShardedSweep(D, rs, RANGE, CROP, WINDOW, FIR, args.sweeps, sizes=sizes, device_copy=False)
+        e2e_shares = "proportional to the measured host-to-device bandwidth of every GPU"
+    e2e_s, e2e_rep = time_e2e(D, sw_e2e, e2e_steps, args.warmup)
+    e2e_ok = None
+    if D.rank == 0:
+        from rtlsdr_b200.planner import fnv1a_int64
+        e2e_ok = bool(f"{fnv1a_int64(e2e_rep.avg):016x}" == verify.get("interval_fnv"))
+    e2e_sizes = list(sw_e2e.sizes)
+    e2e_d2h = sw_e2e.gather.world * sw_e2e.gather.words * 8
+    if sw_e2e is not sw:
+        sw_e2e.close()
 
     # ---- second sharded workload: BASELINE configs[2] (623 hops do not divide evenly) ----
     sw3 = ShardedSweep(D, rs, RANGE3, 0.0, "rectangle", FIR3, max(1, SWEEPS3 * args.sweeps // SWEEPS))
@@ -520,7 +571,7 @@ def run_gpu(args):
         achieved = sw.bytes_rank / (k_ms * 1e-3) / 1e9 if k_n else None
         ncu = read_ncu()
         traffic = ncu.get("dram_bytes_per_launch") if ncu.get("launch_bytes") == sw.bytes_rank else None
-        d2h = sw.gather.world * sw.gather.words * 8
+        d2h = e2e_d2h
         line = {
             "metric": "input Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": D.world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "timed_steps": timed_steps,
@@ -548,6 +599,9 @@ def run_gpu(args):
                          "note": "integer-issue bound, not HBM bound at ds = 1: see DESIGN.md; roofline.issue is the bound it runs against"},
             "e2e": {"value": e2e, "unit": "Msamples/s", "h2d_bytes_per_step": sw.bytes_all,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "hop_shares": e2e_shares, "hops_per_gpu": e2e_sizes,
+                    "h2d_GBps_per_gpu_all_copying": [round(x, 1) for x in h2d],
+                    "report_fnv_equals_verified_interval": e2e_ok,
                     "api": "rtlsdr_gpu_scan_submit_batch (pinned host input, every rank its hops) + report epilogue + "
                            "exchange + gathered report copied to pinned host memory on rank 0; two handles alternate "
                            "so the next interval's copies overlap the transform"},
@@ -592,7 +646,7 @@ def run_gpu(args):
     sw.close()
     ok = True
     if D.rank == 0:
-        ok = bool(verify.get("ok")) and bool(verify3.get("ok"))
+        ok = bool(verify.get("ok")) and bool(verify3.get("ok")) and e2e_ok is not False
         if not ok:
             print("bench.py: VERIFY FAILED: gathered bins differ from the known answer / the 1-rank run", file=sys.stderr)
     if D.world > 1:

@@ -57,6 +57,43 @@ def max_hops_per_rank(tune_count: int, world: int) -> int:
     return -(-tune_count // world)
 
 
+def shard_ranges(tune_count: int, world: int, sizes=None) -> List[range]:
+    """Contiguous hop range of every rank: balanced (shard_hops) or with the given sizes (sum = tune_count),
+    e.g. proportional to each GPU's measured host-to-device bandwidth for host-fed sweeps."""
+    if sizes is None:
+        return [shard_hops(tune_count, world, r) for r in range(world)]
+    assert len(sizes) == world and sum(sizes) == tune_count and min(sizes) >= 0
+    out, lo = [], 0
+    for n in sizes:
+        out.append(range(lo, lo + n))
+        lo += n
+    return out
+
+
+def weighted_sizes(tune_count: int, weights) -> List[int]:
+    """integer shares of tune_count proportional to `weights` (largest remainders), at least one hop per rank
+    when there are enough hops"""
+    w = [max(float(x), 0.0) for x in weights]
+    total = sum(w) or 1.0
+    exact = [tune_count * x / total for x in w]
+    sizes = [int(e) for e in exact]
+    if tune_count >= len(w):
+        sizes = [max(1, n) for n in sizes]
+    order = sorted(range(len(w)), key=lambda i: exact[i] - int(exact[i]), reverse=True)
+    i = 0
+    while sum(sizes) < tune_count:
+        sizes[order[i % len(w)]] += 1
+        i += 1
+    order = sorted(range(len(w)), key=lambda i: sizes[i], reverse=True)
+    i = 0
+    while sum(sizes) > tune_count:
+        j = order[i % len(w)]
+        if sizes[j] > 1:
+            sizes[j] -= 1
+        i += 1
+    return sizes
+
+
 @dataclass
 class IntervalReport:
     avg: np.ndarray       # [tune_count, N] int64, natural FFT order
@@ -74,15 +111,16 @@ class SpectrumGather:
         ... later, rank 0: fetch(k)  (needs publish(..., to_host=True))
     """
 
-    def __init__(self, tune_count, n_bins, db_count, world, rank, device, mode=None):
+    def __init__(self, tune_count, n_bins, db_count, world, rank, device, mode=None, sizes=None):
         self.tune_count, self.n, self.db_count = tune_count, n_bins, db_count
         self.world, self.rank = world, rank
         self.device = torch.device(device)
         self.cuda = self.device.type == "cuda"
-        self.hmax = max_hops_per_rank(tune_count, world)
+        self.ranges = shard_ranges(tune_count, world, sizes)
+        self.hmax = max(1, max(len(r) for r in self.ranges))
         self.smp_words = (self.hmax + 1) // 2
         self.words = self.hmax * (n_bins + db_count) + self.smp_words
-        self.my_hops = shard_hops(tune_count, world, rank)
+        self.my_hops = self.ranges[rank]
         self.peer = None
         # peer mode: int32 flags behind the report buffers of the symmetric allocation:
         # [SLOTS][world] "slot complete" (used in rank 0's copy), [SLOTS] "interval consumed" (every rank's own copy), [1] time-out
@@ -279,7 +317,7 @@ class SpectrumGather:
         db = np.zeros((self.tune_count, self.db_count), dtype=np.float64)
         smp = np.zeros(self.tune_count, dtype=np.int32)
         for r in range(self.world):
-            hops = shard_hops(self.tune_count, self.world, r)
+            hops = self.ranges[r]
             h = len(hops)
             if h == 0:
                 continue

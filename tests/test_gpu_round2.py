@@ -314,7 +314,7 @@ def test_bench_two_ranks_on_one_gpu(scan_mod, tmp_path):
     timed rounds, host-buffer leg, second sharded workload) with two ranks sharing cuda:0 and gloo as the
     exchange (BENCH_GLOO_ONE_GPU=1) at a reduced size: every collective must be entered by both ranks."""
     import json
-    env = dict(os.environ, BENCH_GLOO_ONE_GPU="1")
+    env = dict(os.environ, BENCH_GLOO_ONE_GPU="1", BENCH_E2E_WEIGHTS="3,1")   # host-fed leg with unequal hop shares
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(29400 + os.getpid() % 500), os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "4",
            "--warmup", "3", "--sweeps", "8", "--no-cpu", "--no-companions"]
@@ -329,6 +329,7 @@ def test_bench_two_ranks_on_one_gpu(scan_mod, tmp_path):
     c3 = line["companions"][0]
     assert c3["verify"]["ok"] and c3["hops_per_gpu"] == [312, 311]
     assert line["value"] > 0 and line["e2e"]["value"] > 0 and line["gpu_launches"] >= 4
+    assert line["e2e"]["hops_per_gpu"] == [384, 128] and line["e2e"]["report_fnv_equals_verified_interval"] is True
 
 
 @pytest.mark.parametrize("bin_e,peak", [(12, 0), (10, 1), (14, 0), (0, 0)])

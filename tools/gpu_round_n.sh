@@ -4,7 +4,7 @@
 TAG=${1:-r02}; N=${2:-2}
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/${TAG}_topo.txt 2>&1
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
     bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_n$N.json 2> gpurun_out/${TAG}_bench_n$N.err
 echo "bench N=$N rc=$?"; tail -c 1500 gpurun_out/${TAG}_bench_n$N.err
 python - <<PY
@@ -18,7 +18,7 @@ try:
 except Exception as e:
     print("bench parse failed", e)
 PY
-RTLSDR_B200_NCCL_GATHER=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
+RTLSDR_B200_NCCL_GATHER=1 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
     bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_n${N}_nccl.json 2> gpurun_out/${TAG}_bench_n${N}_nccl.err
 echo "bench (NCCL gather) N=$N rc=$?"; python -c "
 import json; d=json.loads(open('gpurun_out/${TAG}_bench_n${N}_nccl.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['verify'].get('ok'), d['config']['exchange'][:40])"
