@@ -196,8 +196,9 @@ static int sweep(rtlsdr_dev_t *dev, const struct workers *ws, const rp_plan_t *p
 		rtlsdr_read_sync(dev, buf8, plan->buf_len, &got);
 		if (got != plan->buf_len)
 			fprintf(stderr, "Error: dropped samples.\n");
-		/* like the reference, the whole buffer is processed even after a short read */
-		rc = rtlsdr_gpu_scan_submit(gpu, hop - ws->first[w], buf8, (uint32_t)plan->buf_len);
+		/* like the reference, the whole per-hop buffer is processed even after a short read
+		 * (RTLSDR_GPU_FLAG_SHORT_READS keeps tunes[hop].buf8's stale tail inside the library) */
+		rc = rtlsdr_gpu_scan_submit(gpu, hop - ws->first[w], buf8, (uint32_t)(got > 0 && got < plan->buf_len ? got : plan->buf_len));
 		if (rc) {
 			fprintf(stderr, "rtlsdr_gpu_scan_submit: %s (%s)\n", rtlsdr_gpu_scan_strerror(rc),
 				rtlsdr_gpu_scan_last_cuda_error(gpu));
@@ -363,6 +364,7 @@ int main(int argc, char **argv)
 	cfg.rate = plan->rate;
 	cfg.crop = plan->crop;
 	cfg.window_coefs = window_coefs;
+	cfg.flags = RTLSDR_GPU_FLAG_SHORT_READS;
 	if (smooth_iir) {
 		const char *a = getenv("RTL_POWER_IIR_ALPHA");
 		cfg.iir_alpha = (a && *a) ? atof(a) : 0.25;

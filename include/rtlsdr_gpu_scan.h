@@ -112,6 +112,12 @@ typedef struct rtlsdr_gpu_scan_cfg {
  * critical path (what rtl_power does between two reports, rtl_power.c:989-1003, without stalling the scanner).
  * The caller orders its use of the report buffers against the REPORT stream.  Host collects are unchanged. */
 #define RTLSDR_GPU_FLAG_ASYNC_REPORT 2u
+/* cfg.flags: rtlsdr_gpu_scan_submit() accepts len < buf_len like the reference accepts a short rtlsdr_read_sync
+ * (rtl_power.c:657-659: it warns and processes the whole buffer): the handle keeps the reference's per-hop
+ * tunes[i].buf8 (tune_count x buf_len host bytes, zero at init where the reference's malloc leaves garbage), a
+ * short read replaces its first len bytes, the rest is the hop's previous read.  Costs one extra host copy per
+ * submit; without the flag a short len is RTLSDR_GPU_ERR_LENGTH. */
+#define RTLSDR_GPU_FLAG_SHORT_READS 4u
 
 /* ---- lifecycle --------------------------------------------------------- */
 
@@ -127,9 +133,10 @@ RTLSDR_GPU_API void rtlsdr_gpu_scan_close(rtlsdr_gpu_scan_t *h);
  * rtlsdr_read_sync() delivered (rtl_power.c:657).  (buf, len) has the shape of
  * rtlsdr_read_async_cb_t (rtl-sdr.h:472).  The bytes are copied into a pinned,
  * double-buffered staging ring before returning; host-to-device copy and
- * kernels run asynchronously.  len must equal buf_len: the reference processes
- * the full buffer even after a short read (rtl_power.c:658-659), so callers
- * pass the whole buffer they own.
+ * kernels run asynchronously.  len must equal buf_len (the reference processes
+ * the full buffer even after a short read, rtl_power.c:658-659, so callers pass
+ * the whole buffer they own) unless RTLSDR_GPU_FLAG_SHORT_READS is set, which
+ * reproduces that behaviour inside the library.
  */
 RTLSDR_GPU_API int rtlsdr_gpu_scan_submit(rtlsdr_gpu_scan_t *h, int hop, const uint8_t *buf, uint32_t len);
 

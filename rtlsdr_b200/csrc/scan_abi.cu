@@ -107,6 +107,7 @@ struct rtlsdr_gpu_scan {
 	bool ring_busy[2] = { false, false };
 	int cur_half = 0;
 	std::vector<int> ring_hops;
+	std::vector<uint8_t> hop_shadow; /* RTLSDR_GPU_FLAG_SHORT_READS: [tune_count][buf_len], the reference's tunes[i].buf8 */
 
 	DescSlot desc[kDescSlots];
 	int desc_next = 0;
@@ -1546,6 +1547,8 @@ int rtlsdr_gpu_scan_init(const rtlsdr_gpu_scan_cfg_t *cfg_in, rtlsdr_gpu_scan_t 
 			break;
 		}
 		h->ring_hops.reserve(h->ring_reads);
+		if (cfg->flags & RTLSDR_GPU_FLAG_SHORT_READS)
+			h->hop_shadow.assign((size_t)cfg->tune_count * B, 0);
 		if (cudaStreamSynchronize(h->stream) != cudaSuccess)
 			break;
 		rc = 0;
@@ -1593,10 +1596,20 @@ int rtlsdr_gpu_scan_submit(rtlsdr_gpu_scan_t *h, int hop, const uint8_t *buf, ui
 		return RTLSDR_GPU_ERR_NULL;
 	if (hop < 0 || hop >= h->cfg.tune_count)
 		return RTLSDR_GPU_ERR_HOP;
-	if (len != (uint32_t)h->cfg.buf_len)
-		return RTLSDR_GPU_ERR_LENGTH;
 	const size_t B = (size_t)h->cfg.buf_len;
-	memcpy(h->h_ring[h->cur_half] + h->ring_hops.size() * B, buf, B);
+	if (len > (uint32_t)h->cfg.buf_len || (len < (uint32_t)h->cfg.buf_len && h->hop_shadow.empty()))
+		return RTLSDR_GPU_ERR_LENGTH;
+	uint8_t *slot = h->h_ring[h->cur_half] + h->ring_hops.size() * B;
+	if (!h->hop_shadow.empty()) {
+		/* RTLSDR_GPU_FLAG_SHORT_READS: tunes[hop].buf8 of the reference -- a short read overwrites the first
+		 * n_read bytes, the rest still holds the hop's previous read, and the WHOLE buffer is processed
+		 * (rtl_power.c:657-659) */
+		uint8_t *shadow = h->hop_shadow.data() + (size_t)hop * B;
+		memcpy(shadow, buf, len);
+		memcpy(slot, shadow, B);
+	} else {
+		memcpy(slot, buf, B);
+	}
 	h->ring_hops.push_back(hop);
 	if ((int)h->ring_hops.size() >= h->ring_reads) {
 		CU(cudaSetDevice(h->cfg.device));

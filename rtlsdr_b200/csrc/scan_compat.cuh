@@ -133,6 +133,8 @@ SCAN_DEV void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes)
 {
 #ifdef SCAN_EMU
 	::cuda_emu::mbar_arrive(bar, bytes);
+#elif defined(RSCAN_RACECHECK_COPY)
+	(void)bar; (void)bytes; /* debug build: the producer's one arrival happens AFTER its copy, in bulk_copy_g2s */
 #else
 	unsigned s = (unsigned)__cvta_generic_to_shared(bar);
 	asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(s), "r"(bytes)
@@ -168,17 +170,17 @@ SCAN_DEV void bulk_copy_g2s(void *smem_dst, const void *gmem_src, unsigned bytes
 #elif defined(RSCAN_RACECHECK_COPY)
 	/* Debug build for compute-sanitizer racecheck (tools/racecheck_stream.sh), never shipped: racecheck does not
 	 * model the async proxy's writes completing through complete_tx, so it flags every staged read of the real
-	 * build.  Here the SAME producer lane moves the chunk with ordinary loads / stores and then performs the
-	 * complete_tx on the SAME barrier itself: the full / empty protocol and every consumer are unchanged, only
-	 * the copy engine is one the tool understands. */
+	 * build.  Here the SAME producer lane moves the chunk with ordinary loads / stores and then makes the ONE
+	 * arrival the full[] barrier expects (arrive.expect_tx + complete_tx of the real build collapse into a
+	 * plain arrive after the data is written): the full / empty protocol and every consumer are unchanged,
+	 * only the copy engine and the arrival are ones the tool may understand. */
 	{
 		const uint4 *s = (const uint4 *)gmem_src;
 		uint4 *d = (uint4 *)smem_dst;
 		for (unsigned i = 0; i < bytes / 16; ++i)
 			d[i] = s[i];
 		__threadfence_block();
-		unsigned b = (unsigned)__cvta_generic_to_shared(bar);
-		asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(b), "r"(bytes) : "memory");
+		mbar_arrive(bar);
 	}
 #else
 	unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);

@@ -401,3 +401,29 @@ def test_flag_signal_and_sleeping_wait(scan_mod):
     assert flags.tolist() == [5, 7, 0, 1]
     with pytest.raises(scan_mod.ScanError):
         scan_mod.flag_wait(a.cuda_stream, flags.data_ptr() + 1, 1, 1)      # misaligned
+
+
+def test_short_reads_keep_the_hops_previous_tail(scan_mod, port_oracle):
+    """RTLSDR_GPU_FLAG_SHORT_READS: a short rtlsdr_read_sync overwrites the first n_read bytes of tunes[hop].buf8,
+    the rest still holds the hop's previous read, and the reference processes the whole buffer
+    (rtl_power.c:657-659).  Without the flag a short length is an error."""
+    plan = plan_dict(10, tune_count=2, crop=0.0)
+    b = plan["buf_len"]
+    w = port_oracle.window_coefs("hamming", 1024)
+    reads, hops = make_reads(port_oracle.lib, plan, 3, SYNTH_BIASED, seed=77, param=15)
+    lens = [b, b, 5000, b, b, 1]            # hop 0: full, short (5000), full; hop 1: full, full, 1 byte
+    g = scan_mod.GpuScan.from_plan(plan, window_coefs=w, short_reads=True)
+    shadow = np.zeros((2, b), dtype=np.uint8)
+    seen = []
+    for r, h, n in zip(reads, hops, lens):
+        shadow[h, :n] = r[:n]
+        seen.append(shadow[h].copy())
+        scan_mod.load_library().rtlsdr_gpu_scan_submit(g.h, int(h), r.ctypes.data, n)
+    got = g.collect_all()
+    g.close()
+    want = expected(port_oracle, plan, w, np.stack(seen), hops)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and db_close(got[2], want[2])
+    g = scan_mod.GpuScan.from_plan(plan, window_coefs=w)
+    assert scan_mod.load_library().rtlsdr_gpu_scan_submit(g.h, 0, reads[0].ctypes.data, 5000) == -4
+    assert scan_mod.load_library().rtlsdr_gpu_scan_submit(g.h, 0, reads[0].ctypes.data, b + 16) == -4
+    g.close()

@@ -9,7 +9,7 @@ from scan_cases import KAT_ROWS, expected, make_reads
 
 
 def test_tables(ref_oracle, port_oracle):
-    for m in range(1, 15):
+    for m in range(1, 19):
         assert np.array_equal(ref_oracle.sine_table(m), port_oracle.sine_table(m))
     for w in WINDOWS + ["no-such-window"]:
         for f in ("100M:102.4M:2400", "100M:100.5M:10k", "88M:108M:1k"):
@@ -18,8 +18,10 @@ def test_tables(ref_oracle, port_oracle):
 
 
 def test_fix_fft_incl_int16_wrap(ref_oracle, port_oracle):
+    """fix_fft of the restatement == the reference object's, m = 1..17 (rtl_power.c:483 allows up to 21; the large
+    sizes are what the GPU's multi-round path is checked against), incl. full-scale inputs that hit the int16 wrap"""
     rng = np.random.default_rng(1)
-    for m in range(1, 14):
+    for m in range(1, 18):
         ref_oracle.sine_table(m)
         n = 1 << m
         ph = 2 * np.pi * max(n // 8, 1) * np.arange(n) / n + np.pi / 4
@@ -54,6 +56,26 @@ def test_reference_reproduces_survey_rows(ref_oracle, row):
     ref_oracle.scan(passes)
     assert ref_oracle.fnv() == fnv
     assert fnv1a_int64(ref_oracle.avg()) == fnv
+
+
+@pytest.mark.parametrize("freq,bin_e,window,peak", [("100M:102.4M:150", 15, "blackman-harris", 0),
+                                                    ("100M:102.4M:38", 17, "hamming", 1),
+                                                    ("100M:102.4M:600", 13, "bartlett", 0)])
+def test_whole_scans_large_bin_counts(ref_oracle, port_oracle, freq, bin_e, window, peak):
+    """whole-scan restatement vs reference at 2^13 / 2^15 / 2^17 bins (the port's large sizes rested on
+    a single known-answer hash)"""
+    for mode, param in ((SYNTH_BIASED, -31), (SYNTH_TONE, 127), (SYNTH_CONST, 255)):
+        pl = ref_oracle.configure(freq, 0.1, window, -1, peak)
+        assert pl["bin_e"] == bin_e
+        ref_oracle.source(mode, 5, param)
+        ref_oracle.scan(2)
+        reads, hops = make_reads(port_oracle.lib, pl, 2, mode, 5, param)
+        avg, smp, db = expected(port_oracle, pl, ref_oracle.window_coefs(), reads, hops)
+        assert np.array_equal(avg, ref_oracle.avg()), (freq, mode)
+        assert np.array_equal(smp, ref_oracle.samples())
+        from rtlsdr_b200.planner import plan_scan
+        p = plan_scan(freq, 0.1)
+        assert p.csv_row(0, int(smp[0]), db[0]) == ref_oracle.csv(0)
 
 
 @pytest.mark.parametrize("freq,crop,window,fir,peak", [

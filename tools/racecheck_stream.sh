@@ -10,7 +10,7 @@
 TAG=${1:-r02}
 mkdir -p gpurun_out build/racecheck
 DBG=build/racecheck/librtlsdr_gpu_scan_racecopy.so
-if [ ! -f $DBG ]; then
+if [ ! -f $DBG ] || [ -n "$(find rtlsdr_b200/csrc include -newer $DBG -print -quit)" ]; then
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden -shared \
        -DRSCAN_RACECHECK_COPY -o $DBG rtlsdr_b200/csrc/scan_abi.cu
 fi
