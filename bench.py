@@ -311,12 +311,15 @@ def time_device(D, sw, steps, warmup, min_ms=MIN_TIMED_MS, sampler=None):
         sampler.start()
     total_ms, rounds, i0 = 0.0, 0, warmup
     want = 1
+    issue_ms = 0.0      # host time to ISSUE one step (python + CUDA API calls): must stay below the GPU's step time
     while rounds < want:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         D.barrier()
         e0.record(sw.stream)
+        t_issue = time.perf_counter()
         for i in range(steps):
             sw.step_device(i0 + i)
+        issue_ms = max(issue_ms, 1e3 * (time.perf_counter() - t_issue) / steps)
         sw.stream.wait_stream(sw.rstream)   # the last reports ...
         sw.gather.drain(sw.stream)          # ... and exchanges are inside the timed region
         e1.record(sw.stream)
@@ -341,7 +344,7 @@ def time_device(D, sw, steps, warmup, min_ms=MIN_TIMED_MS, sampler=None):
                 sw.g.collect_device(*sw.gather.pointers(0))
             torch.cuda.synchronize()
     return (total_ms / (rounds * steps), rounds * steps, k_ms / max(k_n, 1), k_n,
-            s1["kernel_launches"] - s0["kernel_launches"])
+            s1["kernel_launches"] - s0["kernel_launches"], D.max(issue_ms))
 
 
 def verify_sharded(D, sw, kat_p1, full_interval=True):
@@ -527,7 +530,7 @@ def run_gpu(args):
     sw = ShardedSweep(D, rs, RANGE, CROP, WINDOW, FIR, args.sweeps)
     verify = verify_sharded(D, sw, KAT_P1)
     sampler = ClockSampler(D.local) if D.rank == 0 else None
-    ms_step, timed_steps, k_ms, k_n, launches = time_device(D, sw, args.steps, args.warmup, sampler=sampler)
+    ms_step, timed_steps, k_ms, k_n, launches, issue_ms = time_device(D, sw, args.steps, args.warmup, sampler=sampler)
     clocks = sampler.stop() if sampler else None
     # ---- end to end from host buffers: hop shares proportional to each GPU's host-to-device bandwidth ----
     e2e_steps = max(4, min(args.steps, 24))
@@ -553,7 +556,7 @@ def run_gpu(args):
     # ---- second sharded workload: BASELINE configs[2] (623 hops do not divide evenly) ----
     sw3 = ShardedSweep(D, rs, RANGE3, 0.0, "rectangle", FIR3, max(1, SWEEPS3 * args.sweeps // SWEEPS))
     verify3 = verify_sharded(D, sw3, KAT3_P1, full_interval=False)
-    ms3, steps3, k3_ms, _, _ = time_device(D, sw3, max(4, min(args.steps, 20)), 3)
+    ms3, steps3, k3_ms, _, _, _ = time_device(D, sw3, max(4, min(args.steps, 20)), 3)
     comp3 = None
     if D.rank == 0:
         v3 = sw3.bytes_all / 2 / (ms3 * 1e-3) / 1e6
@@ -589,6 +592,7 @@ def run_gpu(args):
                                  f"({timed_steps} steps timed)",
                        "exchange": sw.gather.describe(), "host_pinning": pin},
             "per_gpu_value": value / D.world,
+            "host_issue_ms_per_step": issue_ms,
             "verify": verify,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,

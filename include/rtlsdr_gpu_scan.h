@@ -238,6 +238,8 @@ RTLSDR_GPU_API int rtlsdr_gpu_scan_level_stats(rtlsdr_gpu_scan_t *h, int hop, ui
  * whatever else the waited-for work needs (e.g. one submit + collect_device) at least once beforehand.
  */
 RTLSDR_GPU_API int rtlsdr_gpu_scan_flag_signal(void *cuda_stream, void *dev_flag, uint32_t value);
+/* the same value into up to 32 flags at unrelated addresses with ONE launch (dev_flags is a host array of device pointers) */
+RTLSDR_GPU_API int rtlsdr_gpu_scan_flag_signal_many(void *cuda_stream, void *const *dev_flags, int count, uint32_t value);
 RTLSDR_GPU_API int rtlsdr_gpu_scan_flag_wait(void *cuda_stream, const void *dev_flags, int count, uint32_t value,
 		uint32_t timeout_ms, void *dev_timed_out);
 

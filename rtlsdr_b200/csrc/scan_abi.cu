@@ -450,7 +450,12 @@ int launch_small_t(rtlsdr_gpu_scan *h, const SmallParams &prm)
 {
 	auto kern = scan_small_kernel<L, PEAK, IN16>;
 	const int smem = SmallSmem<L>::bytes;
-	CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+	static bool attr_set[64] = { false }; /* once per kernel instance and device, not per launch */
+	if (h->cfg.device >= 64 || !attr_set[h->cfg.device]) {
+		CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		if (h->cfg.device < 64)
+			attr_set[h->cfg.device] = true;
+	}
 	/* u8 reads: one resident wave of persistent CTAs, each with an equal share of the working sets;
 	 * decimated images: one CTA per segment */
 	const int grid = IN16 ? std::min(prm.n_segs, h->num_sms * 8)
@@ -1854,12 +1859,21 @@ int rtlsdr_gpu_scan_submit_reads(rtlsdr_gpu_scan_t *h, int n_reads, const int32_
  * meant to release.  Both kernels are therefore loaded (cudaFuncGetAttributes) before either is launched. */
 static int flag_kernels_loaded()
 {
+	static bool loaded[64] = { false }; /* per device: modules load per context */
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess)
+		return RTLSDR_GPU_ERR_CUDA;
+	if (dev >= 0 && dev < 64 && loaded[dev])
+		return 0;
 	cudaFuncAttributes attr;
 	if (cudaFuncGetAttributes(&attr, flag_signal_kernel) != cudaSuccess ||
+	    cudaFuncGetAttributes(&attr, flag_signal_many_kernel) != cudaSuccess ||
 	    cudaFuncGetAttributes(&attr, flag_wait_kernel) != cudaSuccess) {
 		cudaGetLastError();
 		return RTLSDR_GPU_ERR_CUDA;
 	}
+	if (dev >= 0 && dev < 64)
+		loaded[dev] = true;
 	return 0;
 }
 
@@ -1872,6 +1886,26 @@ int rtlsdr_gpu_scan_flag_signal(void *cuda_stream, void *dev_flag, uint32_t valu
 	if (int rc = flag_kernels_loaded())
 		return rc;
 	flag_signal_kernel<<<1, 1, 0, (cudaStream_t)cuda_stream>>>((unsigned *)dev_flag, value);
+	return cudaGetLastError() == cudaSuccess ? 0 : RTLSDR_GPU_ERR_CUDA;
+}
+
+int rtlsdr_gpu_scan_flag_signal_many(void *cuda_stream, void *const *dev_flags, int count, uint32_t value)
+{
+	if (!dev_flags)
+		return RTLSDR_GPU_ERR_NULL;
+	if (count <= 0 || count > kFlagSignalMax)
+		return RTLSDR_GPU_ERR_CONFIG;
+	FlagList list;
+	for (int i = 0; i < count; i++) {
+		if (!dev_flags[i])
+			return RTLSDR_GPU_ERR_NULL;
+		if ((uintptr_t)dev_flags[i] & 3)
+			return RTLSDR_GPU_ERR_ALIGN;
+		list.flag[i] = (unsigned *)dev_flags[i];
+	}
+	if (int rc = flag_kernels_loaded())
+		return rc;
+	flag_signal_many_kernel<<<1, 32, 0, (cudaStream_t)cuda_stream>>>(list, count, value);
 	return cudaGetLastError() == cudaSuccess ? 0 : RTLSDR_GPU_ERR_CUDA;
 }
 

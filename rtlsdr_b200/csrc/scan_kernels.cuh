@@ -2649,6 +2649,25 @@ __global__ void flag_signal_kernel(unsigned *flag, unsigned value)
 #endif
 }
 
+/* the same for up to 32 flags at different addresses (rank 0 raising "interval consumed" in every rank's memory) */
+constexpr int kFlagSignalMax = 32;
+struct FlagList {
+	unsigned *flag[kFlagSignalMax];
+};
+
+__global__ void flag_signal_many_kernel(const FlagList list, int count, unsigned value)
+{
+	const int i = threadIdx.x;
+	if (i >= count)
+		return;
+#ifdef SCAN_EMU
+	*list.flag[i] = value;
+#else
+	__threadfence_system();
+	asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(list.flag[i]), "r"(value) : "memory");
+#endif
+}
+
 /* thread i waits until flags[i] - value >= 0 (wrap-safe); gives up after about `timeout_ns` and reports it */
 __global__ void flag_wait_kernel(const unsigned *flags, int count, unsigned value, unsigned long long timeout_ns,
 				 unsigned *timed_out)

@@ -49,6 +49,7 @@ def load_library():
     L.rtlsdr_gpu_scan_submit_device.argtypes = [vp, i, i, i, vp, i64, i64]
     L.rtlsdr_gpu_scan_submit_reads.argtypes = [vp, i, vp, vp, i64]
     L.rtlsdr_gpu_scan_flag_signal.argtypes = [vp, vp, ctypes.c_uint32]
+    L.rtlsdr_gpu_scan_flag_signal_many.argtypes = [vp, vp, i, ctypes.c_uint32]
     L.rtlsdr_gpu_scan_flag_wait.argtypes = [vp, vp, i, ctypes.c_uint32, ctypes.c_uint32, vp]
     L.rtlsdr_gpu_scan_flush.argtypes = [vp]
     L.rtlsdr_gpu_scan_sync.argtypes = [vp]
@@ -98,6 +99,14 @@ def flag_signal(cuda_stream, dev_flag, value):
     rc = load_library().rtlsdr_gpu_scan_flag_signal(cuda_stream, dev_flag, value & 0xFFFFFFFF)
     if rc:
         raise ScanError(rc, "flag_signal")
+
+
+def flag_signal_many(cuda_stream, dev_flag_addrs, value):
+    """one launch raising the flags at all the given device addresses (<= 32)"""
+    arr = (ctypes.c_void_p * len(dev_flag_addrs))(*dev_flag_addrs)
+    rc = load_library().rtlsdr_gpu_scan_flag_signal_many(cuda_stream, arr, len(dev_flag_addrs), value & 0xFFFFFFFF)
+    if rc:
+        raise ScanError(rc, "flag_signal_many")
 
 
 def flag_wait(cuda_stream, dev_flags, count, value, timeout_ms=0, dev_timed_out=None):

@@ -253,7 +253,7 @@ class SpectrumGather:
             return
         stream = stream or torch.cuda.current_stream()
         if self.mode == "peer" and self.world > 1:
-            from .scan import flag_signal, flag_wait
+            from .scan import flag_signal, flag_signal_many, flag_wait
             self.seq[k] += 1
             seq = self.seq[k]
             # "my slot of buffer k is complete": into rank 0's memory, behind this rank's epilogue
@@ -267,8 +267,10 @@ class SpectrumGather:
                           self._flag_addr(0, SLOTS * self.world + SLOTS))
                 if to_host:
                     self.host[k].copy_(self.recv[k], non_blocking=True)
-                for r in range(self.world):   # "interval consumed": the slot may be rewritten
-                    flag_signal(self.comm.cuda_stream, self._flag_addr(r, SLOTS * self.world + k), seq)
+                # "interval consumed" in every rank's memory (one launch): the slots may be rewritten
+                addrs = [self._flag_addr(r, SLOTS * self.world + k) for r in range(self.world)]
+                for lo in range(0, self.world, 32):
+                    flag_signal_many(self.comm.cuda_stream, addrs[lo:lo + 32], seq)
                 self.gathered[k].record(self.comm)
             self.last_exchange = self.gathered[k]
             return
