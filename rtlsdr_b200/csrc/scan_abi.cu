@@ -157,7 +157,7 @@ struct rtlsdr_gpu_scan {
 	 * RTLSDR_GPU_NO_FUSED_BOXCAR / RTLSDR_GPU_NO_HB_STREAM fall back to the staged kernels */
 	int dbg_boxcar_mode = -1;
 	int dbg_stagger_ns = 0;
-	bool dbg_no_fused_boxcar = false, dbg_no_hb_stream = false;
+	bool dbg_no_fused_boxcar = false, dbg_no_hb_stream = false, dbg_rms_warp = false;
 
 	std::string last_error;
 };
@@ -350,6 +350,15 @@ int build_desc(rtlsdr_gpu_scan *h, const std::vector<long long> &offs, const std
 	       std::vector<long long> &s_offs, std::vector<int> &s_hops, std::vector<int4> &segs)
 {
 	const int n = (int)offs.size(), tc = h->cfg.tune_count;
+	if (h->path == PATH_RMS) {
+		/* 1-bin hops: every read is reduced on its own (one atomic per read), so the reads keep their
+		 * submission order = address order; sorting them by hop would turn the resident CTAs' working window
+		 * from one contiguous stretch into 16 KiB pieces a whole sweep apart */
+		s_offs = offs;
+		s_hops = hops;
+		segs.clear();
+		return 0;
+	}
 	std::vector<int> count(tc + 1, 0);
 	for (int i = 0; i < n; i++)
 		count[hops[i] + 1]++;
@@ -912,6 +921,13 @@ int launch_batch(rtlsdr_gpu_scan *h, const uint8_t *base, const uint8_t *d_desc,
 		p.avg = h->d_avg;
 		p.samples = h->d_smp64;
 		TimedScope ts(h);
+		if (h->cfg.buf_len == kRmsCtaBytes && !h->dbg_rms_warp) {
+			/* one CTA per read, eight resident CTAs per SM */
+			const int blocks = std::max(1, std::min(n_reads, h->num_sms * 8));
+			if ((rc = launch_after_epilogue(h, rms_cta_kernel, blocks, 256, 0, p)))
+				return rc;
+			return check_launch(h, "rms_cta_kernel");
+		}
 		const int blocks = std::max(1, std::min((n_reads + 7) / 8, h->num_sms * 8));
 		if ((rc = launch_after_epilogue(h, rms_kernel, blocks, 256, 0, p)))
 			return rc;
@@ -1365,6 +1381,7 @@ int rtlsdr_gpu_scan_init(const rtlsdr_gpu_scan_cfg_t *cfg_in, rtlsdr_gpu_scan_t 
 	if (const char *f = getenv("RTLSDR_GPU_STAGGER_NS"))
 		h->dbg_stagger_ns = atoi(f);
 	h->dbg_no_hb_stream = getenv("RTLSDR_GPU_NO_HB_STREAM") != nullptr;
+	h->dbg_rms_warp = getenv("RTLSDR_GPU_RMS_WARP") != nullptr; /* 1-bin hops: warp-per-read kernel instead of CTA-per-read */
 	h->cfg.window_coefs = nullptr;
 	h->cfg.sinewave = nullptr;
 	h->N = N;

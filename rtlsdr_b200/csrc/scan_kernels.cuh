@@ -2491,6 +2491,90 @@ rms_kernel(const SCAN_GRID_CONSTANT RmsParams prm)
 	}
 }
 
+/*
+ * The same result with one CTA per read (the planner's rms reads are always 16384 bytes): 256 threads x 4 x 16 bytes
+ * = one read in flight per CTA plus the next one already requested while this one is reduced, i.e. ~1200 long
+ * sequential streams on the device instead of ~9500 warp-private ones, and one barrier per read (the per-warp
+ * partials alternate between two buffers; thread 0 finishes read e while the others already sum read e+1).
+ */
+constexpr int kRmsCtaBytes = 16384;
+
+__global__ void __launch_bounds__(256)
+rms_cta_kernel(const SCAN_GRID_CONSTANT RmsParams prm)
+{
+	__shared__ unsigned part[2][8][2];
+	const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+	int e = blockIdx.x;
+	if (e >= prm.n_reads)
+		return;
+	uint4 cur[4], nxt[4];
+	{
+		const uint8_t *src = prm.base + prm.read_off[e];
+#pragma unroll
+		for (int j = 0; j < 4; ++j)
+			cur[j] = __ldg((const uint4 *)(src + (t + 256 * j) * 16));
+	}
+	int par = 0;
+	bool waited = false;
+	for (; e < prm.n_reads; e += gridDim.x) {
+		const int en = e + gridDim.x;
+		if (en < prm.n_reads) {
+			const uint8_t *src = prm.base + prm.read_off[en];
+#pragma unroll
+			for (int j = 0; j < 4; ++j)
+				nxt[j] = __ldg((const uint4 *)(src + (t + 256 * j) * 16));
+		}
+		unsigned sb = 0, sbb = 0; /* per warp <= 2048 bytes: 2048 * 255^2 fits */
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			sb = __dp4a(cur[j].x, 0x01010101u, sb); sbb = __dp4a(cur[j].x, cur[j].x, sbb);
+			sb = __dp4a(cur[j].y, 0x01010101u, sb); sbb = __dp4a(cur[j].y, cur[j].y, sbb);
+			sb = __dp4a(cur[j].z, 0x01010101u, sb); sbb = __dp4a(cur[j].z, cur[j].z, sbb);
+			sb = __dp4a(cur[j].w, 0x01010101u, sb); sbb = __dp4a(cur[j].w, cur[j].w, sbb);
+		}
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			sb += __shfl_xor_sync(0xffffffffu, sb, o);
+			sbb += __shfl_xor_sync(0xffffffffu, sbb, o);
+		}
+		if (lane == 0) {
+			part[par][w][0] = sb;
+			part[par][w][1] = sbb;
+		}
+		__syncthreads();
+		if (t == 0) {
+			long long tb = 0, tbb = 0;
+#pragma unroll
+			for (int k = 0; k < 8; ++k) {
+				tb += part[par][k][0];
+				tbb += part[par][k][1];
+			}
+			/* s = b - 127:  sum s = sum b - 127 n,  sum s^2 = sum b^2 - 254 sum b + 127^2 n */
+			const long long n = kRmsCtaBytes;
+			const long long ts = tb - 127 * n;
+			long long p = tbb - 254 * tb + 16129 * n;
+			/* same IEEE double operations, in the reference's order, no FMA contraction (rtl_power.c:410-436) */
+			const double dn = (double)kRmsCtaBytes;
+			const double dc = __ddiv_rn((double)ts, dn);
+			const double err = __dsub_rn(__dmul_rn((double)(ts * 2), dc), __dmul_rn(__dmul_rn(dc, dc), dn));
+			p -= (long long)round(err);
+			if (!waited)
+				pdl_wait(); /* the accumulators may still be read by the previous interval's report epilogue */
+			waited = true;
+			atomicAdd((unsigned long long *)(prm.samples + prm.hop_of[e]), 1ull);
+			long long *dst = prm.avg + prm.hop_of[e];
+			if (prm.peak)
+				atomicMax(dst, p);
+			else
+				atomicAdd((unsigned long long *)dst, (unsigned long long)p);
+		}
+		par ^= 1;
+#pragma unroll
+		for (int j = 0; j < 4; ++j)
+			cur[j] = nxt[j];
+	}
+}
+
 /* ======================================================================== *
  *  Soft-AGC byte statistics (src/librtlsdr.c:3288-3306), optional            *
  * ======================================================================== */

@@ -252,7 +252,7 @@ SCAN_DEV int tile_idx(int p) { return p + (p >> 4) + 2 * (p >> 8); }
 constexpr int kLargeSmemB = (kWS + kWS / 16 + 2 * (kWS / 256) + 16) * 4;
 
 template <int LB, bool LAST, bool PEAK>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 2) /* (3 CTAs per SM at 80 registers: measured 103 vs 105 G samples/s) */
 large_round_b_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
 {
 	SCAN_DYN_SMEM(smem);

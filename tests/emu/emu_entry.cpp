@@ -272,6 +272,9 @@ void emu_small_decim(int L, int peak, const uint8_t *reads, int n_reads, int buf
 	run_small(L, p, peak, 1);
 }
 
+static int g_emu_rms_warp = 0;
+void emu_set_rms_warp(int v) { g_emu_rms_warp = v; }
+
 void emu_rms(const uint8_t *reads, int n_reads, int buf_len, const int *hop_of, int peak, long long *avg)
 {
 	std::vector<long long> offs(n_reads);
@@ -287,7 +290,10 @@ void emu_rms(const uint8_t *reads, int n_reads, int buf_len, const int *hop_of, 
 	p.peak = peak;
 	p.avg = avg;
 	p.samples = smp.data();
-	cuda_emu::launch(dim3((n_reads + 7) / 8 > 2 ? 2 : 1), dim3(256), 0, [&]() { rms_kernel(p); });
+	if (buf_len == kRmsCtaBytes && !g_emu_rms_warp)
+		cuda_emu::launch(dim3(n_reads > 3 ? 3 : 1), dim3(256), 0, [&]() { rms_cta_kernel(p); });
+	else
+		cuda_emu::launch(dim3((n_reads + 7) / 8 > 2 ? 2 : 1), dim3(256), 0, [&]() { rms_kernel(p); });
 }
 
 void emu_epilogue(const long long *avg, const int *samples, double *db, int bin_e, int i1, int i2, int rate, int hops)

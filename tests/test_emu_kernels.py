@@ -156,9 +156,12 @@ def test_rms_and_epilogue_kernels(emu, port_oracle):
         plan = plan_dict(0, tune_count=3, peak_hold=peak, rate=1000000)
         reads, hops = make_reads(port_oracle.lib, plan, 3, SYNTH_BIASED, seed=1, param=50)
         want, smp, db = expected(port_oracle, plan, np.zeros(1, np.int32), reads, hops)
-        avg = np.zeros(3, dtype=np.int64)
-        emu.emu_rms(vp(reads), len(reads), 16384, vp(hops.astype(np.int32)), peak, vp(avg))
-        assert np.array_equal(avg, want[:, 0])
+        for warp_kernel in (0, 1):          # CTA-per-read (default for 16384-byte reads) and warp-per-read kernels
+            emu.emu_set_rms_warp(warp_kernel)
+            avg = np.zeros(3, dtype=np.int64)
+            emu.emu_rms(vp(reads), len(reads), 16384, vp(hops.astype(np.int32)), peak, vp(avg))
+            assert np.array_equal(avg, want[:, 0]), warp_kernel
+        emu.emu_set_rms_warp(0)
         out = np.zeros((3, 2), dtype=np.float64)
         emu.emu_epilogue(vp(avg), vp(smp.astype(np.int32)), vp(out), 0, 0, 0, 1000000, 3)
         assert np.allclose(out, db, rtol=1e-12)
