@@ -89,8 +89,6 @@ struct rtlsdr_gpu_scan {
 	int2 *d_tw = nullptr;
 	int2 *d_twc = nullptr;          /* small path: per-stage compact twiddles (shared-memory image) */
 	int2 *d_twb = nullptr;          /* large path: round-B twiddles re-ordered [se][plow][ilow] */
-	int2 *d_twt = nullptr;          /* two-round large path (2^13..2^17): top-stage twiddles [se][ilow][plow] */
-	uint16_t *d_wperm = nullptr;    /* two-round large path: window coefficients in position order */
 	uint16_t *d_win = nullptr;
 	double *d_db = nullptr;
 	double *d_iir = nullptr;        /* -s iir smoothing state [tune_count][db_count - 1] */
@@ -159,7 +157,7 @@ struct rtlsdr_gpu_scan {
 	 * RTLSDR_GPU_NO_FUSED_BOXCAR / RTLSDR_GPU_NO_HB_STREAM fall back to the staged kernels */
 	int dbg_boxcar_mode = -1;
 	int dbg_stagger_ns = 0;
-	bool dbg_no_fused_boxcar = false, dbg_no_hb_stream = false, dbg_rms_warp = false, dbg_large3 = false;
+	bool dbg_no_fused_boxcar = false, dbg_no_hb_stream = false, dbg_rms_warp = false;
 
 	std::string last_error;
 };
@@ -1168,8 +1166,6 @@ void free_all(rtlsdr_gpu_scan *h)
 	cudaFree(h->d_level);
 	cudaFree(h->d_done);
 	cudaFree(h->d_twb);
-	cudaFree(h->d_twt);
-	cudaFree(h->d_wperm);
 	cudaFree(h->d_twc);
 	cudaFree(h->d_win);
 	cudaFree(h->d_db);
@@ -1385,7 +1381,6 @@ int rtlsdr_gpu_scan_init(const rtlsdr_gpu_scan_cfg_t *cfg_in, rtlsdr_gpu_scan_t 
 	if (const char *f = getenv("RTLSDR_GPU_STAGGER_NS"))
 		h->dbg_stagger_ns = atoi(f);
 	h->dbg_no_hb_stream = getenv("RTLSDR_GPU_NO_HB_STREAM") != nullptr;
-	h->dbg_large3 = getenv("RTLSDR_GPU_LARGE_3ROUND") != nullptr; /* 2^13..2^17 bins: round 1's three-round path */
 	h->dbg_rms_warp = getenv("RTLSDR_GPU_RMS_WARP") != nullptr; /* 1-bin hops: warp-per-read kernel instead of CTA-per-read */
 	h->cfg.window_coefs = nullptr;
 	h->cfg.sinewave = nullptr;
@@ -1555,38 +1550,6 @@ int rtlsdr_gpu_scan_init(const rtlsdr_gpu_scan_cfg_t *cfg_in, rtlsdr_gpu_scan_t 
 				break;
 			}
 			if (cudaMemcpy(h->d_twb, twb.data(), twb.size() * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess)
-				break;
-		}
-		if (h->path == PATH_LARGE && cfg->bin_e <= 17 && !h->dbg_large3) {
-			/* two-round path: stages 4..11 compact (like the small path, taken from the 2^L table), top stages
-			 * [se][ilow][plow], window coefficients in position order */
-			const int L = cfg->bin_e, lt = L - 12;
-			std::vector<int2> twc((size_t)kWS - 16);
-			for (int st = 4; st < 12; st++)
-				for (int m = 0; m < (1 << st); m++)
-					twc[(size_t)(1 << st) - 16 + m] = h->tw_host[(size_t)m << (L - 1 - st)];
-			std::vector<int2> twt((size_t)4096 * ((1 << lt) - 1));
-			for (int se = 0; se < lt; se++)
-				for (int ilow = 0; ilow < (1 << se); ilow++)
-					for (int plow = 0; plow < 4096; plow++)
-						twt[(size_t)4096 * ((1 << se) - 1) + ((size_t)ilow << 12) + plow] =
-							h->tw_host[((size_t)(ilow << 12) | plow) << (L - 13 - se)];
-			std::vector<uint16_t> wperm((size_t)N);
-			for (int pidx = 0; pidx < N; pidx++) {
-				unsigned n = 0;
-				for (int b = 0; b < L; b++)
-					n |= ((pidx >> b) & 1u) << (L - 1 - b);
-				wperm[pidx] = (uint16_t)((cfg->window_coefs ? cfg->window_coefs[n] : 256) & 0xFFFF);
-			}
-			if (cudaMalloc(&h->d_twc, twc.size() * sizeof(int2)) != cudaSuccess ||
-			    cudaMalloc(&h->d_twt, twt.size() * sizeof(int2)) != cudaSuccess ||
-			    cudaMalloc(&h->d_wperm, wperm.size() * sizeof(uint16_t)) != cudaSuccess) {
-				rc = RTLSDR_GPU_ERR_NOMEM;
-				break;
-			}
-			if (cudaMemcpy(h->d_twc, twc.data(), twc.size() * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess ||
-			    cudaMemcpy(h->d_twt, twt.data(), twt.size() * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess ||
-			    cudaMemcpy(h->d_wperm, wperm.data(), wperm.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess)
 				break;
 		}
 

@@ -382,392 +382,4 @@ large_round_c_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
 	}
 }
 
-
-/* ======================================================================== *
- *  Two-round path for 2^13 .. 2^17 bins (round 2)                           *
- * ======================================================================== */
-
-/*
- * The three-round path above spends ~215 instructions per sample at 2^17 bins where the stages themselves need
- * 17 x 8: every round pays a load / transpose / store of its own, and rounds A and B are one-tile CTAs with
- * nothing in flight while they transform.  Here the stages are cut 12 + (L - 12):
- *
- *   permute   (memory bound)  u8 -> packed int16 (minus 127, rtl_power.c:666-668) written at its bit-reversed
- *                             position (fix_fft's permutation, :282-297) as a tile transpose with 32/64-byte
- *                             runs on both sides; also the byte sums remove_dc needs (:586-588) -- no separate
- *                             pass over the input
- *   mid       stages 0..11    persistent CTAs, equal runs of 4096-position tiles (16 KiB, contiguous), the next
- *                             tile in flight (cp.async) while this one is transformed with the register-blocked
- *                             engine of scan_kernels.cuh; DC + window applied on the way in (window table stored
- *                             in position order), result written back in place
- *   top       stages 12..L-1  tile = 2^(L-12) rows 4096 apart x (4096 >> (L-12)) consecutive columns; a CTA keeps
- *                             its tile's twiddles in shared memory and walks several reads, |X|^2 accumulated in
- *                             registers (rtl_power.c:708-716), one coalesced 64-bit RED per bin and hop
- * Rounding, halving, twiddles and int16 wrap are those of butterfly() at every stage.
- */
-struct Large2Params {
-	const uint8_t *base;        /* u8 reads or decimated c16 images */
-	const long long *read_off;  /* byte offset per entry, NULL = regular */
-	long long regular_stride;
-	int entry_base;
-	const int *hop_of;
-	c16 *scratch;               /* [chunk][N], position order */
-	long long *sums;            /* [chunk][2] byte sums (u8) / sample sums (c16), zeroed by the host for u8 */
-	long long *avg;
-	long long *samples;
-	int samples_per_read;
-	const uint16_t *wperm;      /* [N] window coefficients in POSITION order: wperm[p] = win[bitrev_L(p)] */
-	const int2 *twc12;          /* stages 4..11, group m of stage s at (1<<s)-16+m = tw[m << (L-1-s)] */
-	const int2 *twt;            /* top stages: stage 12+se, [ilow < 2^se][plow < 4096] at 4096*((1<<se)-1) + (ilow<<12) + plow */
-	int L;
-	int n_entries;
-	int top_reads;              /* reads one CTA of the top kernel walks */
-	int in16;                   /* input is a decimated c16 image (sums come from the decimators) */
-	PassTw tw0;
-};
-
-SCAN_DEV long long large2_entry_offset(const Large2Params &prm, int e)
-{
-	return prm.read_off ? prm.read_off[e] : (long long)(e - prm.entry_base) * prm.regular_stride;
-}
-
-/* ---- permute ----------------------------------------------------------- */
-
-constexpr int kLarge2SmemPermute = kXchWords * 4;
-
-template <bool IN16>
-__global__ void __launch_bounds__(kThreads)
-large2_permute_kernel(const SCAN_GRID_CONSTANT Large2Params prm)
-{
-	SCAN_DYN_SMEM(smem);
-	c16 *stage = (c16 *)smem;
-	const int t = threadIdx.x, L = prm.L;
-	const int tile = blockIdx.x, rel = blockIdx.y, e = prm.entry_base + rel;
-	const long long N = 1ll << L;
-	const uint8_t *src = prm.base + large2_entry_offset(prm, e);
-
-	if (t == 0 && tile == 0)
-		atomicAdd((unsigned long long *)(prm.samples + prm.hop_of[e]), (unsigned long long)prm.samples_per_read);
-	/* gather: thread t owns row t = 16 consecutive input samples; park them column-major */
-	{
-		const long long n0 = ((long long)t << (L - 8)) + 16 * tile;
-		if constexpr (!IN16) {
-			const uint4 a = __ldg((const uint4 *)(src + 2 * n0));
-			const uint4 b = __ldg((const uint4 *)(src + 2 * n0 + 16));
-			const unsigned w[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
-			unsigned sI = 0, sQ = 0;
-#pragma unroll
-			for (int k = 0; k < 8; ++k) {
-				sI = __dp4a(w[k], 0x00010001u, sI);
-				sQ = __dp4a(w[k], 0x01000100u, sQ);
-			}
-#pragma unroll
-			for (int c = 0; c < 16; ++c) {
-				const unsigned raw = (w[c >> 1] >> (16 * (c & 1))) & 0xFFFFu;
-				stage[xch_idx(c * 256 + t)] = c16_pack((int)(raw & 0xFFu) - 127, (int)(raw >> 8) - 127);
-			}
-			/* byte sums of the whole read (remove_dc, rtl_power.c:586-588): one 64-bit atomic pair per warp */
-#pragma unroll
-			for (int o = 16; o > 0; o >>= 1) {
-				sI += __shfl_xor_sync(0xffffffffu, sI, o);
-				sQ += __shfl_xor_sync(0xffffffffu, sQ, o);
-			}
-			if ((t & 31) == 0) {
-				atomicAdd((unsigned long long *)(prm.sums + 2 * rel), (unsigned long long)sI);
-				atomicAdd((unsigned long long *)(prm.sums + 2 * rel + 1), (unsigned long long)sQ);
-			}
-		} else {
-#pragma unroll
-			for (int k = 0; k < 4; ++k) {
-				const uint4 a = __ldg((const uint4 *)(src + 4 * n0 + 16 * k));
-				stage[xch_idx((4 * k + 0) * 256 + t)] = a.x;
-				stage[xch_idx((4 * k + 1) * 256 + t)] = a.y;
-				stage[xch_idx((4 * k + 2) * 256 + t)] = a.z;
-				stage[xch_idx((4 * k + 3) * 256 + t)] = a.w;
-			}
-		}
-	}
-	__syncthreads();
-	/* scatter: sample (row i, column cc) of this tile has index n = (i << (L-8)) + 16*tile + cc, its position is
-	 * bitrev_L(n) = (bitrev_{L-8}(16*tile + cc) << 8) | bitrev8(i).  Register r of thread t writes column
-	 * cc = t >> 4, position low byte q = (r << 4) | (t & 15): 16 consecutive words per half warp */
-	c16 *dst = prm.scratch + (long long)rel * N;
-	const int cc = t >> 4;
-	const long long phi = (long long)brev_bits((unsigned)(16 * tile + cc), L - 8) << 8;
-#pragma unroll
-	for (int r = 0; r < kPts; ++r) {
-		const int q = (r << 4) | (t & 15);
-		const int i = brev_bits((unsigned)q, 8);
-		dst[phi | q] = stage[xch_idx(cc * 256 + i)];
-	}
-}
-
-/* ---- mid: stages 0..11 on contiguous 4096-position tiles ------------------ */
-
-struct Large2MidSmem {
-	static constexpr int slot_bytes = kWS * 4 + kWS * 2;          /* tile data + its window slice */
-	static constexpr int off_slot = 0;                            /* two slots; the current one doubles as a transpose buffer */
-	static constexpr int off_xch = 2 * slot_bytes;                /* the other transpose buffer */
-	static constexpr int off_tw = off_xch + kXchWords * 4;
-	static constexpr int off_dck = off_tw + (kWS - 16) * 8;       /* [2 items][2] DC constants */
-	static constexpr int bytes = off_dck + 32;
-};
-static_assert(Large2MidSmem::slot_bytes >= kXchWords * 4, "a slot must hold a padded transpose buffer");
-
-struct TwMid {
-	static constexpr bool kTrivial = true;
-	const int2 *tws;
-	const PassTw *tw0;
-	template <int K>
-	SCAN_DEV int2 get(int s, int pa) const
-	{
-		const int m = pa & ((1 << s) - 1);
-		if constexpr (K == 0)
-			return tw0->w[(1 << s) - 1 + m];
-		else
-			return tws[(1 << s) - 16 + m];
-	}
-};
-
-__global__ void __launch_bounds__(kThreads, 2)
-large2_mid_kernel(const SCAN_GRID_CONSTANT Large2Params prm)
-{
-	SCAN_DYN_SMEM(smem);
-	typedef Large2MidSmem SM;
-	c16 *xchb = (c16 *)(smem + SM::off_xch);
-	int2 *tws = (int2 *)(smem + SM::off_tw);
-	int *dck = (int *)(smem + SM::off_dck);
-	const int t = threadIdx.x, L = prm.L;
-	const long long N = 1ll << L;
-	const int tiles = (int)(N / kWS);
-	const long long total = (long long)prm.n_entries * tiles;
-	const long long w_lo = total * blockIdx.x / gridDim.x, w_hi = total * (blockIdx.x + 1) / gridDim.x;
-	if (w_lo >= w_hi)
-		return;
-
-	for (int i = t; i < (kWS - 16) / 2; i += kThreads)
-		cp_async16((uint8_t *)tws + 16 * i, (const uint8_t *)prm.twc12 + 16 * i);
-	TwMid tw;
-	tw.tws = tws;
-	tw.tw0 = &prm.tw0;
-
-	auto prefetch = [&](long long w, int slot) {
-		const int rel = (int)(w / tiles), tile = (int)(w - (long long)rel * tiles);
-		const uint8_t *d = (const uint8_t *)(prm.scratch + (long long)rel * N + (long long)tile * kWS);
-		const uint8_t *wv = (const uint8_t *)(prm.wperm + (long long)tile * kWS);
-		uint8_t *dst = smem + SM::off_slot + slot * SM::slot_bytes;
-#pragma unroll
-		for (int i = 0; i < kWS * 4 / (kThreads * 16); ++i)
-			cp_async16(dst + (i * kThreads + t) * 16, d + (i * kThreads + t) * 16);
-#pragma unroll
-		for (int i = 0; i < kWS * 2 / (kThreads * 16); ++i)
-			cp_async16(dst + kWS * 4 + (i * kThreads + t) * 16, wv + (i * kThreads + t) * 16);
-		cp_async_commit();
-	};
-	/* the int16 averages remove_dc subtracts (rtl_power.c:581-596: divisors 2N and 2N - 1, truncating), as seen by
-	 * the stored (b - 127) / decimated values; computed by two threads one item ahead */
-	auto dc_of = [&](long long w, int which) {
-		const int rel = (int)(w / tiles);
-		if (t < 2) {
-			const long long s = prm.sums[2 * rel + t];
-			dck[which * 2 + t] = prm.in16 ? dc_average(s, (int)(2 * N) - t) : dc_average(s - 127ll * N, (int)(2 * N) - t);
-		}
-	};
-
-	prefetch(w_lo, 0);
-	dc_of(w_lo, 0);
-	for (long long w = w_lo; w < w_hi; ++w) {
-		const int u = (int)(w - w_lo), slot = u & 1;
-		cp_async_wait_all();
-		__syncthreads(); /* slot landed (and its DC constants); the other slot is no longer read as a transpose buffer */
-		if (w + 1 < w_hi) {
-			prefetch(w + 1, slot ^ 1);
-			dc_of(w + 1, slot ^ 1);
-		}
-		const int rel = (int)(w / tiles), tile = (int)(w - (long long)rel * tiles);
-		c16 *cur = (c16 *)(smem + SM::off_slot + slot * SM::slot_bytes);
-		const uint16_t *wsl = (const uint16_t *)(cur + kWS);
-		const int kI = dck[slot * 2], kQ = dck[slot * 2 + 1];
-
-		/* thread t takes positions 16t .. 16t+15: 64 contiguous bytes of samples, 32 of coefficients */
-		X2 x[kPts];
-		{
-			const uint4 *dp = (const uint4 *)(cur + 16 * t);
-			const uint4 *wp = (const uint4 *)(wsl + 16 * t);
-			const uint4 wa = wp[0], wb = wp[1];
-			const unsigned ww[8] = { wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w };
-#pragma unroll
-			for (int k = 0; k < 4; ++k) {
-				const uint4 q = dp[k];
-				const unsigned v[4] = { q.x, q.y, q.z, q.w };
-#pragma unroll
-				for (int j = 0; j < 4; ++j) {
-					const int r = 4 * k + j;
-					const unsigned wx = (r & 1) ? (ww[r >> 1] & 0xFFFF0000u) : (ww[r >> 1] << 16);
-					x[r].re = (int)((unsigned)(c16_re(v[j]) - kI) * wx);
-					x[r].im = (int)((unsigned)(c16_im(v[j]) - kQ) * wx);
-				}
-			}
-		}
-		c16 pk[kPts];
-		run_pass<0, 12>(x, t, tw);
-		exchange_pk<0, 1, BlockBar>(x, pk, xchb, t, t, BlockBar());
-		run_pass<1, 12>(x, t, tw, pk);
-		exchange_pk<1, 2, BlockBar>(x, pk, cur, t, t, BlockBar()); /* the consumed slot is the second transpose buffer */
-		run_pass<2, 12>(x, t, tw, pk);
-
-		c16 *out = prm.scratch + (long long)rel * N + (long long)tile * kWS;
-#pragma unroll
-		for (int r = 0; r < kPts; ++r)
-			out[last_pos<12>(t, r)] = x_pack(x[r]);
-	}
-}
-
-/* ---- top: stages 12..L-1 + |X|^2 ---------------------------------------- */
-
-template <int LT>
-struct Large2TopSmem {
-	static constexpr int off_stage = 0;                             /* two 16 KiB tiles */
-	static constexpr int off_xch = 2 * kWS * 4;                     /* LT = 5 only: one transpose buffer, and (same
-	                                                                 * memory, 4096 x u64) the flush's transpose */
-	static constexpr int off_tw = off_xch + (LT > 4 ? kWS * 8 : 0);
-	static constexpr int tw_entries = ((1 << LT) - 1) * (kWS >> LT); /* stage se: [ilow][col] at ((1<<se)-1)*ncols */
-	static constexpr int bytes = off_tw + tw_entries * 8 + 16;
-};
-
-template <int LT>
-struct TwTop {
-	static constexpr bool kTrivial = false;
-	const int2 *tws;
-	/* engine position pa = (col << LT) | i; stage se pairs i and i + 2^se, twiddle group m = (i mod 2^se, plow) */
-	template <int K>
-	SCAN_DEV int2 get(int se, int pa) const
-	{
-		constexpr int ncols = kWS >> LT;
-		const int col = pa >> LT, ilow = pa & ((1 << se) - 1);
-		return tws[((1 << se) - 1) * ncols + ilow * ncols + col];
-	}
-};
-
-template <int LT, bool PEAK>
-__global__ void __launch_bounds__(kThreads, 2)
-large2_top_kernel(const SCAN_GRID_CONSTANT Large2Params prm)
-{
-	SCAN_DYN_SMEM(smem);
-	typedef Large2TopSmem<LT> SM;
-	constexpr int ncols = kWS >> LT, rows = 1 << LT;
-	c16 *xch = (c16 *)(smem + SM::off_xch);
-	int2 *tws = (int2 *)(smem + SM::off_tw);
-	const int t = threadIdx.x, L = prm.L;
-	const long long N = 1ll << L;
-	const int plow0 = blockIdx.x * ncols;
-	const int rel0 = blockIdx.y * prm.top_reads;
-	const int rel1 = (rel0 + prm.top_reads < prm.n_entries) ? rel0 + prm.top_reads : prm.n_entries;
-	if (rel0 >= rel1)
-		return;
-
-	/* this tile's twiddles, once per CTA: stage 12+se, (ilow, col) <- twt[4096*((1<<se)-1) + (ilow << 12) + plow0 + col] */
-	for (int idx = t; idx < SM::tw_entries; idx += kThreads) {
-		int se = 0, off = 0;
-		while (idx >= off + (ncols << se)) {
-			off += ncols << se;
-			se++;
-		}
-		const int ilow = (idx - off) / ncols, col = (idx - off) % ncols;
-		tws[idx] = __ldg(prm.twt + 4096ll * ((1 << se) - 1) + ((long long)ilow << 12) + plow0 + col);
-	}
-	TwTop<LT> tw;
-	tw.tws = tws;
-
-	/* tile of read `rel`: row i (0 .. 2^LT-1) = ncols consecutive words at scratch[rel][(i << 12) + plow0] */
-	auto prefetch = [&](int rel, int slot) {
-		const uint8_t *d = (const uint8_t *)(prm.scratch + (long long)rel * N + plow0);
-		uint8_t *dst = smem + SM::off_stage + slot * kWS * 4;
-		constexpr int chunks_per_row = ncols * 4 / 16;
-#pragma unroll
-		for (int k = 0; k < kWS * 4 / (kThreads * 16); ++k) {
-			const int c = k * kThreads + t;
-			const int i = c / chunks_per_row, j = c - i * chunks_per_row;
-			cp_async16(dst + ((long long)i * ncols * 4) + j * 16, d + ((long long)i << 14) + j * 16);
-		}
-		cp_async_commit();
-	};
-
-	unsigned long long acc[kPts];
-#pragma unroll
-	for (int r = 0; r < kPts; ++r)
-		acc[r] = 0ull;
-	int cur_hop = prm.hop_of[prm.entry_base + rel0];
-	bool waited = false;
-	prefetch(rel0, 0);
-	for (int rel = rel0; rel < rel1; ++rel) {
-		const int slot = (rel - rel0) & 1;
-		cp_async_wait_all();
-		__syncthreads();
-		if (rel + 1 < rel1)
-			prefetch(rel + 1, slot ^ 1);
-		const c16 *cur = (const c16 *)(smem + SM::off_stage + slot * kWS * 4);
-		/* engine position 16t + r = (col << LT) | i  ->  staged word i * ncols + col */
-		X2 x[kPts];
-#pragma unroll
-		for (int r = 0; r < kPts; ++r) {
-			const int p = 16 * t + r, col = p >> LT, i = p & (rows - 1);
-			x[r] = x_unpack(cur[i * ncols + col]);
-		}
-		run_pass<0, LT>(x, t, tw);
-		if constexpr (LT > 4) {
-			exchange<0, 1, true>(x, xch, t, t);
-			run_pass<1, LT>(x, t, tw);
-		}
-#pragma unroll
-		for (int r = 0; r < kPts; ++r)
-			accumulate_power<PEAK>(acc[r], x[r].re >> 16, x[r].im >> 16);
-
-		const int next_hop = (rel + 1 < rel1) ? prm.hop_of[prm.entry_base + rel + 1] : -1;
-		if (next_hop != cur_hop) {
-			if (!waited)
-				pdl_wait();
-			waited = true;
-			long long *out = prm.avg + ((long long)cur_hop << L) + plow0;
-			if constexpr (LT <= 4) {
-				/* one pass: register r of thread t holds (col, i) = (p >> LT, p mod 2^LT), p = 16t + r: for a
-				 * fixed r the lanes' bins are at most 2^(4-LT) words apart -> coalesced as they are */
-#pragma unroll
-				for (int r = 0; r < kPts; ++r) {
-					const int p = last_pos<LT>(t, r), col = p >> LT, i = p & (rows - 1);
-					long long *dst = out + ((long long)i << 12) + col;
-					if (PEAK)
-						atomicMax(dst, (long long)acc[r]);
-					else
-						atomicAdd((unsigned long long *)dst, acc[r]);
-					acc[r] = 0ull;
-				}
-			} else {
-				/* after the second pass the lanes of a warp hold rows 4096 bins apart: transpose the sums through
-				 * shared memory (the transpose buffer, idle here) so that a warp's atomics cover 32 consecutive bins */
-				unsigned long long *fb = (unsigned long long *)(smem + SM::off_xch);
-				__syncthreads();
-#pragma unroll
-				for (int r = 0; r < kPts; ++r) {
-					const int p = last_pos<LT>(t, r), col = p >> LT, i = p & (rows - 1);
-					fb[i * ncols + col] = acc[r];
-					acc[r] = 0ull;
-				}
-				__syncthreads();
-#pragma unroll
-				for (int k = 0; k < kPts; ++k) {
-					const int idx = t + kThreads * k, i = idx / ncols, col = idx - i * ncols;
-					long long *dst = out + ((long long)i << 12) + col;
-					if (PEAK)
-						atomicMax(dst, (long long)fb[idx]);
-					else
-						atomicAdd((unsigned long long *)dst, fb[idx]);
-				}
-				/* (the next transpose into this buffer starts with a barrier: exchange<0, 1, true>) */
-			}
-			cur_hop = next_hop;
-		}
-	}
-}
-
 } // namespace rscan

@@ -53,127 +53,12 @@ int launch_round_c(rtlsdr_gpu_scan *h, const LargeParams &p, dim3 grid, int lc)
 	}
 }
 
-/* reads one CTA of the top kernel walks: the grid (tiles x groups of R reads) should be a whole number of resident waves */
-int large2_top_reads(const rtlsdr_gpu_scan *h, int cnt, int tiles)
-{
-	const int slots = h->num_sms * h->ctas_per_sm;
-	int best_r = 1;
-	long long best_cost = -1;
-	for (int r = 1; r <= 32; r++) {
-		const long long ctas = (long long)tiles * ((cnt + r - 1) / r);
-		const long long cost = ((ctas + slots - 1) / slots) * r;
-		if (best_cost < 0 || cost < best_cost || (cost == best_cost && r > best_r)) {
-			best_cost = cost;
-			best_r = r;
-		}
-	}
-	return best_r;
-}
-
-template <int LT>
-int launch_large2_top_t(rtlsdr_gpu_scan *h, const Large2Params &p, dim3 grid)
-{
-	const int smem = Large2TopSmem<LT>::bytes;
-	if (h->cfg.peak_hold) {
-		auto k = large2_top_kernel<LT, true>;
-		CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-		k<<<grid, kThreads, smem, h->stream>>>(p);
-	} else {
-		auto k = large2_top_kernel<LT, false>;
-		CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-		k<<<grid, kThreads, smem, h->stream>>>(p);
-	}
-	return check_launch(h, "large2_top_kernel");
-}
-
-/* 2^13 .. 2^17 bins: permute (+ byte sums) -> stages 0..11 -> stages 12..L-1 + |X|^2 (scan_large.cuh, second half) */
-int large2_process(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_offs, const int *d_hops, int n_reads)
-{
-	const int L = h->cfg.bin_e;
-	const size_t N = (size_t)1 << L;
-	const bool decim = (h->cfg.boxcar && h->cfg.downsample > 1) || h->cfg.downsample_passes > 0;
-	const size_t per = N * 4 + 16 + (decim ? DecimScratch::per_entry(h) : 0);
-	const size_t extra = decim ? DecimScratch::slack() + 512 : 512;
-	const int chunk_max = (int)std::max<size_t>(1, kScratchBudget / per);
-	const int tiles = (int)(N / kWS);
-	int rc;
-	for (int e0 = 0; e0 < n_reads; e0 += chunk_max) {
-		const int cnt = std::min(chunk_max, n_reads - e0);
-		if ((rc = ensure_scratch(h, per * (size_t)cnt + extra)))
-			return rc;
-		uint8_t *sp = h->d_scratch;
-		c16 *data = (c16 *)sp;
-		sp += (size_t)cnt * N * 4;
-		long long *sums = (long long *)sp;
-		sp += (size_t)cnt * 16;
-
-		Large2Params p;
-		memset(&p, 0, sizeof(p));
-		p.entry_base = e0;
-		p.hop_of = d_hops;
-		p.scratch = data;
-		p.sums = sums;
-		p.avg = h->d_avg;
-		p.samples = h->d_smp64;
-		p.samples_per_read = h->samples_per_read;
-		p.wperm = h->d_wperm;
-		p.twc12 = h->d_twc;
-		p.twt = h->d_twt;
-		p.L = L;
-		p.n_entries = cnt;
-		p.tw0 = h->tw0;
-		p.in16 = decim ? 1 : 0;
-
-		dim3 grid_tiles((unsigned)tiles, (unsigned)cnt);
-		if (!decim) {
-			CU(cudaMemsetAsync(sums, 0, (size_t)cnt * 16, h->stream));
-			p.base = base;
-			p.read_off = d_offs;
-			large2_permute_kernel<false><<<grid_tiles, kThreads, kLarge2SmemPermute, h->stream>>>(p);
-		} else {
-			DecimScratch sc(h, cnt, (uint8_t *)(((uintptr_t)sp + 255) & ~(uintptr_t)255));
-			if ((rc = run_decimators(h, base, d_offs + e0, cnt, sc)))
-				return rc;
-			CU(cudaMemcpyAsync(sums, sc.sums, (size_t)cnt * 16, cudaMemcpyDeviceToDevice, h->stream));
-			p.base = (const uint8_t *)sc.img;
-			p.read_off = nullptr;
-			p.regular_stride = h->image_stride * 4;
-			large2_permute_kernel<true><<<grid_tiles, kThreads, kLarge2SmemPermute, h->stream>>>(p);
-		}
-		if ((rc = check_launch(h, "large2_permute_kernel")))
-			return rc;
-
-		const int smem_mid = Large2MidSmem::bytes;
-		CU(cudaFuncSetAttribute(large2_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_mid));
-		const int grid_mid = (int)std::min<long long>((long long)cnt * tiles, (long long)h->num_sms * h->ctas_per_sm);
-		large2_mid_kernel<<<grid_mid, kThreads, smem_mid, h->stream>>>(p);
-		if ((rc = check_launch(h, "large2_mid_kernel")))
-			return rc;
-
-		const int lt = L - 12;
-		p.top_reads = large2_top_reads(h, cnt, tiles);
-		dim3 grid_top((unsigned)tiles, (unsigned)((cnt + p.top_reads - 1) / p.top_reads));
-		switch (lt) {
-		case 1: rc = launch_large2_top_t<1>(h, p, grid_top); break;
-		case 2: rc = launch_large2_top_t<2>(h, p, grid_top); break;
-		case 3: rc = launch_large2_top_t<3>(h, p, grid_top); break;
-		case 4: rc = launch_large2_top_t<4>(h, p, grid_top); break;
-		default: rc = launch_large2_top_t<5>(h, p, grid_top); break;
-		}
-		if (rc)
-			return rc;
-	}
-	return 0;
-}
-
 /*
  * Entries [0, n_reads) of the (hop-sorted) batch, `chunk` at a time.
  * Scratch per chunk: [data chunk x N c16][sums chunk x 2 int64][decimation scratch].
  */
 int large_process(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_offs, const int *d_hops, int n_reads)
 {
-	if (h->cfg.bin_e <= 17 && h->d_twt)
-		return large2_process(h, base, d_offs, d_hops, n_reads); /* two-round path */
 	const int L = h->cfg.bin_e;
 	const size_t N = (size_t)1 << L;
 	const bool decim = (h->cfg.boxcar && h->cfg.downsample > 1) || h->cfg.downsample_passes > 0;

@@ -145,13 +145,9 @@ def test_large_kernels(emu, port_oracle, bin_e, peak):
     sreads, shops, _ = sort_by_hop(reads, hops, 2)
     tw = twiddles(port_oracle.sine_table(bin_e), bin_e)
     w16 = (win & 0xFFFF).astype(np.uint16)
-    # 2^13..2^17 bins: the two-round path (permute -> stages 0..11 -> top stages) and round 1's three-round path
-    for three_round in ((0, 1) if bin_e <= 17 else (1,)):
-        emu.emu_set_large3(three_round)
-        avg = np.zeros((2, n), dtype=np.int64)
-        emu.emu_large(bin_e, peak, 0, vp(sreads), len(sreads), vp(shops.astype(np.int32)), vp(tw), vp(w16), None, vp(avg))
-        assert np.array_equal(avg, want), three_round
-    emu.emu_set_large3(0)
+    avg = np.zeros((2, n), dtype=np.int64)
+    emu.emu_large(bin_e, peak, 0, vp(sreads), len(sreads), vp(shops.astype(np.int32)), vp(tw), vp(w16), None, vp(avg))
+    assert np.array_equal(avg, want)
 
 
 def test_rms_and_epilogue_kernels(emu, port_oracle):
