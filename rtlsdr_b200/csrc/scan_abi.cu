@@ -126,6 +126,8 @@ struct rtlsdr_gpu_scan {
 	 * transform of chunk k on two auxiliary streams */
 	cudaStream_t aux[2] = { nullptr, nullptr };
 	cudaEvent_t fork_ev = nullptr, join_ev[2] = { nullptr, nullptr };
+	cudaStream_t hb_head_stream = nullptr;  /* -F chain: head tiles beside the streaming kernel */
+	cudaEvent_t hb_fork = nullptr, hb_join = nullptr;
 	cudaStream_t copy_stream = nullptr;
 	cudaEvent_t bulk_free = nullptr;   /* last kernel that reads d_bulk has finished */
 	bool bulk_used = false;
@@ -785,9 +787,26 @@ int run_decimators(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_o
 		CU(cudaFuncSetAttribute(halfband_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 		CU(cudaMemsetAsync(sc.sums, 0, (size_t)n * 16, h->stream));
 		dim3 grid(stream ? 1 : (M + tile - 1) / tile, n);
-		halfband_chain_kernel<<<grid, stream ? 64 : 256, smem, h->stream>>>(p);
+		/* With the streaming kernel the tile kernel only computes the eased-in heads (final samples 0..15 of
+		 * every read): small latency-bound CTAs that write other words than the streaming kernel and share
+		 * only the atomically updated DC sums -- they run beside it on a stream of their own instead of in
+		 * front of it (19 us of a 200 us step at -F 9, ds = 16). */
+		cudaStream_t head_stream = h->stream;
+		if (stream) {
+			if (!h->hb_head_stream) {
+				CU(cudaStreamCreateWithFlags(&h->hb_head_stream, cudaStreamNonBlocking));
+				CU(cudaEventCreateWithFlags(&h->hb_fork, cudaEventDisableTiming));
+				CU(cudaEventCreateWithFlags(&h->hb_join, cudaEventDisableTiming));
+			}
+			head_stream = h->hb_head_stream;
+			CU(cudaEventRecord(h->hb_fork, h->stream)); /* behind the memset of the sums and whatever produced the input */
+			CU(cudaStreamWaitEvent(head_stream, h->hb_fork, 0));
+		}
+		halfband_chain_kernel<<<grid, stream ? 64 : 256, smem, head_stream>>>(p);
 		if ((rc = check_launch(h, "halfband_chain_kernel")))
 			return rc;
+		if (stream)
+			CU(cudaEventRecord(h->hb_join, head_stream));
 		if (stream) {
 			HalfbandStreamParams q;
 			q.base = base;
@@ -817,6 +836,7 @@ int run_decimators(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_o
 			}
 			if ((rc = check_launch(h, "halfband_stream_kernel")))
 				return rc;
+			CU(cudaStreamWaitEvent(h->stream, h->hb_join, 0)); /* heads done before the DC constants / the transform */
 		}
 	} else {
 		const int passes = h->cfg.downsample_passes;
@@ -1183,6 +1203,12 @@ void free_all(rtlsdr_gpu_scan *h)
 	}
 	if (h->fork_ev)
 		cudaEventDestroy(h->fork_ev);
+	if (h->hb_head_stream)
+		cudaStreamDestroy(h->hb_head_stream);
+	if (h->hb_fork)
+		cudaEventDestroy(h->hb_fork);
+	if (h->hb_join)
+		cudaEventDestroy(h->hb_join);
 	if (h->copy_stream)
 		cudaStreamDestroy(h->copy_stream);
 	if (h->bulk_free)
