@@ -35,6 +35,17 @@ SCAN_DEV void cp_async16(void *smem_dst, const void *gmem_src)
 #endif
 }
 
+/* 8-byte form (LDGSTS.64): destinations that are only 8-byte aligned (swizzled tile rows of the large path) */
+SCAN_DEV void cp_async8(void *smem_dst, const void *gmem_src)
+{
+#ifdef SCAN_EMU
+	::cuda_emu::copy8(smem_dst, gmem_src);
+#else
+	unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem_src) : "memory");
+#endif
+}
+
 SCAN_DEV void cp_async_commit()
 {
 #ifndef SCAN_EMU

@@ -42,6 +42,8 @@ struct LargeParams {
 	const uint16_t *win;        /* [N] */
 	int L;
 	int n_entries;              /* entries in this chunk */
+	int c_reads;                /* reads per CTA of round C (round_c_reads) */
+	int tiles_log2;             /* pipelined rounds: log2 of the 4096-sample tiles per read (L - 12) */
 	PassTw tw0;
 };
 
@@ -304,82 +306,269 @@ large_round_b_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
 	}
 }
 
+/*
+ * Round B (stages 8..15, not the last round), software pipelined, items in TILE-MAJOR order
+ * (all reads of one tile, then the next tile): a resident grid of CTAs walks equal runs of the (tile, read)
+ * items like scan_small_kernel walks reads.  A tile is 256 strided rows x 16 consecutive positions and stays in
+ * the scratch's own row-major order in shared memory, so the next one arrives by 8-byte cp.async while this one
+ * is transformed, and the result leaves with 16-byte loads / stores.  Word (row i, column c) lives at
+ *     272 * (i >> 4) + 16 * (i & 15) + (c ^ 2 * (((i >> 1) ^ (i >> 5)) & 7))
+ * (16 pad words per 16 rows + an XOR on column bits 1..3): the engine reads register r of thread t at row
+ * 16 * (t & 15) + r, column t >> 4 and writes it back at row 16 * r + (t & 15) -- both patterns touch 32
+ * different banks per warp, and column pairs stay adjacent and 8-byte aligned.
+ * The twiddles of a tile depend on its 16 columns only, not on the read: in tile-major order a CTA's whole run
+ * uses one or two sets, kept in shared memory (the 16 x 240 values of stages 12..15 are contiguous in the
+ * host's re-ordered table twb[se][plow][ilow], those of stages 8..11 are 16 x 15 gathered values).  The
+ * one-tile-per-CTA kernel fetches 30 twiddles per thread and tile through L1/L2 (61 KB requested per 16 KB
+ * tile; ncu: 0.93 long-scoreboard stall cycles per issued instruction).
+ */
+constexpr int kTileRowWords = 4352; /* 16 row groups x 272 words */
+constexpr int kTwsWords = (16 * 240 + 16 * 15 + 16) * 2; /* int2 tables of one tile */
+constexpr int kLargeSmemBP = kTileRowWords * 4 * 2 + kXchWords * 4 + kTwsWords * 4;
+
+SCAN_DEV int tile_row_swz(int i) { return 2 * (((i >> 1) ^ (i >> 5)) & 7); }
+SCAN_DEV int tile_row_base(int i) { return 272 * (i >> 4) + 16 * (i & 15); }
+
+struct TwLargeBS {
+	static constexpr bool kTrivial = false;
+	const int2 *t1; /* [se = 4..7][col][ilow]: stage se at 16 * ((1 << se) - 16) */
+	const int2 *t0; /* [col][15]: stage se < 4, group g at (1 << se) - 1 + g */
+	template <int K>
+	SCAN_DEV int2 get(int se, int pa) const
+	{
+		const int col = pa >> 8, ilow = pa & ((1 << se) - 1);
+		if (K >= 1)
+			return t1[16 * ((1 << se) - 16) + (col << se) + ilow];
+		return t0[col * 15 + (1 << se) - 1 + ilow];
+	}
+};
+
+__global__ void __launch_bounds__(kThreads, 2)
+large_round_b_pipe_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
+{
+	constexpr int LB = 8;
+	SCAN_DYN_SMEM(smem);
+	c16 *in = (c16 *)smem;                 /* two tiles */
+	c16 *xch = in + 2 * kTileRowWords;
+	int2 *tws1 = (int2 *)(xch + kXchWords);
+	int2 *tws0 = tws1 + 16 * 240;
+	const int t = threadIdx.x, L = prm.L;
+	const long long N = 1ll << L;
+	const int n_rel = prm.n_entries;
+	const long long W = (long long)n_rel << prm.tiles_log2;
+	const long long w0 = W * blockIdx.x / gridDim.x, w1 = W * (blockIdx.x + 1) / gridDim.x;
+	if (w0 >= w1)
+		return;
+	/* item w = tile * n_rel + rel */
+	int tile = (int)(w0 / n_rel), rel = (int)(w0 - (long long)tile * n_rel);
+
+	auto tile_ptr = [&](int tl, int rl) {
+		return prm.scratch + (long long)rl * N + ((long long)(tl >> 4) << (8 + LB)) + (tl & 15) * 16;
+	};
+	auto prefetch = [&](int tl, int rl, int buf) {
+		const c16 *data = tile_ptr(tl, rl);
+		c16 *dst = in + buf * kTileRowWords;
+#pragma unroll
+		for (int k = 0; k < 8; ++k) {
+			const int q = t + kThreads * k, i = q >> 3, j = q & 7;
+			cp_async8(dst + tile_row_base(i) + ((2 * j) ^ tile_row_swz(i)), data + ((long long)i << 8) + 2 * j);
+		}
+		cp_async_commit();
+	};
+	auto load_tables = [&](int tl) {
+		const int plow0 = (tl & 15) * 16;
+#pragma unroll
+		for (int se = 4; se < 8; ++se) {
+			const int2 *src = prm.twb + twb_offset(se) + ((long long)plow0 << se);
+			int2 *dst = tws1 + 16 * ((1 << se) - 16);
+			for (int k = t; k < (8 << se); k += kThreads) /* 16 << se entries, two per 16-byte copy */
+				cp_async16(dst + 2 * k, src + 2 * k);
+		}
+		if (t < 240) {
+			const int col = t / 15, e = t % 15;
+			int se = 0;
+			while (e >= (2 << se) - 1)
+				se++;
+			const long long m = ((long long)(e - ((1 << se) - 1)) << 8) | (plow0 + col);
+			tws0[t] = prm.tw[m << (L - 9 - se)];
+		}
+		cp_async_commit();
+	};
+	prefetch(tile, rel, 0);
+	int tab_tile = -1;
+	TwLargeBS tw;
+	tw.t1 = tws1;
+	tw.t0 = tws0;
+	for (long long w = w0; w < w1; ++w) {
+		const int buf = (int)(w - w0) & 1;
+		c16 *cur = in + buf * kTileRowWords;
+		c16 *data = const_cast<c16 *>(tile_ptr(tile, rel));
+		cp_async_wait_all();
+		__syncthreads(); /* tile w has landed for everybody; the other buffer's stores of item w-1 have been read */
+		int ntile = tile, nrel = rel + 1;
+		if (nrel == n_rel)
+			nrel = 0, ntile++;
+		if (w + 1 < w1)
+			prefetch(ntile, nrel, buf ^ 1);
+		if (tile != tab_tile) { /* CTA-uniform, once or twice per run: nobody reads the old tables any more */
+			tab_tile = tile;
+			load_tables(tile);
+			cp_async_wait_all();
+			__syncthreads();
+		}
+		X2 x[kPts];
+		{
+			const int col = t >> 4;
+#pragma unroll
+			for (int r = 0; r < kPts; ++r) {
+				const int i = ((t & 15) << 4) | r;
+				x[r] = x_unpack(cur[tile_row_base(i) + (col ^ tile_row_swz(i))]);
+			}
+		}
+		run_pass<0, LB>(x, t, tw);
+		exchange<0, 1, false>(x, xch, t, t);
+		run_pass<1, LB>(x, t, tw);
+		{
+			const int col = t >> 4;
+#pragma unroll
+			for (int r = 0; r < kPts; ++r) {
+				const int i = (r << 4) | (t & 15);
+				cur[tile_row_base(i) + (col ^ tile_row_swz(i))] = x_pack(x[r]);
+			}
+		}
+		__syncthreads();
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			const int q = t + kThreads * k, i = q >> 2, j = q & 3;
+			const int s = tile_row_swz(i);
+			uint4 v = *(const uint4 *)(cur + tile_row_base(i) + ((4 * j) ^ (s & 12)));
+			if (s & 2)
+				v = uint4{ v.z, v.w, v.x, v.y };
+			*(uint4 *)(data + ((long long)i << 8) + 4 * j) = v;
+		}
+		tile = ntile, rel = nrel;
+	}
+}
+
 /* ---- round C ----------------------------------------------------------- */
 
-constexpr int kRoundCReads = 16; /* reads one CTA of round C walks through */
+constexpr int kRoundCReads = 16; /* reads one CTA of round C walks through at most */
 
-template <int LC, bool PEAK>
+/* reads per CTA of round C: up to kRoundCReads (register accumulation before the atomics), fewer when the
+ * launch would otherwise not fill the GPU (at least ~4 CTAs of `cta_x` per SM) */
+inline int round_c_reads(int n_reads, int cta_x)
+{
+	const long long want = ((long long)n_reads * cta_x + 591) / 592;
+	return (int)(want < 1 ? 1 : (want > kRoundCReads ? kRoundCReads : want));
+}
+
+/*
+ * VEC consecutive positions per thread (16-byte loads for VEC = 4) and the NEXT read's words requested before
+ * the current read's butterflies: the round is a pure stream over the scratch (4 bytes per sample, one butterfly
+ * per 2^LC points and stage), so what matters is bytes in flight -- the scalar version (two 4-byte loads in
+ * flight per thread) ran at 2.3 TB/s.
+ */
+template <int LC, bool PEAK, int VEC>
 __global__ void __launch_bounds__(kThreads)
 large_round_c_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
 {
 	constexpr int R = 1 << LC;
 	constexpr bool kHoist = LC <= 3; /* twiddles depend on the position only: keep them in registers */
 	const int L = prm.L;
-	const int plow = blockIdx.x * kThreads + threadIdx.x; /* 0 .. 65535 */
+	const int plow = (blockIdx.x * kThreads + threadIdx.x) * VEC; /* 0 .. 65535 */
 	const long long N = 1ll << L;
-	int2 wreg[kHoist ? R - 1 : 1];
+	int2 wreg[kHoist ? (R - 1) * VEC : 1];
 	if constexpr (kHoist) {
 #pragma unroll
 		for (int se = 0; se < LC; ++se)
 #pragma unroll
-			for (int g = 0; g < (1 << se); ++g) {
-				const long long m = ((long long)g << 16) | plow;
-				wreg[(1 << se) - 1 + g] = __ldg(prm.tw + (m << (L - 17 - se)));
-			}
-	}
-	unsigned long long acc[R];
+			for (int g = 0; g < (1 << se); ++g)
 #pragma unroll
-	for (int r = 0; r < R; ++r)
+				for (int j = 0; j < VEC; ++j) {
+					const long long m = ((long long)g << 16) | (plow + j);
+					wreg[((1 << se) - 1 + g) * VEC + j] = __ldg(prm.tw + (m << (L - 17 - se)));
+				}
+	}
+	unsigned long long acc[R * VEC];
+#pragma unroll
+	for (int r = 0; r < R * VEC; ++r)
 		acc[r] = 0ull;
 	int cur_hop = -1;
-	const int rel0 = blockIdx.y * kRoundCReads;
-	const int rel1 = (rel0 + kRoundCReads < prm.n_entries) ? rel0 + kRoundCReads : prm.n_entries;
+	const int rel0 = blockIdx.y * prm.c_reads;
+	const int rel1 = (rel0 + prm.c_reads < prm.n_entries) ? rel0 + prm.c_reads : prm.n_entries;
+	c16 nxt[R * VEC];
+	auto fetch = [&](int rel) {
+		const c16 *data = prm.scratch + (long long)rel * N + plow;
+#pragma unroll
+		for (int r = 0; r < R; ++r) {
+			if constexpr (VEC == 4) {
+				const uint4 q = *(const uint4 *)(data + ((long long)r << 16));
+				nxt[4 * r] = q.x, nxt[4 * r + 1] = q.y, nxt[4 * r + 2] = q.z, nxt[4 * r + 3] = q.w;
+			} else if constexpr (VEC == 2) {
+				const uint2 q = *(const uint2 *)(data + ((long long)r << 16));
+				nxt[2 * r] = q.x, nxt[2 * r + 1] = q.y;
+			} else {
+				nxt[r] = data[(long long)r << 16];
+			}
+		}
+	};
+	if (rel0 < rel1)
+		fetch(rel0);
 	for (int rel = rel0; rel <= rel1; ++rel) {
 		const int hop = (rel < rel1) ? prm.hop_of[prm.entry_base + rel] : -1;
 		if (hop != cur_hop) {
 			if (cur_hop >= 0) {
 				long long *out = prm.avg + ((long long)cur_hop << L) + plow;
 #pragma unroll
-				for (int r = 0; r < R; ++r) {
-					if (PEAK)
-						atomicMax(out + ((long long)r << 16), (long long)acc[r]);
-					else
-						atomicAdd((unsigned long long *)(out + ((long long)r << 16)), acc[r]);
-					acc[r] = 0ull;
-				}
+				for (int r = 0; r < R; ++r)
+#pragma unroll
+					for (int j = 0; j < VEC; ++j) {
+						if (PEAK)
+							atomicMax(out + ((long long)r << 16) + j, (long long)acc[r * VEC + j]);
+						else
+							atomicAdd((unsigned long long *)(out + ((long long)r << 16) + j), acc[r * VEC + j]);
+						acc[r * VEC + j] = 0ull;
+					}
 			}
 			cur_hop = hop;
 		}
 		if (rel == rel1)
 			break;
-		const c16 *data = prm.scratch + (long long)rel * N + plow;
-		c16 v[R];
+		c16 v[R * VEC];
 #pragma unroll
-		for (int r = 0; r < R; ++r)
-			v[r] = data[(long long)r << 16];
+		for (int r = 0; r < R * VEC; ++r)
+			v[r] = nxt[r];
+		if (rel + 1 < rel1)
+			fetch(rel + 1);
 #pragma unroll
 		for (int se = 0; se < LC; ++se) {
 #pragma unroll
 			for (int r = 0; r < R; ++r) {
 				if ((r & (1 << se)) == 0) {
 					const int g = r & ((1 << se) - 1);
-					int2 w;
-					if constexpr (kHoist) {
-						w = wreg[(1 << se) - 1 + g];
-					} else {
-						const long long m = ((long long)g << 16) | plow;
-						w = __ldg(prm.tw + (m << (L - 17 - se)));
+#pragma unroll
+					for (int j = 0; j < VEC; ++j) {
+						int2 w;
+						if constexpr (kHoist) {
+							w = wreg[((1 << se) - 1 + g) * VEC + j];
+						} else {
+							const long long m = ((long long)g << 16) | (plow + j);
+							w = __ldg(prm.tw + (m << (L - 17 - se)));
+						}
+						butterfly(v[r * VEC + j], v[(r | (1 << se)) * VEC + j], w.x, w.y);
 					}
-					butterfly(v[r], v[r | (1 << se)], w.x, w.y);
 				}
 			}
 		}
 #pragma unroll
-		for (int r = 0; r < R; ++r) {
+		for (int r = 0; r < R * VEC; ++r) {
 			const int re = c16_re(v[r]), im = c16_im(v[r]);
 			accumulate_power<PEAK>(acc[r], re, im);
 		}
 	}
 }
+
+/* positions per thread of round C for 2^LC strided points: 16-byte loads while the accumulators fit */
+constexpr int round_c_vec(int lc) { return lc <= 2 ? 4 : (lc == 3 ? 2 : 1); }
 
 } // namespace rscan

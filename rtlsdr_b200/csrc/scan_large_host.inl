@@ -35,9 +35,9 @@ template <int LC>
 int launch_round_c_t(rtlsdr_gpu_scan *h, const LargeParams &p, dim3 grid)
 {
 	if (h->cfg.peak_hold)
-		large_round_c_kernel<LC, true><<<grid, kThreads, 0, h->stream>>>(p);
+		large_round_c_kernel<LC, true, round_c_vec(LC)><<<grid, kThreads, 0, h->stream>>>(p);
 	else
-		large_round_c_kernel<LC, false><<<grid, kThreads, 0, h->stream>>>(p);
+		large_round_c_kernel<LC, false, round_c_vec(LC)><<<grid, kThreads, 0, h->stream>>>(p);
 	return check_launch(h, "large_round_c_kernel");
 }
 
@@ -94,6 +94,9 @@ int large_process(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_of
 
 		const int smem_a = kLargeSmemA;
 		dim3 grid_tiles((unsigned)(N / kWS), (unsigned)cnt);
+		/* pipelined round B: one resident wave of CTAs, equal runs of the (tile, read) items */
+		p.tiles_log2 = L - 12;
+		const unsigned grid_pipe = (unsigned)std::min<long long>((long long)cnt << (L - 12), 2ll * h->num_sms);
 		if (!decim) {
 			CU(cudaMemsetAsync(sums, 0, (size_t)cnt * 16, h->stream));
 			DcSumU8Params d;
@@ -130,10 +133,18 @@ int large_process(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_of
 		}
 		/* (letting round B take 9-10 stages to save round C was measured slower: 32-byte runs) */
 		const int lb = std::min(8, L - 8);
-		if ((rc = launch_round_b(h, p, grid_tiles, lb, 8 + lb == L)))
+		if (8 + lb < L && h->dbg_large_pipe) {
+			auto k = large_round_b_pipe_kernel;
+			CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kLargeSmemBP));
+			k<<<grid_pipe, kThreads, kLargeSmemBP, h->stream>>>(p);
+			if ((rc = check_launch(h, "large_round_b_pipe_kernel")))
+				return rc;
+		} else if ((rc = launch_round_b(h, p, grid_tiles, lb, 8 + lb == L)))
 			return rc;
 		if (8 + lb < L) {
-			dim3 g(65536 / kThreads, (unsigned)((cnt + kRoundCReads - 1) / kRoundCReads));
+			const int cta_x = 65536 / (kThreads * round_c_vec(L - 16));
+			p.c_reads = round_c_reads(cnt, cta_x);
+			dim3 g((unsigned)cta_x, (unsigned)((cnt + p.c_reads - 1) / p.c_reads));
 			if ((rc = launch_round_c(h, p, g, L - 16)))
 				return rc;
 		}

@@ -50,6 +50,14 @@ inline void copy16(void *d, const void *s)
 	}
 	memcpy(d, s, 16);
 }
+inline void copy8(void *d, const void *s)
+{
+	if (((uintptr_t)d & 7) || ((uintptr_t)s & 7)) {
+		fprintf(stderr, "cuda_emu: cp.async 8 with a misaligned address\n");
+		abort();
+	}
+	memcpy(d, s, 8);
+}
 inline unsigned linear_tid() { return t_threadIdx.x + g_blockDim.x * (t_threadIdx.y + g_blockDim.y * t_threadIdx.z); }
 
 template <class T>

@@ -1,5 +1,8 @@
 /* large path (bin_e 13..21) through the emulator: u8 reads [n_reads][2N] -> spectra.
  * in16 != 0: `reads` are decimated c16 images [n_reads][N] and `sums_in` their DC sums. */
+static int g_large_pipe = 1;
+void emu_set_large_pipe(int v) { g_large_pipe = v; }
+
 void emu_large(int L, int peak, int in16, const uint8_t *reads, int n_reads, const int *hop_of,
 	       const int *tw, const uint16_t *win, const long long *sums_in, long long *avg)
 {
@@ -37,6 +40,8 @@ void emu_large(int L, int peak, int in16, const uint8_t *reads, int n_reads, con
 	p.n_entries = n_reads;
 	fill_tw0(p.tw0, p.tw, L);
 	dim3 tiles((unsigned)(N / kWS), n_reads);
+	p.tiles_log2 = L - 12;
+	const unsigned pipe_grid = 5; /* runs that start and end inside a read */
 	if (!in16) {
 		DcSumU8Params d;
 		d.base = reads;
@@ -65,16 +70,20 @@ void emu_large(int L, int peak, int in16, const uint8_t *reads, int n_reads, con
 	else if (lb == 9) RB(9, true);
 	else if (lb == 10) RB(10, true);
 	else if (last) RB(8, true);
+	else if (g_large_pipe)
+		cuda_emu::launch(dim3(pipe_grid), dim3(kThreads), kLargeSmemBP, [&]() { large_round_b_pipe_kernel(p); });
 	else RB(8, false);
 #undef RB
 	if (8 + lb < L) {
-		dim3 g(65536 / kThreads, (n_reads + kRoundCReads - 1) / kRoundCReads);
+		const int lc = L - 16, cta_x = 65536 / (kThreads * round_c_vec(lc));
+		p.c_reads = n_reads > 2 ? 2 : 1; /* more than one CTA row and a hop change inside a CTA's run */
+		dim3 g(cta_x, (n_reads + p.c_reads - 1) / p.c_reads);
 #define RC(LCV)                                                                                         \
 	do {                                                                                            \
 		if (peak)                                                                               \
-			cuda_emu::launch(g, dim3(kThreads), 0, [&]() { large_round_c_kernel<LCV, true>(p); }); \
+			cuda_emu::launch(g, dim3(kThreads), 0, [&]() { large_round_c_kernel<LCV, true, round_c_vec(LCV)>(p); }); \
 		else                                                                                    \
-			cuda_emu::launch(g, dim3(kThreads), 0, [&]() { large_round_c_kernel<LCV, false>(p); }); \
+			cuda_emu::launch(g, dim3(kThreads), 0, [&]() { large_round_c_kernel<LCV, false, round_c_vec(LCV)>(p); }); \
 	} while (0)
 		switch (L - 16) {
 		case 1: RC(1); break;

@@ -146,8 +146,13 @@ def test_large_kernels(emu, port_oracle, bin_e, peak):
     tw = twiddles(port_oracle.sine_table(bin_e), bin_e)
     w16 = (win & 0xFFFF).astype(np.uint16)
     avg = np.zeros((2, n), dtype=np.int64)
-    emu.emu_large(bin_e, peak, 0, vp(sreads), len(sreads), vp(shops.astype(np.int32)), vp(tw), vp(w16), None, vp(avg))
-    assert np.array_equal(avg, want)
+    # pipelined round B (the default for N >= 2^17) and the one-tile-per-CTA kernel it replaces (A/B switch)
+    for pipe in (1, 0):
+        avg[:] = 0
+        emu.emu_set_large_pipe(pipe)
+        emu.emu_large(bin_e, peak, 0, vp(sreads), len(sreads), vp(shops.astype(np.int32)), vp(tw), vp(w16), None, vp(avg))
+        assert np.array_equal(avg, want), pipe
+    emu.emu_set_large_pipe(1)
 
 
 def test_rms_and_epilogue_kernels(emu, port_oracle):
