@@ -215,6 +215,20 @@ RTLSDR_GPU_API int rtlsdr_gpu_scan_collect_all(rtlsdr_gpu_scan_t *h, int64_t *av
 RTLSDR_GPU_API int rtlsdr_gpu_scan_collect_device(rtlsdr_gpu_scan_t *h, void *dev_avg, void *dev_samples, void *dev_db);
 
 /*
+ * Reads of the SAME hops processed by several handles (e.g. one per GPU, each fed a share of the reads of a
+ * single-hop scan): fold `sets` external accumulator sets into this handle's.  Set s is what
+ * rtlsdr_gpu_scan_collect_device() wrote for a handle with the same configuration: raw bins int64
+ * [tune_count << bin_e] at dev_avg + s * set_stride and sample counts int32 [tune_count] at
+ * dev_samples + s * set_stride (bytes; 8-byte aligned).  Bins are added, or maximised under peak_hold; counts are
+ * added -- exactly what the reference's accumulation does read by read (rtl_power.c:708-717), so a following
+ * collect() of this handle returns bit-identical bins, counts and dB to ONE handle that had seen all the reads.
+ * Asynchronous on the handle's stream; the external memory may be a peer mapping of another GPU and must stay
+ * valid until the work has run.  (iir_alpha: smoothing state is only updated by this handle's own collects.)
+ */
+RTLSDR_GPU_API int rtlsdr_gpu_scan_merge_device(rtlsdr_gpu_scan_t *h, const void *dev_avg, const void *dev_samples,
+		int sets, int64_t set_stride);
+
+/*
  * Soft-AGC statistics of hop `hop` since its last collect (needs RTLSDR_GPU_FLAG_LEVEL_STATS):
  * overload = bytes equal to 0 or 255 (0 dBFS), high_level = bytes < 64 or > 191 (-6 dBFS), as
  * softagc() counts them per buffer (src/librtlsdr.c:3299-3306), bytes = bytes looked at.

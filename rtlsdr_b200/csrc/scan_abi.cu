@@ -87,7 +87,7 @@ struct rtlsdr_gpu_scan {
 	unsigned long long *d_level = nullptr; /* [tune_count][2] soft-AGC byte counts (optional) */
 	std::vector<uint64_t> level_bytes;
 	int2 *d_tw = nullptr;
-	int2 *d_twc = nullptr;          /* small path: per-stage compact twiddles (shared-memory image) */
+	int2 *d_twc = nullptr;          /* small path: per-stage compact twiddles (shared-memory image); large path: round A's */
 	int2 *d_twb = nullptr;          /* large path: round-B twiddles re-ordered [se][plow][ilow] */
 	uint16_t *d_win = nullptr;
 	double *d_db = nullptr;
@@ -145,6 +145,7 @@ struct rtlsdr_gpu_scan {
 	 * only then may the next transform kernel be launched programmatically dependent (it reads
 	 * nothing the epilogue writes before its pdl_wait) */
 	bool last_was_epilogue = false;
+	bool samples_on_device = false; /* set by merge_device(): collect() reads the counts back from d_smp64 */
 	uint64_t launches = 0, h2d = 0, d2h = 0;
 	/* timing of the transform kernels */
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
@@ -1566,6 +1567,19 @@ int rtlsdr_gpu_scan_init(const rtlsdr_gpu_scan_cfg_t *cfg_in, rtlsdr_gpu_scan_t 
 				break;
 		}
 		if (h->path == PATH_LARGE) {
+			/* round A's compact table: stage s (4..7), group m at (1<<s)-16+m = tw[m << (L-1-s)] */
+			std::vector<int2> twc(240);
+			for (int st = 4; st < 8; st++)
+				for (int m = 0; m < (1 << st); m++)
+					twc[(size_t)(1 << st) - 16 + m] = h->tw_host[(size_t)m << (cfg->bin_e - 1 - st)];
+			if (cudaMalloc(&h->d_twc, twc.size() * sizeof(int2)) != cudaSuccess) {
+				rc = RTLSDR_GPU_ERR_NOMEM;
+				break;
+			}
+			if (cudaMemcpy(h->d_twc, twc.data(), twc.size() * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess)
+				break;
+		}
+		if (h->path == PATH_LARGE) {
 			/* twb[se][plow][ilow] = tw[((ilow << 8) | plow) << (L-9-se)], se = 4 .. min(8, L-8)-1 */
 			const int L = cfg->bin_e, lb = std::min(8, L - 8);
 			std::vector<int2> twb((size_t)256 * 240, make_int2(0, 0));
@@ -1995,6 +2009,12 @@ static int collect_range(rtlsdr_gpu_scan_t *h, int hop0, int nhops, int64_t *avg
 				   cudaMemcpyDeviceToHost, h->stream));
 		h->d2h += (uint64_t)nhops * N * sizeof(long long);
 	}
+	std::vector<long long> dev_smp;
+	if (h->samples_on_device && samples) { /* after merge_device(): the counts live in d_smp64 only */
+		dev_smp.resize(nhops);
+		CU(cudaMemcpyAsync(dev_smp.data(), h->d_smp64 + hop0, (size_t)nhops * sizeof(long long), cudaMemcpyDeviceToHost,
+				   h->stream));
+	}
 	/* read-and-zero, like csv_dbm (rtl_power.c:761-764) */
 	h->last_was_epilogue = false;
 	if (nhops == h->cfg.tune_count) {
@@ -2008,11 +2028,13 @@ static int collect_range(rtlsdr_gpu_scan_t *h, int hop0, int nhops, int64_t *avg
 	CU(cudaStreamSynchronize(h->stream));
 	for (int i = 0; i < nhops; i++) {
 		if (samples)
-			samples[i] = h->samples[hop0 + i];
+			samples[i] = dev_smp.empty() ? h->samples[hop0 + i] : (int)dev_smp[i];
 		h->samples[hop0 + i] = 0;
 		if (h->d_level)
 			h->level_bytes[hop0 + i] = 0;
 	}
+	if (nhops == h->cfg.tune_count)
+		h->samples_on_device = false; /* everything is zero again: the host mirror is exact from here on */
 	return 0;
 }
 
@@ -2069,6 +2091,7 @@ int rtlsdr_gpu_scan_collect_device(rtlsdr_gpu_scan_t *h, void *dev_avg, void *de
 		if (h->report_pending[h->cur_acc]) /* the set the next submits use: its last report (two collects ago) is done */
 			CU(cudaStreamWaitEvent(main_stream, h->ev_report[h->cur_acc], 0));
 		std::fill(h->samples.begin(), h->samples.end(), 0);
+		h->samples_on_device = false;
 		return 0;
 	}
 	if ((rc = run_epilogue(h, 0, (int)tc, (double *)dev_db, (long long *)dev_avg, (int *)dev_samples, fused_zero)))
@@ -2083,7 +2106,38 @@ int rtlsdr_gpu_scan_collect_device(rtlsdr_gpu_scan_t *h, void *dev_avg, void *de
 		std::fill(h->level_bytes.begin(), h->level_bytes.end(), 0);
 	}
 	std::fill(h->samples.begin(), h->samples.end(), 0);
+	h->samples_on_device = false;
 	return 0;
+}
+
+int rtlsdr_gpu_scan_merge_device(rtlsdr_gpu_scan_t *h, const void *dev_avg, const void *dev_samples, int sets,
+				 int64_t set_stride)
+{
+	if (!h || !dev_avg || !dev_samples)
+		return RTLSDR_GPU_ERR_NULL;
+	if (sets <= 0 || (sets > 1 && set_stride <= 0))
+		return RTLSDR_GPU_ERR_CONFIG;
+	if (((uintptr_t)dev_avg & 7) || ((uintptr_t)dev_samples & 3) || (set_stride & 7))
+		return RTLSDR_GPU_ERR_ALIGN;
+	CU(cudaSetDevice(h->cfg.device));
+	int rc = flush_ring(h);
+	if (rc)
+		return rc;
+	MergeParams p;
+	p.avg = h->d_avg;
+	p.samples = h->d_smp64;
+	p.ext_avg = (const uint8_t *)dev_avg;
+	p.ext_smp = (const uint8_t *)dev_samples;
+	p.stride = set_stride;
+	p.bins = (long long)h->cfg.tune_count * h->N;
+	p.hops = h->cfg.tune_count;
+	p.sets = sets;
+	p.peak = h->cfg.peak_hold ? 1 : 0;
+	const int grid = (int)std::min<long long>((p.bins + 255) / 256, (long long)h->num_sms * 8);
+	h->last_was_epilogue = false;
+	merge_sets_kernel<<<std::max(grid, 1), 256, 0, h->stream>>>(p);
+	h->samples_on_device = true; /* the host mirror of tunes[i].samples no longer knows the totals */
+	return check_launch(h, "merge_sets_kernel");
 }
 
 int rtlsdr_gpu_scan_level_stats(rtlsdr_gpu_scan_t *h, int hop, uint64_t *overload, uint64_t *high_level, uint64_t *bytes)

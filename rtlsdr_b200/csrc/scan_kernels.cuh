@@ -2711,6 +2711,51 @@ epilogue_kernel(const SCAN_GRID_CONSTANT EpilogueParams prm)
 }
 
 /* ======================================================================== *
+ *  Merging accumulator sets (reads of ONE hop sharded over several GPUs)     *
+ * ======================================================================== */
+
+/*
+ * tunes[i].avg is a sum (or, with -P, a maximum) of per-read |X|^2 and tunes[i].samples a sum of per-read counts
+ * (rtl_power.c:708-717): both are associative and exact in int64, so the reads of one hop can be split over
+ * several handles / GPUs and their raw accumulators combined afterwards -- the report computed from the merged
+ * integers is bit-identical to a single handle's.  `sets` external sets (raw bins as rtlsdr_gpu_scan_collect_device
+ * writes them, int32 sample counts) are folded into the handle's accumulators; the external memory may be a peer
+ * mapping (the slots the other GPUs' epilogues stored into over NVLink).
+ */
+struct MergeParams {
+	long long *avg;          /* [bins] this handle's accumulators */
+	long long *samples;      /* [hops] */
+	const uint8_t *ext_avg;  /* set s: int64 [bins] at ext_avg + s * stride */
+	const uint8_t *ext_smp;  /* set s: int32 [hops] at ext_smp + s * stride */
+	long long stride;
+	long long bins;
+	int hops;
+	int sets;
+	int peak;
+};
+
+__global__ void __launch_bounds__(256)
+merge_sets_kernel(const SCAN_GRID_CONSTANT MergeParams prm)
+{
+	const long long step = (long long)gridDim.x * blockDim.x;
+	const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	for (long long i = first; i < prm.bins; i += step) {
+		long long v = prm.avg[i];
+		for (int s = 0; s < prm.sets; ++s) {
+			const long long e = ((const long long *)(prm.ext_avg + s * prm.stride))[i];
+			v = prm.peak ? (e > v ? e : v) : v + e;
+		}
+		prm.avg[i] = v;
+	}
+	for (long long i = first; i < prm.hops; i += step) {
+		long long v = prm.samples[i];
+		for (int s = 0; s < prm.sets; ++s)
+			v += ((const int *)(prm.ext_smp + s * prm.stride))[i];
+		prm.samples[i] = v;
+	}
+}
+
+/* ======================================================================== *
  *  Device-side flags for the per-interval report exchange (multi-GPU)       *
  * ======================================================================== */
 

@@ -34,6 +34,8 @@ struct LargeParams {
 	const int *hop_of;          /* hop per entry (absolute entry index) */
 	c16 *scratch;               /* [chunk][N] */
 	const long long *dc_sums;   /* [chunk][2] */
+	const int2 *dc_consts;      /* u8 reads: [chunk] (127 + average of I, of Q), written by dc_sums_u8_kernel */
+	const int2 *twc_a;          /* round A: host-built compact table, stage s (4..7), group m at (1<<s)-16+m */
 	long long *avg;
 	long long *samples;         /* [tune_count] */
 	int samples_per_read;
@@ -59,12 +61,15 @@ struct DcSumU8Params {
 	int entry_base;
 	int buf_len;
 	long long *sums; /* [chunk][2], zeroed by the host */
+	unsigned *tickets; /* [chunk], zeroed by the host */
+	int2 *consts;    /* [chunk]: the constants round A subtracts from the raw bytes (127 + int16 average) */
 };
 
 __global__ void __launch_bounds__(256)
 dc_sums_u8_kernel(const SCAN_GRID_CONSTANT DcSumU8Params prm)
 {
 	const int rel = blockIdx.y;
+	pdl_launch_dependents(); /* round A's CTAs may take free slots and load their twiddle table meanwhile */
 	const uint8_t *src = prm.base + prm.read_off[prm.entry_base + rel];
 	unsigned sI = 0, sQ = 0; /* <= 2^21 bytes of 255 per component: fits */
 	const int stride = gridDim.x * blockDim.x * 16;
@@ -90,10 +95,35 @@ dc_sums_u8_kernel(const SCAN_GRID_CONSTANT DcSumU8Params prm)
 		sI += __shfl_xor_sync(0xffffffffu, sI, o);
 		sQ += __shfl_xor_sync(0xffffffffu, sQ, o);
 	}
+	__shared__ unsigned part[2][8];
 	if ((threadIdx.x & 31) == 0) {
-		atomicAdd((unsigned long long *)(prm.sums + 2 * rel), (unsigned long long)sI);
-		atomicAdd((unsigned long long *)(prm.sums + 2 * rel + 1), (unsigned long long)sQ);
+		part[0][threadIdx.x >> 5] = sI;
+		part[1][threadIdx.x >> 5] = sQ;
 	}
+	__syncthreads();
+	if (threadIdx.x != 0)
+		return;
+	long long tI = 0, tQ = 0;
+	for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+		tI += part[0][w];
+		tQ += part[1][w];
+	}
+	/* The sums become remove_dc's averages here (rtl_power.c:581-596: divisors = the interleaved length and
+	 * length - 1, truncating), so that round A's CTAs -- one per tile -- load two words instead of each waiting
+	 * for a 64-bit division in front of their first barrier.  One CTA per read (many reads): no atomics at all;
+	 * several CTAs per read: the last one to arrive (ticket) converts the total. */
+	if (gridDim.x > 1) {
+		atomicAdd((unsigned long long *)(prm.sums + 2 * rel), (unsigned long long)tI);
+		atomicAdd((unsigned long long *)(prm.sums + 2 * rel + 1), (unsigned long long)tQ);
+		__threadfence();
+		if (atomicAdd(prm.tickets + rel, 1u) != gridDim.x - 1)
+			return;
+		tI = (long long)atomicAdd((unsigned long long *)(prm.sums + 2 * rel), 0ull);
+		tQ = (long long)atomicAdd((unsigned long long *)(prm.sums + 2 * rel + 1), 0ull);
+	}
+	const long long half = prm.buf_len / 2;
+	prm.consts[rel] = int2{ 127 + dc_average(tI - 127ll * half, prm.buf_len),
+				127 + dc_average(tQ - 127ll * half, prm.buf_len - 1) };
 }
 
 /* ---- round A ----------------------------------------------------------- */
@@ -128,23 +158,21 @@ large_round_a_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
 	const long long N = 1ll << L;
 	const uint8_t *src = prm.base + large_entry_offset(prm, e);
 
-	if (t < 240) {
-		/* entry t of the compact table: stage s = 4 + floor(log2(t/16 + 1)) */
-		int s = 4, off = 0;
-		while (t >= off + (1 << s)) {
-			off += 1 << s;
-			s++;
-		}
-		twc[t] = prm.tw[(size_t)(t - off) << (L - 1 - s)];
-	}
+	if (t < 240)
+		twc[t] = __ldg(prm.twc_a + t);
+	/* The rounds of one chunk are launched programmatically dependent on each other: a kernel reads what its
+	 * predecessor wrote only behind pdl_wait().  Round A has many waves, so only its LAST wave lets round B's
+	 * CTAs in early (they would otherwise sit on shared memory that round A's own CTAs need). */
+	if ((long long)(gridDim.y - 1 - blockIdx.y) * gridDim.x + (gridDim.x - 1 - blockIdx.x) < 4 * 148)
+		pdl_launch_dependents();
+	pdl_wait();
 	if (t == 0 && tile == 0)
 		atomicAdd((unsigned long long *)(prm.samples + prm.hop_of[e]), (unsigned long long)prm.samples_per_read);
-	if (t < 2) {
-		long long s = prm.dc_sums[2 * rel + t];
-		if constexpr (!IN16)
-			dck[t] = 127 + dc_average(s - 127ll * N, (int)(2 * N) - t);
-		else
-			dck[t] = dc_average(s, (int)(2 * N) - t);
+	if constexpr (!IN16) {
+		if (t == 0)
+			*(int2 *)dck = prm.dc_consts[rel];
+	} else if (t < 2) {
+		dck[t] = dc_average(prm.dc_sums[2 * rel + t], (int)(2 * N) - t);
 	}
 
 	__syncthreads();
@@ -394,8 +422,12 @@ large_round_b_pipe_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
 		}
 		cp_async_commit();
 	};
+	/* this tile's twiddle tables do not depend on round A: they are on their way before the wait */
+	pdl_launch_dependents();
+	load_tables(tile);
+	int tab_tile = tile;
+	pdl_wait();
 	prefetch(tile, rel, 0);
-	int tab_tile = -1;
 	TwLargeBS tw;
 	tw.t1 = tws1;
 	tw.t0 = tws0;
@@ -494,6 +526,7 @@ large_round_c_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
 	for (int r = 0; r < R * VEC; ++r)
 		acc[r] = 0ull;
 	int cur_hop = -1;
+	pdl_wait(); /* the twiddles above did not depend on round B */
 	const int rel0 = blockIdx.y * prm.c_reads;
 	const int rel1 = (rel0 + prm.c_reads < prm.n_entries) ? rel0 + prm.c_reads : prm.n_entries;
 	c16 nxt[R * VEC];

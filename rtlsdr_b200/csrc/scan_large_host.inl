@@ -2,6 +2,24 @@
  * after the handle definition. */
 namespace {
 
+/* launch programmatically dependent on the previous kernel in the stream (the kernel has a pdl_wait()) */
+template <class K, class P>
+int launch_pdl(rtlsdr_gpu_scan *h, K kern, dim3 grid, int smem, const P &prm)
+{
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = grid;
+	cfg.blockDim = dim3(kThreads);
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = h->stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = 1;
+	CU(cudaLaunchKernelEx(&cfg, kern, prm));
+	return 0;
+}
+
 template <int LB, bool LAST>
 int launch_round_b_t(rtlsdr_gpu_scan *h, const LargeParams &p, dim3 grid)
 {
@@ -34,10 +52,13 @@ int launch_round_b(rtlsdr_gpu_scan *h, const LargeParams &p, dim3 grid, int lb, 
 template <int LC>
 int launch_round_c_t(rtlsdr_gpu_scan *h, const LargeParams &p, dim3 grid)
 {
+	int rc;
 	if (h->cfg.peak_hold)
-		large_round_c_kernel<LC, true, round_c_vec(LC)><<<grid, kThreads, 0, h->stream>>>(p);
+		rc = launch_pdl(h, large_round_c_kernel<LC, true, round_c_vec(LC)>, grid, 0, p);
 	else
-		large_round_c_kernel<LC, false, round_c_vec(LC)><<<grid, kThreads, 0, h->stream>>>(p);
+		rc = launch_pdl(h, large_round_c_kernel<LC, false, round_c_vec(LC)>, grid, 0, p);
+	if (rc)
+		return rc;
 	return check_launch(h, "large_round_c_kernel");
 }
 
@@ -62,7 +83,7 @@ int large_process(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_of
 	const int L = h->cfg.bin_e;
 	const size_t N = (size_t)1 << L;
 	const bool decim = (h->cfg.boxcar && h->cfg.downsample > 1) || h->cfg.downsample_passes > 0;
-	const size_t per = N * 4 + 16 + (decim ? DecimScratch::per_entry(h) : 0);
+	const size_t per = N * 4 + 32 + (decim ? DecimScratch::per_entry(h) : 0); /* data, sums, tickets + constants */
 	const size_t extra = decim ? DecimScratch::slack() + 512 : 512;
 	const int chunk_max = (int)std::max<size_t>(1, kScratchBudget / per);
 	int rc;
@@ -75,6 +96,10 @@ int large_process(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_of
 		sp += (size_t)cnt * N * 4;
 		long long *sums = (long long *)sp;
 		sp += (size_t)cnt * 16;
+		unsigned *tickets = (unsigned *)sp;   /* directly behind the sums: one memset clears both */
+		sp += (size_t)cnt * 8;
+		int2 *consts = (int2 *)sp;
+		sp += (size_t)cnt * 8;
 
 		LargeParams p;
 		memset(&p, 0, sizeof(p));
@@ -82,6 +107,8 @@ int large_process(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_of
 		p.hop_of = d_hops;
 		p.scratch = data;
 		p.dc_sums = sums;
+		p.dc_consts = consts;
+		p.twc_a = h->d_twc;
 		p.avg = h->d_avg;
 		p.samples = h->d_smp64;
 		p.samples_per_read = h->samples_per_read;
@@ -98,14 +125,21 @@ int large_process(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_of
 		p.tiles_log2 = L - 12;
 		const unsigned grid_pipe = (unsigned)std::min<long long>((long long)cnt << (L - 12), 2ll * h->num_sms);
 		if (!decim) {
-			CU(cudaMemsetAsync(sums, 0, (size_t)cnt * 16, h->stream));
+			/* 32 KiB per CTA, up to 32 CTAs per read (one CTA per read took 30 us instead of 16-22 for 256 reads of
+			 * 256 KiB: too few bytes in flight) */
+			const unsigned per_read =
+				(unsigned)std::max<size_t>(1, std::min<size_t>(32, (size_t)h->cfg.buf_len / (256 * 16 * 8)));
+			if (per_read > 1)
+				CU(cudaMemsetAsync(sums, 0, (size_t)cnt * 24, h->stream));
 			DcSumU8Params d;
 			d.base = base;
 			d.read_off = d_offs;
 			d.entry_base = e0;
 			d.buf_len = h->cfg.buf_len;
 			d.sums = sums;
-			dim3 g((unsigned)std::max<size_t>(1, std::min<size_t>(32, (size_t)h->cfg.buf_len / (256 * 16 * 8))), (unsigned)cnt);
+			d.tickets = tickets;
+			d.consts = consts;
+			dim3 g(per_read, (unsigned)cnt);
 			dc_sums_u8_kernel<<<g, 256, 0, h->stream>>>(d);
 			if ((rc = check_launch(h, "dc_sums_u8_kernel")))
 				return rc;
@@ -113,7 +147,8 @@ int large_process(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_of
 			p.read_off = d_offs;
 			auto k = large_round_a_kernel<false>;
 			CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a));
-			k<<<grid_tiles, kThreads, smem_a, h->stream>>>(p);
+			if ((rc = launch_pdl(h, k, grid_tiles, smem_a, p)))
+				return rc;
 			if ((rc = check_launch(h, "large_round_a_kernel")))
 				return rc;
 		} else {
@@ -136,7 +171,8 @@ int large_process(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_of
 		if (8 + lb < L && h->dbg_large_pipe) {
 			auto k = large_round_b_pipe_kernel;
 			CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kLargeSmemBP));
-			k<<<grid_pipe, kThreads, kLargeSmemBP, h->stream>>>(p);
+			if ((rc = launch_pdl(h, k, dim3(grid_pipe), kLargeSmemBP, p)))
+				return rc;
 			if ((rc = check_launch(h, "large_round_b_pipe_kernel")))
 				return rc;
 		} else if ((rc = launch_round_b(h, p, grid_tiles, lb, 8 + lb == L)))

@@ -56,6 +56,7 @@ def load_library():
     L.rtlsdr_gpu_scan_collect.argtypes = [vp, i, vp, vp, vp]
     L.rtlsdr_gpu_scan_collect_all.argtypes = [vp, vp, vp, vp]
     L.rtlsdr_gpu_scan_collect_device.argtypes = [vp, vp, vp, vp]
+    L.rtlsdr_gpu_scan_merge_device.argtypes = [vp, vp, vp, i, i64]
     L.rtlsdr_gpu_scan_db_count.argtypes = [vp]
     L.rtlsdr_gpu_scan_host_alloc.argtypes = [ctypes.c_size_t]
     L.rtlsdr_gpu_scan_host_alloc.restype = vp
@@ -245,6 +246,11 @@ class GpuScan:
 
     def collect_device(self, dev_avg=None, dev_samples=None, dev_db=None):
         self._check(self.lib.rtlsdr_gpu_scan_collect_device(self.h, dev_avg, dev_samples, dev_db), "collect_device")
+
+    def merge_device(self, dev_avg, dev_samples, sets=1, set_stride=0):
+        """fold `sets` external accumulator sets (raw int64 bins + int32 counts as collect_device writes them,
+        `set_stride` bytes apart; may be peer memory) into this handle's: sums, or maxima under peak hold"""
+        self._check(self.lib.rtlsdr_gpu_scan_merge_device(self.h, dev_avg, dev_samples, sets, set_stride), "merge_device")
 
     def set_stream(self, cuda_stream):
         self._check(self.lib.rtlsdr_gpu_scan_set_stream(self.h, cuda_stream), "set_stream")

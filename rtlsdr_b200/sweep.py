@@ -111,12 +111,15 @@ class SpectrumGather:
         ... later, rank 0: fetch(k)  (needs publish(..., to_host=True))
     """
 
-    def __init__(self, tune_count, n_bins, db_count, world, rank, device, mode=None, sizes=None):
+    def __init__(self, tune_count, n_bins, db_count, world, rank, device, mode=None, sizes=None, replicated=False):
         self.tune_count, self.n, self.db_count = tune_count, n_bins, db_count
         self.world, self.rank = world, rank
         self.device = torch.device(device)
         self.cuda = self.device.type == "cuda"
-        self.ranges = shard_ranges(tune_count, world, sizes)
+        # replicated: every rank reports ALL hops (the reads of the hops are sharded instead, see ReadShardedMerge);
+        # rank 0 then holds `world` partial accumulator sets per interval instead of disjoint hop ranges
+        self.replicated = replicated
+        self.ranges = [range(tune_count)] * world if replicated else shard_ranges(tune_count, world, sizes)
         self.hmax = max(1, max(len(r) for r in self.ranges))
         self.smp_words = (self.hmax + 1) // 2
         self.words = self.hmax * (n_bins + db_count) + self.smp_words
@@ -149,6 +152,10 @@ class SpectrumGather:
                          if rank == 0 else None)
         if mode == "host" and self.cuda:
             self.stage = [torch.zeros(self.words, dtype=torch.int64).pin_memory() for _ in range(SLOTS)]
+        # rank 0, replicated: private device copy of a gathered buffer, made before the writers may reuse the slots
+        self.dev_copy = None
+        if replicated and rank == 0 and self.cuda:
+            self.dev_copy = [torch.zeros(world, self.words, dtype=torch.int64, device=self.device) for _ in range(SLOTS)]
         # rank 0: pinned landing area of a gathered report
         self.host = None
         if rank == 0 and self.cuda and mode != "host":
@@ -267,6 +274,8 @@ class SpectrumGather:
                           self._flag_addr(0, SLOTS * self.world + SLOTS))
                 if to_host:
                     self.host[k].copy_(self.recv[k], non_blocking=True)
+                if self.dev_copy is not None:
+                    self.dev_copy[k].copy_(self.recv[k], non_blocking=True)
                 # "interval consumed" in every rank's memory (one launch): the slots may be rewritten
                 addrs = [self._flag_addr(r, SLOTS * self.world + k) for r in range(self.world)]
                 for lo in range(0, self.world, 32):
@@ -289,6 +298,8 @@ class SpectrumGather:
                 src = None
             if to_host and self.rank == 0 and src is not None:
                 self.host[k].copy_(src, non_blocking=True)
+            if self.dev_copy is not None:
+                self.dev_copy[k].copy_(src if src is not None else self.recv[k], non_blocking=True)
             self.gathered[k].record(self.comm)
         self.last_exchange = self.gathered[k]
 
@@ -312,6 +323,15 @@ class SpectrumGather:
         else:
             bufs = self.host[k].numpy()
         return self.unpack(bufs)
+
+    def partial_sets(self, k):
+        """rank 0, replicated mode: (device address of set 0's raw bins, of its int32 counts, number of sets, bytes
+        between sets) of the gathered buffer k, for rtlsdr_gpu_scan_merge_device() on a stream that has waited for
+        `gathered[k]`.  The copy was made before any rank may rewrite its slot."""
+        assert self.replicated and self.rank == 0 and self.dev_copy is not None
+        base = self.dev_copy[k].data_ptr()
+        smp = base + (self.hmax * self.n + self.hmax * self.db_count) * 8
+        return base, smp, self.world, self.words * 8
 
     def unpack(self, bufs) -> IntervalReport:
         """bufs: int64 [world, words] -> rows in hop order"""

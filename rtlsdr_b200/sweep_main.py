@@ -10,6 +10,10 @@ bins + dB rows + sample counts reach rank 0 -- written by every rank's report ep
 into rank 0's buffer over NVLink (symmetric-memory peer mapping, one barrier per interval), or by
 ONE NCCL gather where peer mapping is unavailable / RTLSDR_B200_NCCL_GATHER=1 -- and rank 0 prints
 the reference's CSV rows in hop order (rtl_power.c:995-1000).  With N = 1 no process group is created.
+Scans with fewer hops than GPUs (BASELINE configs 1 and 4 are ONE hop) shard the READS instead (--shard reads):
+every rank transforms its share of each hop's reads into its own accumulators, the raw int64 bins and counts
+reach rank 0 the same way, and rank 0 folds them into its handle (rtlsdr_gpu_scan_merge_device: int64 sums, or
+maxima under -P, are associative and exact) before its ordinary collect -- rows byte-identical to one GPU's.
 Hop order inside a rank's shard can be randomised (--random-hops SEED, the reference's TODO list
 rtl_power.c:29-36): the bins are order independent (int64 sums / maxima, rtl_power.c:708-716).
 """
@@ -36,6 +40,9 @@ def main(argv=None):
     ap.add_argument("--stamp", default="2026-01-01, 00:00:00", help="fixed 'date, time' prefix of the rows")
     ap.add_argument("--random-hops", type=int, default=None, metavar="SEED",
                     help="visit the hops of every sweep in a random order (results do not depend on it)")
+    ap.add_argument("--shard", default="hops", choices=["hops", "reads"],
+                    help="hops: contiguous hop ranges per GPU (default); reads: every GPU takes a share of the sweeps "
+                         "of ALL hops and rank 0 merges the raw accumulators (single-hop scans)")
     ap.add_argument("--backend", default="nccl", choices=["nccl", "gloo"],
                     help="gloo: reports are staged through host memory (e.g. several ranks on one GPU in tests)")
     ap.add_argument("--device", type=int, default=None, help="CUDA device of this rank (default: LOCAL_RANK)")
@@ -47,7 +54,7 @@ def main(argv=None):
 
     from . import scan as rs
     from .planner import host_library, plan_scan, synth_cube
-    from .sweep import SpectrumGather, format_rows, shard_hops
+    from .sweep import IntervalReport, SpectrumGather, format_rows, shard_hops
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -69,6 +76,9 @@ def main(argv=None):
     tc, b, n = pd["tune_count"], pd["buf_len"], 1 << pd["bin_e"]
     mine = shard_hops(tc, world, rank)
     mode = ["xorshift", "counter", "const", "biased", "tone"].index(args.synth)
+    if args.shard == "reads":
+        return _main_read_sharded(args, rs, host, plan, pd, mode, world, rank, local, torch, dist,
+                                  IntervalReport, SpectrumGather, format_rows, shard_hops, synth_cube)
 
     g = None
     if len(mine):
@@ -135,6 +145,56 @@ def main(argv=None):
                 f.write(text)
     if g:
         g.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def _main_read_sharded(args, rs, host, plan, pd, mode, world, rank, local, torch, dist,
+                       IntervalReport, SpectrumGather, format_rows, shard_hops, synth_cube):
+    """--shard reads: rank r transforms sweeps [S*r/W, S*(r+1)/W) of every interval for ALL hops; rank 0 merges"""
+    tc, b, n = pd["tune_count"], pd["buf_len"], 1 << pd["bin_e"]
+    sweeps = shard_hops(args.sweeps, world, rank)            # the same balanced split, over sweeps
+    window = rs.window_coefs(args.window, n) if pd["bin_e"] else None
+    g = rs.GpuScan.from_plan(pd, window_coefs=window, device=local)
+    gather = SpectrumGather(tc, n, g.db_count, world, rank, torch.device("cuda", local),
+                            mode=("host" if args.backend == "gloo" and world > 1 else None), replicated=True)
+    if rank == 0 and world > 1:
+        print("sweep_main: reads sharded %s over %d ranks; partial accumulators: %s" % (
+            [len(shard_hops(args.sweeps, world, r)) for r in range(world)], world, gather.describe()), file=sys.stderr)
+    stream = torch.cuda.ExternalStream(g.get_stream())
+    pinned = [rs.PinnedBuffer(max(1, len(sweeps) * tc * b)) for _ in range(2)]
+    consumed = [None, None]
+    rows_out = []
+    for interval in range(args.intervals):
+        k = interval & 1
+        if consumed[k] is not None:
+            consumed[k].synchronize()
+        if len(sweeps):
+            synth_cube(pinned[k].ptr, mode, args.seed, args.param, tc, 0, tc,
+                       interval * args.sweeps + sweeps.start, len(sweeps), b)
+            g.submit_batch(0, tc, len(sweeps), pinned[k].ptr, tc * b, b)
+        gather.before_collect(k, stream)
+        p_avg, p_smp, _ = gather.pointers(k)
+        g.collect_device(p_avg, p_smp, None)                 # raw bins + counts only: dB comes from the merged integers
+        consumed[k] = torch.cuda.Event()
+        consumed[k].record(stream)
+        gather.publish(k, stream)
+        if rank == 0:
+            stream.wait_event(gather.gathered[k])
+            g.merge_device(*gather.partial_sets(k))
+            avg, smp, db = g.collect_all()
+            rows_out.extend(format_rows(plan, IntervalReport(avg, db, smp), args.stamp))
+    if rank == 0:
+        text = "".join(rows_out)
+        if args.out == "-":
+            sys.stdout.write(text)
+        else:
+            with open(args.out, "w") as f:
+                f.write(text)
+    torch.cuda.synchronize()
+    g.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

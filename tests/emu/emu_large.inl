@@ -12,6 +12,12 @@ void emu_large(int L, int peak, int in16, const uint8_t *reads, int n_reads, con
 		offs[i] = (long long)i * (long long)(in16 ? 4 * N : 2 * N);
 	std::vector<c16> scratch((size_t)n_reads * N, 0xDEADBEEFu);
 	std::vector<long long> sums((size_t)n_reads * 2, 0);
+	std::vector<unsigned> tickets(n_reads, 0);
+	std::vector<int2> consts(n_reads, int2{ -1, -1 });
+	std::vector<int2> twc_a(240);
+	for (int st = 4; st < 8; st++)
+		for (int m = 0; m < (1 << st); m++)
+			twc_a[(size_t)(1 << st) - 16 + m] = ((const int2 *)tw)[(size_t)m << (L - 1 - st)];
 	LargeParams p;
 	memset(&p, 0, sizeof(p));
 	p.base = reads;
@@ -20,6 +26,8 @@ void emu_large(int L, int peak, int in16, const uint8_t *reads, int n_reads, con
 	p.hop_of = hop_of;
 	p.scratch = scratch.data();
 	p.dc_sums = sums.data();
+	p.dc_consts = consts.data();
+	p.twc_a = twc_a.data();
 	std::vector<long long> smp(4096, 0);
 	p.avg = avg;
 	p.samples = smp.data();
@@ -49,7 +57,9 @@ void emu_large(int L, int peak, int in16, const uint8_t *reads, int n_reads, con
 		d.entry_base = 0;
 		d.buf_len = (int)(2 * N);
 		d.sums = sums.data();
-		cuda_emu::launch(dim3(3, n_reads), dim3(256), 0, [&]() { dc_sums_u8_kernel(d); });
+		d.tickets = tickets.data();
+		d.consts = consts.data();
+		cuda_emu::launch(dim3((L & 1) ? 1 : 3, n_reads), dim3(256), 0, [&]() { dc_sums_u8_kernel(d); }); /* both forms: one CTA per read / ticketed */
 		cuda_emu::launch(tiles, dim3(kThreads), kLargeSmemA, [&]() { large_round_a_kernel<false>(p); });
 	} else {
 		memcpy(sums.data(), sums_in, sums.size() * 8);

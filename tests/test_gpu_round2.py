@@ -427,3 +427,83 @@ def test_short_reads_keep_the_hops_previous_tail(scan_mod, port_oracle):
     assert scan_mod.load_library().rtlsdr_gpu_scan_submit(g.h, 0, reads[0].ctypes.data, 5000) == -4
     assert scan_mod.load_library().rtlsdr_gpu_scan_submit(g.h, 0, reads[0].ctypes.data, b + 16) == -4
     g.close()
+
+
+@pytest.mark.parametrize("bin_e,peak,buf_len,async_report", [(10, 0, 16384, False), (12, 1, 16384, True),
+                                                             (13, 1, 16384, False), (0, 0, 16384, False)])
+def test_merge_device_reads_of_one_hop_on_three_handles(scan_mod, port_oracle, bin_e, peak, buf_len, async_report):
+    """VERDICT r1 missing #6: the READS of the same hops split over several handles (one per GPU on a multi-GPU
+    box, three on cuda:0 here), raw accumulators collected on the device and folded into the first handle with
+    rtlsdr_gpu_scan_merge_device(): bins, counts AND dB identical to the oracle's for all the reads, i.e. to one
+    handle -- int64 sums / peak-hold maxima are exact in any grouping (rtl_power.c:708-717)."""
+    import torch
+    n, tc, passes = 1 << bin_e, 2, 7
+    plan = plan_dict(bin_e, buf_len=buf_len, peak_hold=peak, tune_count=tc, crop=0.1 if bin_e else 0.0)
+    win = port_oracle.window_coefs("hamming", n) if bin_e else None
+    reads, hops = make_reads(port_oracle.lib, plan, passes, SYNTH_BIASED, seed=bin_e + 3, param=29)
+    owin = win if win is not None else np.zeros(1, np.int32)      # the oracle wants an array even for rms bins
+    want_avg, want_smp, want_db = expected(port_oracle, plan, owin, reads, hops)
+    shares = [(0, 3), (3, 5), (5, 7)]                      # sweeps per handle
+    gs = [scan_mod.GpuScan.from_plan(plan, window_coefs=win, async_report=async_report) for _ in shares]
+    try:
+        words = tc * n + (tc + 1) // 2                     # [avg tc*N int64 | samples tc x int32]
+        slots = torch.zeros(len(shares), words, dtype=torch.int64, device="cuda")
+        dev = torch.from_numpy(np.ascontiguousarray(reads)).cuda()
+        torch.cuda.synchronize()
+        for k, (g, (lo, hi)) in enumerate(zip(gs, shares)):
+            g.submit_device(0, tc, hi - lo, dev[lo * tc:].data_ptr(), tc * buf_len, buf_len)
+            base = slots[k].data_ptr()
+            g.collect_device(base, base + tc * n * 8, None)
+        torch.cuda.synchronize()                           # the reports may be on the handles' report streams
+        # every handle (the merging one included) is empty again; fold all three sets into handle 0
+        gs[0].merge_device(slots.data_ptr(), slots.data_ptr() + tc * n * 8, len(shares), words * 8)
+        avg, smp, db = gs[0].collect_all()
+        assert np.array_equal(avg, want_avg) and np.array_equal(smp, want_smp)
+        assert db_close(db, want_db)
+        # read-and-zero still holds after a merge, and per-hop collects see merged counts too
+        gs[0].merge_device(slots.data_ptr(), slots.data_ptr() + tc * n * 8, 2, words * 8)
+        a1, s1, _ = gs[0].collect(1)
+        sub = np.concatenate([reads[0:3 * tc], reads[3 * tc:5 * tc]]), np.concatenate([hops[0:3 * tc], hops[3 * tc:5 * tc]])
+        w_avg, w_smp, _ = expected(port_oracle, plan, owin, *sub)
+        assert np.array_equal(a1, w_avg[1]) and s1 == w_smp[1]
+        a0, s0, _ = gs[0].collect(0)
+        assert np.array_equal(a0, w_avg[0]) and s0 == w_smp[0]
+        avg, smp, _ = gs[0].collect_all()
+        assert not avg.any() and not smp.any()
+    finally:
+        for g in gs:
+            g.close()
+
+
+def test_merge_device_argument_checks(scan_mod):
+    import torch
+    g = scan_mod.GpuScan(1, 4, 16384)
+    try:
+        buf = torch.zeros(64, dtype=torch.int64, device="cuda")
+        L = g.lib
+        assert L.rtlsdr_gpu_scan_merge_device(None, buf.data_ptr(), buf.data_ptr(), 1, 0) == -1
+        assert L.rtlsdr_gpu_scan_merge_device(g.h, None, buf.data_ptr(), 1, 0) == -1
+        assert L.rtlsdr_gpu_scan_merge_device(g.h, buf.data_ptr(), buf.data_ptr(), 0, 0) == -2
+        assert L.rtlsdr_gpu_scan_merge_device(g.h, buf.data_ptr(), buf.data_ptr(), 2, 0) == -2
+        assert L.rtlsdr_gpu_scan_merge_device(g.h, buf.data_ptr() + 4, buf.data_ptr(), 1, 0) == -8
+        assert L.rtlsdr_gpu_scan_merge_device(g.h, buf.data_ptr(), buf.data_ptr(), 2, 12) == -8
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("args", [
+    ["-f", "100M:102.4M:2400", "--sweeps", "7", "--intervals", "3", "--synth", "biased", "--seed", "2", "--param", "33"],
+    ["-f", "100M:102.4M:300", "-w", "blackman-harris", "-P", "--sweeps", "5", "--intervals", "2", "--seed", "6"],
+    ["-f", "100M:104M:1M", "--sweeps", "6", "--intervals", "2", "--synth", "biased", "--param", "9"],
+])
+def test_sweep_main_read_sharded_single_hop(scan_mod, tmp_path, args):
+    """--shard reads (BASELINE configs 1 and 4 are single-hop scans: nothing to shard by hop): 1, 2 or 3 ranks on
+    cuda:0 over gloo, several intervals through the alternating buffers -- CSV byte-identical to the plain
+    hop-sharded 1-rank run (splits 7 -> 3+2+2, 5 -> 3+2, 6 -> 2+2+2; 1024 bins, 2^13 bins with peak hold, rms bins)."""
+    plain = _run_sweep_main(args, tmp_path / "plain.csv", 1, tmp_path)
+    world = 2 if "-P" in args else 3                        # (one multi-rank launch per case keeps the suite short)
+    many = _run_sweep_main(args + ["--shard", "reads"], tmp_path / "rn.csv", world, tmp_path)
+    assert len(plain) > 100 and plain == many
+    if "-P" not in args and "--param" in args and args[args.index("--param") + 1] == "33":
+        one = _run_sweep_main(args + ["--shard", "reads"], tmp_path / "r1.csv", 1, tmp_path)
+        assert one == plain
