@@ -18,8 +18,11 @@
  *   -t workers   "multiple FFT workers": the hops are dealt in contiguous ranges to `workers`
  *                B200s (one rtlsdr_gpu_scan handle per device, first device RTLSDR_GPU_DEVICE,
  *                or the list RTLSDR_GPU_DEVICES=0,2,3); hops are independent (rtl_power.c:650-719),
- *                so the CSV bytes do not depend on the worker count.  The reference parses -t and
- *                ignores it (:844-846); one worker is the default here too.
+ *                so the CSV bytes do not depend on the worker count.  With more workers than hops
+ *                (single-hop scans) every worker owns all hops and takes every workers-th SWEEP; at a
+ *                report their raw int64 accumulators are merged into worker 0's
+ *                (rtlsdr_gpu_scan_merge_device: sums / -P maxima are exact in any grouping), same bytes
+ *                again.  The reference parses -t and ignores it (:844-846); one worker is the default.
  *   -s iir       "continuous IIR smoothing" of the dB rows across reports (cfg.iir_alpha,
  *                RTL_POWER_IIR_ALPHA, default 0.25); -s avg = the reference's behaviour.
  *   -R seed      (extension) "randomized hopping": every sweep visits the hops in a fresh random
@@ -80,7 +83,7 @@ static void print_usage(void)
 		"\t[-F fir_size (default: disabled)] (0 or 9; switches boxcar off)\n"
 		"\t[-P enables peak hold (default: off)]\n"
 		"\t[-s avg|iir (default: avg; iir smooths the dB rows across reports)]\n"
-		"\t[-t workers (default: 1; hops are sharded over this many GPUs)]\n"
+		"\t[-t workers (default: 1; hops -- or, with fewer hops than workers, sweeps -- are sharded over this many GPUs)]\n"
 		"\t[-R seed (visit the hops of every sweep in a random order)]\n"
 		"\tfilename (a '-' dumps samples to stdout, the default)\n");
 	exit(1);
@@ -130,9 +133,12 @@ struct visit_ctx {
 
 #define MAX_WORKERS 16
 
-/* the GPU workers: worker w owns hops [first[w], first[w + 1]) */
+/* the GPU workers: worker w owns hops [first[w], first[w + 1]); with more workers than hops (by_pass) every
+ * worker owns ALL hops and takes every count-th sweep instead -- the reads of a hop are then spread over the
+ * workers and their raw accumulators are merged at report time (rtlsdr_gpu_scan_merge_device) */
 struct workers {
 	int count;
+	int by_pass, cur;
 	int first[MAX_WORKERS + 1];
 	rtlsdr_gpu_scan_t *gpu[MAX_WORKERS];
 };
@@ -140,6 +146,8 @@ struct workers {
 static int worker_of(const struct workers *ws, int hop)
 {
 	int w = 0;
+	if (ws->by_pass)
+		return ws->cur;
 	while (w + 1 < ws->count && hop >= ws->first[w + 1])
 		w++;
 	return w;
@@ -233,6 +241,8 @@ int main(int argc, char **argv)
 	int passes_per_report = env_int("RTL_POWER_PASSES", 0), passes = 0, rc = 0, hop, w;
 	int max_reports = env_int("RTL_POWER_REPORTS", 0), reports = 0;
 	int want_workers = 1, smooth_iir = 0, shuffle = 0, db_count, devices[MAX_WORKERS];
+	uint8_t *parts = NULL;      /* by_pass: raw bins + counts of workers 1.., pinned (device-readable) */
+	size_t part_avg_bytes = 0, part_bytes = 0;
 	const int use_async = getenv("RTL_POWER_ASYNC") != NULL;
 	uint64_t shuffle_state = 0;
 	long exit_after = 0;
@@ -343,14 +353,16 @@ int main(int argc, char **argv)
 	/* the GPU workers: contiguous, balanced hop ranges (sizes differ by at most one) */
 	if (want_workers < 1)
 		want_workers = 1;
-	if (want_workers > plan->tune_count)
-		want_workers = plan->tune_count;
+	if (want_workers > MAX_WORKERS)
+		want_workers = MAX_WORKERS;
 	ws.count = device_list(want_workers, devices);
-	if (ws.count > plan->tune_count)
-		ws.count = plan->tune_count;
+	if (ws.count > want_workers)
+		ws.count = want_workers;
+	/* fewer hops than workers (single-hop scans): shard the sweeps, not the hops */
+	ws.by_pass = ws.count > plan->tune_count;
 	for (w = 0; w <= ws.count; w++) {
 		const int base = plan->tune_count / ws.count, extra = plan->tune_count % ws.count;
-		ws.first[w] = w * base + (w < extra ? w : extra);
+		ws.first[w] = ws.by_pass ? (w < ws.count ? 0 : plan->tune_count) : w * base + (w < extra ? w : extra);
 	}
 	memset(&cfg, 0, sizeof(cfg));
 	cfg.struct_size = sizeof(cfg);
@@ -371,16 +383,28 @@ int main(int argc, char **argv)
 	}
 	for (w = 0; w < ws.count; w++) {
 		cfg.device = devices[w];
-		cfg.tune_count = ws.first[w + 1] - ws.first[w];
+		cfg.tune_count = ws.by_pass ? plan->tune_count : ws.first[w + 1] - ws.first[w];
 		rc = rtlsdr_gpu_scan_init(&cfg, &ws.gpu[w]);
 		if (rc) {
 			fprintf(stderr, "rtlsdr_gpu_scan_init (device %d): %s\n", devices[w], rtlsdr_gpu_scan_strerror(rc));
 			return 1;
 		}
 	}
-	if (ws.count > 1)
+	if (ws.count > 1 && ws.by_pass)
+		fprintf(stderr, "GPU workers: %d (all %d hops each, every %d-th sweep; accumulators merged per report)\n",
+			ws.count, plan->tune_count, ws.count);
+	else if (ws.count > 1)
 		fprintf(stderr, "GPU workers: %d (hops per worker: %d..%d)\n", ws.count,
 			plan->tune_count / ws.count, (plan->tune_count + ws.count - 1) / ws.count);
+	if (ws.by_pass) {
+		part_avg_bytes = (sizeof(int64_t) << plan->bin_e) * (size_t)plan->tune_count;
+		part_bytes = part_avg_bytes + ((sizeof(int) * (size_t)plan->tune_count + 7) & ~(size_t)7);
+		parts = (uint8_t *)rtlsdr_gpu_scan_host_alloc(part_bytes * (size_t)(ws.count - 1));
+		if (!parts) {
+			fprintf(stderr, "Out of memory.\n");
+			return 1;
+		}
+	}
 
 	db_count = rtlsdr_gpu_scan_db_count(ws.gpu[0]);
 	buf8 = (uint8_t *)malloc((size_t)plan->buf_len);
@@ -401,6 +425,7 @@ int main(int argc, char **argv)
 		exit_time = time(NULL) + exit_after;
 
 	while (!stop_requests) {
+		ws.cur = ws.by_pass ? passes % ws.count : 0;
 		rc = sweep(dev, &ws, plan, buf8, order, shuffle ? &shuffle_state : NULL, use_async);
 		if (rc)
 			break;
@@ -416,7 +441,22 @@ int main(int argc, char **argv)
 		}
 		/* one report per worker: ONE epilogue launch, one copy, one synchronisation each
 		 * (csv_dbm's reads and zeroing, rtl_power.c:730-764), then the rows in hop order (:995-1000) */
-		for (w = 0; w < ws.count && !rc; w++) {
+		if (ws.by_pass) {
+			/* the other workers' raw int64 bins and counts land in pinned memory, worker 0 folds them into its
+			 * own accumulators (sums, or maxima under -P: exact in any grouping) and reports alone */
+			for (w = 1; w < ws.count && !rc; w++)
+				rc = rtlsdr_gpu_scan_collect_all(ws.gpu[w], (int64_t *)(parts + (size_t)(w - 1) * part_bytes),
+								 (int *)(parts + (size_t)(w - 1) * part_bytes + part_avg_bytes), NULL);
+			if (!rc)
+				rc = rtlsdr_gpu_scan_merge_device(ws.gpu[0], parts, parts + part_avg_bytes, ws.count - 1,
+								  (int64_t)part_bytes);
+			if (!rc)
+				rc = rtlsdr_gpu_scan_collect_all(ws.gpu[0], NULL, samples, db);
+			if (rc)
+				fprintf(stderr, "merging the workers' accumulators: %s (%s)\n", rtlsdr_gpu_scan_strerror(rc),
+					rtlsdr_gpu_scan_last_cuda_error(ws.gpu[0]));
+		}
+		for (w = 0; w < ws.count && !rc && !ws.by_pass; w++) {
 			rc = rtlsdr_gpu_scan_collect_all(ws.gpu[w], NULL, samples + ws.first[w],
 							 db + (size_t)ws.first[w] * (size_t)db_count);
 			if (rc)
@@ -453,6 +493,7 @@ int main(int argc, char **argv)
 	free(buf8);
 	rtlsdr_gpu_scan_host_free(db);
 	rtlsdr_gpu_scan_host_free(samples);
+	rtlsdr_gpu_scan_host_free(parts);
 	free(order);
 	free(row);
 	free(window_coefs);

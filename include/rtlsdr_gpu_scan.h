@@ -222,8 +222,9 @@ RTLSDR_GPU_API int rtlsdr_gpu_scan_collect_device(rtlsdr_gpu_scan_t *h, void *de
  * dev_samples + s * set_stride (bytes; 8-byte aligned).  Bins are added, or maximised under peak_hold; counts are
  * added -- exactly what the reference's accumulation does read by read (rtl_power.c:708-717), so a following
  * collect() of this handle returns bit-identical bins, counts and dB to ONE handle that had seen all the reads.
- * Asynchronous on the handle's stream; the external memory may be a peer mapping of another GPU and must stay
- * valid until the work has run.  (iir_alpha: smoothing state is only updated by this handle's own collects.)
+ * Asynchronous on the handle's stream; the external memory may be device memory, a peer mapping of another GPU
+ * or pinned host memory from rtlsdr_gpu_scan_host_alloc() (what another handle's collect_all() filled), and must
+ * stay valid until the work has run.  (iir_alpha: smoothing state is only updated by this handle's own collects.)
  */
 RTLSDR_GPU_API int rtlsdr_gpu_scan_merge_device(rtlsdr_gpu_scan_t *h, const void *dev_avg, const void *dev_samples,
 		int sets, int64_t set_stride);

@@ -235,6 +235,12 @@ def test_cli_workers_and_random_hops_same_rows(scan_mod, tmp_path):
     if torch.cuda.device_count() >= 2:
         real, _ = _run_cli(args + ["-t", "2"], tmp_path / "w2real.csv", {})
         assert real == one
+    # more workers than hops (a single-hop scan, 2^13 bins with peak hold): the SWEEPS are dealt to the workers and
+    # their raw accumulators merged into worker 0's at every report -- same bytes again
+    args = ["-f", "100M:102.4M:300", "-w", "blackman-harris", "-P"]
+    one, _ = _run_cli(args, tmp_path / "s1.csv", {})
+    three, err = _run_cli(args + ["-t", "3"], tmp_path / "s3.csv", {"RTLSDR_GPU_DEVICES": "0,0,0"})
+    assert "every 3-th sweep" in err and len(one) > 1000 and one == three
 
 
 def test_cli_iir_rows(scan_mod, port_oracle, tmp_path):
