@@ -459,6 +459,120 @@ def probe_h2d(D):
     return [float(t.item()) for t in every]
 
 
+class ReadShardedSweep:
+    """A scan with fewer hops than GPUs (BASELINE configs[3]: ONE hop of 2^17 bins, peak hold): the READS of every
+    interval are dealt to the ranks, every rank's epilogue stores its raw int64 bins + counts into its slot of rank
+    0's buffer (same exchange as the hop-sharded report), rank 0 folds the slots into its own handle
+    (rtlsdr_gpu_scan_merge_device: sums / peak-hold maxima, exact) and writes the final report."""
+
+    def __init__(self, D, rs, rng, window, peak, reads):
+        import numpy as np
+        from rtlsdr_b200.planner import plan_scan, synth_cube
+        from rtlsdr_b200.sweep import SpectrumGather, shard_hops
+        torch = D.torch
+        self.D, self.rs, self.np = D, rs, np
+        pd = plan_scan(rng, 0.0, None).as_dict()
+        pd["peak_hold"] = peak
+        self.pd, self.reads = pd, reads
+        self.tc, self.b, self.n = pd["tune_count"], pd["buf_len"], 1 << pd["bin_e"]
+        self.mine = shard_hops(reads, D.world, D.rank)            # contiguous share of the interval's sweeps
+        self.window = rs.window_coefs(window, self.n)
+        self.g = rs.GpuScan.from_plan(pd, window_coefs=self.window, device=D.local)
+        self.stream = torch.cuda.ExternalStream(self.g.get_stream())
+        self.gather = SpectrumGather(self.tc, self.n, self.g.db_count, D.world, D.rank, torch.device("cuda", D.local),
+                                     mode=("host" if os.environ.get("BENCH_GLOO_ONE_GPU") and D.world > 1 else None),
+                                     replicated=True)
+        self.bytes_all = reads * self.tc * self.b
+        nb = max(1, len(self.mine) * self.tc * self.b)
+        pinned = rs.PinnedBuffer(nb)
+        if len(self.mine):
+            synth_cube(pinned.ptr, SYNTH_XORSHIFT, 0, 0, self.tc, 0, self.tc, self.mine.start, len(self.mine), self.b)
+        self.dev_in = torch.empty(nb, dtype=torch.uint8, device="cuda")
+        self.dev_in.copy_(torch.from_numpy(pinned.array), non_blocking=False)
+        pinned.free()
+        self.out = torch.zeros(self.tc * (self.n + self.g.db_count + 1), dtype=torch.int64, device="cuda") \
+            if D.rank == 0 else None
+
+    def step(self, i):
+        k = i & 1
+        if len(self.mine):
+            self.g.submit_device(0, self.tc, len(self.mine), self.dev_in.data_ptr(), self.tc * self.b, self.b)
+        self.gather.before_collect(k, self.stream)
+        p_avg, p_smp, _ = self.gather.pointers(k)
+        self.g.collect_device(p_avg, p_smp, None)
+        self.gather.publish(k, self.stream)
+        if self.D.rank == 0:
+            self.stream.wait_event(self.gather.gathered[k])
+            self.g.merge_device(*self.gather.partial_sets(k))
+            base = self.out.data_ptr()
+            p_db = base + self.tc * self.n * 8
+            self.g.collect_device(base, p_db + self.tc * self.g.db_count * 8, p_db)
+
+    def merged_bins(self):
+        self.D.torch.cuda.synchronize()
+        return self.out[: self.tc * self.n].cpu().numpy().reshape(self.tc, self.n)
+
+    def close(self):
+        self.g.close()
+
+
+def read_sharded_companion(D, rs, steps, peak_gbs):
+    """N > 1: BASELINE configs[3] with 8 x 256 reads per interval dealt to the ranks (strong scaling of one job);
+    the merged bins of one interval are verified against a 1-rank scan of the same bytes on rank 0."""
+    from rtlsdr_b200.planner import fnv1a_int64, synth_cube
+    from rtlsdr_b200.sweep import shard_hops
+    torch = D.torch
+    rng, window, reads = "100M:102.4M:19", "blackman-harris", 2048
+    sw = ReadShardedSweep(D, rs, rng, window, 1, reads)
+    out = {"workload": "large_fft_2^17_blackman-harris_peak_hold (BASELINE configs[3]), READS sharded over the GPUs, "
+                       "raw accumulators merged on rank 0 (rtlsdr_gpu_scan_merge_device)",
+           "cli": f"-f {rng} -P", "reads_per_interval": reads,
+           "reads_per_gpu": [len(shard_hops(reads, D.world, r)) for r in range(D.world)], "unit": "Msamples/s",
+           "exchange": sw.gather.describe()}
+    # ---- verification (outside the timed region): one full interval vs a 1-rank scan of ALL its bytes on rank 0
+    sw.step(0)
+    got = sw.merged_bins() if D.rank == 0 else None
+    if D.rank == 0:
+        g1 = rs.GpuScan.from_plan(sw.pd, window_coefs=sw.window, device=D.local)
+        chunk = 256
+        hb = rs.PinnedBuffer(chunk * sw.tc * sw.b)
+        for lo in range(0, reads, chunk):
+            synth_cube(hb.ptr, SYNTH_XORSHIFT, 0, 0, sw.tc, 0, sw.tc, lo, chunk, sw.b)
+            g1.submit_batch(0, sw.tc, chunk, hb.ptr, sw.tc * sw.b, sw.b)
+            g1.sync()
+        avg1, _, _ = g1.collect_all(want_db=False)
+        g1.close()
+        hb.free()
+        out["verify"] = {"ok": bool(fnv1a_int64(avg1) == fnv1a_int64(got)), "fnv": f"{fnv1a_int64(got):016x}",
+                         "check": "merged bins of the read-sharded interval == a 1-rank scan of the same 2048 reads on rank 0"}
+    D.barrier()
+    for i in range(3):
+        sw.step(1 + i)
+    sw.gather.drain(sw.stream)
+    D.barrier()
+    total, done, want, rounds = 0.0, 0, 1, 0
+    while rounds < want:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        D.barrier()
+        e0.record(sw.stream)
+        for i in range(steps):
+            sw.step(4 + done + i)
+        sw.gather.drain(sw.stream)
+        e1.record(sw.stream)
+        D.barrier()
+        ms = D.max(e0.elapsed_time(e1))
+        total += ms
+        done += steps
+        rounds += 1
+        if rounds == 1:
+            want = max(1, min(50, int(-(-MIN_TIMED_MS // max(ms, 1e-3)))))
+    sw.close()
+    ms = total / done
+    out.update(value=sw.bytes_all / 2 / (ms * 1e-3) / 1e6, ms_per_step=ms, timed_steps=done, bytes_per_step=sw.bytes_all,
+               frac_of_hbm_peak=sw.bytes_all / (ms * 1e-3) / 1e9 / (peak_gbs * D.world))
+    return out
+
+
 def companion(rs, plan_scan, torch, name, freq, crop, window, fir, peak, passes, steps, peak_gbs):
     """Device-resident throughput of another rtl_power configuration on one GPU (same method as `value`)."""
     plan = plan_scan(freq, crop, fir)
@@ -566,6 +680,10 @@ def run_gpu(args):
                  "bytes_per_step": sw3.bytes_all, "frac_of_hbm_peak": sw3.bytes_all / (ms3 * 1e-3) / 1e9 / (peak * D.world),
                  "verify": verify3}
     sw3.close()
+    # ---- N > 1: a single-hop scan (BASELINE configs[3]) with its READS sharded and an exact merge on rank 0 ----
+    comp4 = None
+    if D.world > 1 and not args.no_companions:
+        comp4 = read_sharded_companion(D, rs, max(4, min(args.steps, 20)), peak)
 
     if D.rank == 0:
         samples_step = sw.bytes_all // 2
@@ -620,7 +738,7 @@ def run_gpu(args):
             line["roofline"]["issue"] = {"bound": "issue", "achieved": ipc, "peak": pk, "unit": "warp-instr/clk/SM",
                                          "frac": ipc / pk, "warp_instructions_per_launch": inst,
                                          "sm_mhz": clocks["sm_mhz"], "sms": sms, "peak_source": ncu.get("issue_peak_source")}
-        comps = [comp3]
+        comps = [comp3] + ([comp4] if comp4 else [])
         if D.world == 1 and not args.no_companions:
             try:
                 comps += [

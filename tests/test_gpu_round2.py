@@ -323,7 +323,7 @@ def test_bench_two_ranks_on_one_gpu(scan_mod, tmp_path):
     env = dict(os.environ, BENCH_GLOO_ONE_GPU="1", BENCH_E2E_WEIGHTS="3,1")   # host-fed leg with unequal hop shares
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(29400 + os.getpid() % 500), os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "4",
-           "--warmup", "3", "--sweeps", "8", "--no-cpu", "--no-companions"]
+           "--warmup", "3", "--sweeps", "8", "--no-cpu"]
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=420)
     assert r.returncode == 0, r.stderr[-3000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
@@ -334,6 +334,8 @@ def test_bench_two_ranks_on_one_gpu(scan_mod, tmp_path):
     assert v["interval_ranks"] == 2 and v["interval_fnv"] == v["interval_fnv_check"]
     c3 = line["companions"][0]
     assert c3["verify"]["ok"] and c3["hops_per_gpu"] == [312, 311]
+    c4 = line["companions"][1]     # the single-hop scan with its READS sharded and merged on rank 0
+    assert c4["verify"]["ok"] and c4["reads_per_gpu"] == [1024, 1024] and c4["value"] > 0
     assert line["value"] > 0 and line["e2e"]["value"] > 0 and line["gpu_launches"] >= 4
     assert line["e2e"]["hops_per_gpu"] == [384, 128] and line["e2e"]["report_fnv_equals_verified_interval"] is True
 
