@@ -161,7 +161,7 @@ struct rtlsdr_gpu_scan {
 	int dbg_boxcar_mode = -1;
 	int dbg_stagger_ns = 0;
 	bool dbg_no_fused_boxcar = false, dbg_no_hb_stream = false, dbg_rms_warp = false;
-	int dbg_large_pipe = 2;
+	int dbg_large_pipe = 1;
 
 	std::string last_error;
 };
@@ -1409,8 +1409,8 @@ int rtlsdr_gpu_scan_init(const rtlsdr_gpu_scan_cfg_t *cfg_in, rtlsdr_gpu_scan_t 
 	if (const char *f = getenv("RTLSDR_GPU_STAGGER_NS"))
 		h->dbg_stagger_ns = atoi(f);
 	h->dbg_no_hb_stream = getenv("RTLSDR_GPU_NO_HB_STREAM") != nullptr;
-	if (const char *f = getenv("RTLSDR_GPU_LARGE_PIPE")) /* A/B switch, N >= 2^17: 0 = one-tile-per-CTA round B, 1 = pipelined round B + round C, 2 = (2^17) rounds B + C fused */
-		h->dbg_large_pipe = std::max(0, std::min(2, atoi(f)));
+	if (const char *f = getenv("RTLSDR_GPU_LARGE_PIPE")) /* A/B switch: 0 = one-tile-per-CTA round B for N >= 2^17 */
+		h->dbg_large_pipe = atoi(f) != 0;
 	h->dbg_rms_warp = getenv("RTLSDR_GPU_RMS_WARP") != nullptr; /* 1-bin hops: warp-per-read kernel instead of CTA-per-read */
 	h->cfg.window_coefs = nullptr;
 	h->cfg.sinewave = nullptr;

@@ -46,17 +46,6 @@ SCAN_DEV void cp_async8(void *smem_dst, const void *gmem_src)
 #endif
 }
 
-/* 4-byte form (LDGSTS.32): destinations padded by single words */
-SCAN_DEV void cp_async4(void *smem_dst, const void *gmem_src)
-{
-#ifdef SCAN_EMU
-	memcpy(smem_dst, gmem_src, 4);
-#else
-	unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem_src) : "memory");
-#endif
-}
-
 SCAN_DEV void cp_async_commit()
 {
 #ifndef SCAN_EMU

@@ -482,162 +482,6 @@ large_round_b_pipe_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
 	}
 }
 
-/*
- * N = 2^17: rounds B and C as ONE pipelined kernel -- stages 8..16 (nine: passes of 4 + 4 + 1) on tiles of 512
- * strided rows x 8 consecutive positions, |X|^2 accumulated in a shared-memory image over the reads of the CTA's
- * tile-major run and flushed with one atomic per bin when the tile or the hop changes.  Round C's pass over the
- * scratch (136 MB from DRAM per 256 reads, 36 us) and round B's write-back disappear; the ninth stage costs one
- * more transpose and 8 butterflies per thread, whose 8 twiddles (tw[(t << 8) + plow0 + c], 64 contiguous bytes)
- * live in registers for the whole run of a tile.
- * Tile image: word (row i, column c) at 8 i + (i >> 4) + c (one pad word per 16 rows): pass 0 reads register r of
- * thread t at row 16 (t & 31) + r, column t >> 5 -> bank (t & 31) + 8 r + c, conflict-free; the odd offsets are why
- * the tile arrives by 4-byte cp.async.  One transpose buffer serves both exchanges (the second one leads with a
- * barrier): four barriers per tile.  Shared memory 99 KB per CTA, two CTAs per SM.
- */
-constexpr int kTile9Words = 4096 + 32;
-constexpr int kLargeSmemB9 = kTile9Words * 4 * 2 + kXchWords * 4 + (8 * 240 + 8 * 15 + 8) * 8 + kWS * 8;
-
-struct TwLargeB9 {
-	static constexpr bool kTrivial = false;
-	const int2 *t1; /* [se = 4..7][col][ilow]: stage se at 8 * ((1 << se) - 16) */
-	const int2 *t0; /* [col][15]: stage se < 4, group g at (1 << se) - 1 + g */
-	int2 w8[8];     /* stage 16: this thread's twiddle for column c */
-	template <int K>
-	SCAN_DEV int2 get(int se, int pa) const
-	{
-		const int col = pa >> 9;
-		if (K >= 2)
-			return w8[col];
-		const int ilow = pa & ((1 << se) - 1);
-		if (K == 1)
-			return t1[8 * ((1 << se) - 16) + (col << se) + ilow];
-		return t0[col * 15 + (1 << se) - 1 + ilow];
-	}
-};
-
-template <bool PEAK>
-__global__ void __launch_bounds__(kThreads, 2)
-large_round_b9_acc_kernel(const SCAN_GRID_CONSTANT LargeParams prm)
-{
-	constexpr int L = 17;
-	SCAN_DYN_SMEM(smem);
-	c16 *in = (c16 *)smem;                 /* two tiles */
-	c16 *xch = in + 2 * kTile9Words;
-	int2 *tws1 = (int2 *)(xch + kXchWords);
-	int2 *tws0 = tws1 + 8 * 240;
-	unsigned long long *acc = (unsigned long long *)(tws0 + 8 * 15 + 8);
-	const int t = threadIdx.x;
-	const long long N = 1ll << L;
-	const int n_rel = prm.n_entries;
-	const long long W = (long long)n_rel * 32; /* 32 tiles of 8 columns per read */
-	const long long w0 = W * blockIdx.x / gridDim.x, w1 = W * (blockIdx.x + 1) / gridDim.x;
-	if (w0 >= w1)
-		return;
-	int tile = (int)(w0 / n_rel), rel = (int)(w0 - (long long)tile * n_rel); /* item w = tile * n_rel + rel */
-
-	auto prefetch = [&](int tl, int rl, int buf) {
-		const c16 *data = prm.scratch + (long long)rl * N + tl * 8;
-		c16 *dst = in + buf * kTile9Words;
-#pragma unroll
-		for (int k = 0; k < 16; ++k) {
-			const int q = t + kThreads * k, i = q >> 3, c = q & 7;
-			cp_async4(dst + 8 * i + (i >> 4) + c, data + ((long long)i << 8) + c);
-		}
-		cp_async_commit();
-	};
-	TwLargeB9 tw;
-	tw.t1 = tws1;
-	tw.t0 = tws0;
-	auto load_tables = [&](int tl) {
-		const int plow0 = tl * 8;
-#pragma unroll
-		for (int se = 4; se < 8; ++se) {
-			const int2 *src = prm.twb + twb_offset(se) + ((long long)plow0 << se);
-			int2 *dst = tws1 + 8 * ((1 << se) - 16);
-			for (int k = t; k < (4 << se); k += kThreads) /* 8 << se entries, two per 16-byte copy */
-				cp_async16(dst + 2 * k, src + 2 * k);
-		}
-		if (t < 120) {
-			const int col = t / 15, e = t % 15;
-			int se = 0;
-			while (e >= (2 << se) - 1)
-				se++;
-			const long long m = ((long long)(e - ((1 << se) - 1)) << 8) | (plow0 + col);
-			tws0[t] = prm.tw[m << (L - 9 - se)];
-		}
-		cp_async_commit();
-#pragma unroll
-		for (int c = 0; c < 8; ++c)
-			tw.w8[c] = __ldg(prm.tw + ((long long)t << 8) + plow0 + c);
-	};
-#pragma unroll
-	for (int r = 0; r < kPts; ++r)
-		acc[r * kThreads + t] = 0ull;
-	pdl_launch_dependents();
-	load_tables(tile);
-	int tab_tile = tile;
-	pdl_wait();
-	prefetch(tile, rel, 0);
-	int cur_hop = prm.hop_of[prm.entry_base + rel];
-	auto flush = [&](int tl, int hop) {
-		long long *out = prm.avg + ((long long)hop << L) + tl * 8;
-#pragma unroll
-		for (int r = 0; r < kPts; ++r) {
-			const int i = ((r & 1) << 8) | t, c = r >> 1;
-			const unsigned long long v = acc[r * kThreads + t];
-			if (PEAK)
-				atomicMax(out + ((long long)i << 8) + c, (long long)v);
-			else
-				atomicAdd((unsigned long long *)(out + ((long long)i << 8) + c), v);
-			acc[r * kThreads + t] = 0ull;
-		}
-	};
-	for (long long w = w0; w < w1; ++w) {
-		const int buf = (int)(w - w0) & 1;
-		const c16 *cur = in + buf * kTile9Words;
-		cp_async_wait_all();
-		__syncthreads(); /* tile w has landed for everybody; nobody reads the other buffer or the old tables any more */
-		int ntile = tile, nrel = rel + 1;
-		if (nrel == n_rel)
-			nrel = 0, ntile++;
-		if (w + 1 < w1)
-			prefetch(ntile, nrel, buf ^ 1);
-		if (tile != tab_tile) { /* CTA-uniform, once or twice per run */
-			tab_tile = tile;
-			load_tables(tile);
-			cp_async_wait_all();
-			__syncthreads();
-		}
-		X2 x[kPts];
-		{
-			const int col = t >> 5;
-#pragma unroll
-			for (int r = 0; r < kPts; ++r) {
-				const int i = ((t & 31) << 4) | r;
-				x[r] = x_unpack(cur[8 * i + (i >> 4) + col]);
-			}
-		}
-		run_pass<0, 9>(x, t, tw);
-		exchange<0, 1, false>(x, xch, t, t);
-		run_pass<1, 9>(x, t, tw);
-		exchange<1, 2, true>(x, xch, t, t);
-		run_pass<2, 9>(x, t, tw);
-#pragma unroll
-		for (int r = 0; r < kPts; ++r) {
-			unsigned long long a = acc[r * kThreads + t];
-			accumulate_power<PEAK>(a, x[r].re >> 16, x[r].im >> 16);
-			acc[r * kThreads + t] = a;
-		}
-		/* the run moves on to another tile or hop (or ends): this thread's 16 bins leave with one atomic each */
-		const int nhop = (w + 1 < w1 && ntile == tile) ? prm.hop_of[prm.entry_base + nrel] : -1;
-		if (nhop != cur_hop) {
-			flush(tile, cur_hop);
-			cur_hop = (w + 1 < w1) ? prm.hop_of[prm.entry_base + nrel] : -1;
-		}
-		tile = ntile, rel = nrel;
-	}
-}
-
 /* ---- round C ----------------------------------------------------------- */
 
 constexpr int kRoundCReads = 16; /* reads one CTA of round C walks through at most */

@@ -168,21 +168,6 @@ int large_process(rtlsdr_gpu_scan *h, const uint8_t *base, const long long *d_of
 		}
 		/* (letting round B take 9-10 stages to save round C was measured slower: 32-byte runs) */
 		const int lb = std::min(8, L - 8);
-		if (L == 17 && h->dbg_large_pipe >= 2) {
-			/* 2^17 bins: stages 8..16 and the |X|^2 accumulation in one pipelined kernel, no round C */
-			if (h->cfg.peak_hold) {
-				auto k = large_round_b9_acc_kernel<true>;
-				CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kLargeSmemB9));
-				rc = launch_pdl(h, k, dim3(grid_pipe), kLargeSmemB9, p);
-			} else {
-				auto k = large_round_b9_acc_kernel<false>;
-				CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kLargeSmemB9));
-				rc = launch_pdl(h, k, dim3(grid_pipe), kLargeSmemB9, p);
-			}
-			if (rc || (rc = check_launch(h, "large_round_b9_acc_kernel")))
-				return rc;
-			continue;
-		}
 		if (8 + lb < L && h->dbg_large_pipe) {
 			auto k = large_round_b_pipe_kernel;
 			CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kLargeSmemBP));

@@ -1,6 +1,6 @@
 /* large path (bin_e 13..21) through the emulator: u8 reads [n_reads][2N] -> spectra.
  * in16 != 0: `reads` are decimated c16 images [n_reads][N] and `sums_in` their DC sums. */
-static int g_large_pipe = 2;
+static int g_large_pipe = 1;
 void emu_set_large_pipe(int v) { g_large_pipe = v; }
 
 void emu_large(int L, int peak, int in16, const uint8_t *reads, int n_reads, const int *hop_of,
@@ -64,13 +64,6 @@ void emu_large(int L, int peak, int in16, const uint8_t *reads, int n_reads, con
 	} else {
 		memcpy(sums.data(), sums_in, sums.size() * 8);
 		cuda_emu::launch(tiles, dim3(kThreads), kLargeSmemA, [&]() { large_round_a_kernel<true>(p); });
-	}
-	if (L == 17 && g_large_pipe >= 2) {
-		if (peak)
-			cuda_emu::launch(dim3(pipe_grid), dim3(kThreads), kLargeSmemB9, [&]() { large_round_b9_acc_kernel<true>(p); });
-		else
-			cuda_emu::launch(dim3(pipe_grid), dim3(kThreads), kLargeSmemB9, [&]() { large_round_b9_acc_kernel<false>(p); });
-		return;
 	}
 	const int lb = L - 8 < 8 ? L - 8 : 8;
 	const bool last = 8 + lb == L;

@@ -1,8 +1,8 @@
-# large-FFT path (config 4): A/B by RTLSDR_GPU_LARGE_PIPE (0 = one-tile round B, 1 = pipelined round B + round C, 2 = rounds B + C fused),
+# large-FFT path (config 4): A/B of the pipelined rounds (RTLSDR_GPU_LARGE_PIPE bit 0 = round A, bit 1 = round B),
 # per-kernel times of the default under ncu, then the large-path parity tests.  usage: tools/exp_large.sh TAG
 TAG=${1:-r03b}
 mkdir -p gpurun_out
-for m in 1 2; do
+for m in 0 1; do
   echo "RTLSDR_GPU_LARGE_PIPE=$m"; RTLSDR_GPU_LARGE_PIPE=$m python tools/ab_small.py cfg4 2>&1 | grep -v Warn
 done | tee gpurun_out/${TAG}_large_ab.txt
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/${TAG}_large_launches.csv python tools/ab_small.py cfg4 > /dev/null 2>&1
