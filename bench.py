@@ -477,8 +477,14 @@ class ReadShardedSweep:
         self.tc, self.b, self.n = pd["tune_count"], pd["buf_len"], 1 << pd["bin_e"]
         self.mine = shard_hops(reads, D.world, D.rank)            # contiguous share of the interval's sweeps
         self.window = rs.window_coefs(window, self.n)
-        self.g = rs.GpuScan.from_plan(pd, window_coefs=self.window, device=D.local)
+        # async_report: the epilogue that stores this rank's raw bins runs on the handle's report stream while its own
+        # stream already transforms the next interval into the second accumulator set.  Rank 0 merges and reports
+        # with a SECOND handle on that handle's stream, so nothing of the exchange sits on a transform stream.
+        self.g = rs.GpuScan.from_plan(pd, window_coefs=self.window, device=D.local, async_report=True)
         self.stream = torch.cuda.ExternalStream(self.g.get_stream())
+        self.rstream = torch.cuda.ExternalStream(self.g.get_report_stream())
+        self.g_merge = rs.GpuScan.from_plan(pd, window_coefs=self.window, device=D.local) if D.rank == 0 else None
+        self.mstream = torch.cuda.ExternalStream(self.g_merge.get_stream()) if self.g_merge else None
         self.gather = SpectrumGather(self.tc, self.n, self.g.db_count, D.world, D.rank, torch.device("cuda", D.local),
                                      mode=("host" if os.environ.get("BENCH_GLOO_ONE_GPU") and D.world > 1 else None),
                                      replicated=True)
@@ -497,16 +503,24 @@ class ReadShardedSweep:
         k = i & 1
         if len(self.mine):
             self.g.submit_device(0, self.tc, len(self.mine), self.dev_in.data_ptr(), self.tc * self.b, self.b)
-        self.gather.before_collect(k, self.stream)
+        self.gather.before_collect(k, self.rstream)
         p_avg, p_smp, _ = self.gather.pointers(k)
         self.g.collect_device(p_avg, p_smp, None)
-        self.gather.publish(k, self.stream)
+        self.gather.publish(k, self.rstream)
         if self.D.rank == 0:
-            self.stream.wait_event(self.gather.gathered[k])
-            self.g.merge_device(*self.gather.partial_sets(k))
+            self.mstream.wait_event(self.gather.gathered[k])
+            self.g_merge.merge_device(*self.gather.partial_sets(k))
+            self.gather.release_copy(k, self.mstream)
             base = self.out.data_ptr()
             p_db = base + self.tc * self.n * 8
-            self.g.collect_device(base, p_db + self.tc * self.g.db_count * 8, p_db)
+            self.g_merge.collect_device(base, p_db + self.tc * self.g.db_count * 8, p_db)
+
+    def drain(self):
+        """the handle's stream waits for every report, exchange and merge issued so far"""
+        self.stream.wait_stream(self.rstream)
+        self.gather.drain(self.stream)
+        if self.mstream is not None:
+            self.stream.wait_stream(self.mstream)
 
     def merged_bins(self):
         self.D.torch.cuda.synchronize()
@@ -514,6 +528,8 @@ class ReadShardedSweep:
 
     def close(self):
         self.g.close()
+        if self.g_merge:
+            self.g_merge.close()
 
 
 def read_sharded_companion(D, rs, steps, peak_gbs):
@@ -548,7 +564,7 @@ def read_sharded_companion(D, rs, steps, peak_gbs):
     D.barrier()
     for i in range(3):
         sw.step(1 + i)
-    sw.gather.drain(sw.stream)
+    sw.drain()
     D.barrier()
     total, done, want, rounds = 0.0, 0, 1, 0
     while rounds < want:
@@ -557,7 +573,7 @@ def read_sharded_companion(D, rs, steps, peak_gbs):
         e0.record(sw.stream)
         for i in range(steps):
             sw.step(4 + done + i)
-        sw.gather.drain(sw.stream)
+        sw.drain()
         e1.record(sw.stream)
         D.barrier()
         ms = D.max(e0.elapsed_time(e1))

@@ -154,6 +154,7 @@ class SpectrumGather:
             self.stage = [torch.zeros(self.words, dtype=torch.int64).pin_memory() for _ in range(SLOTS)]
         # rank 0, replicated: private device copy of a gathered buffer, made before the writers may reuse the slots
         self.dev_copy = None
+        self.copy_free = [None] * SLOTS     # events after which dev_copy[k] may be overwritten (release_copy)
         if replicated and rank == 0 and self.cuda:
             self.dev_copy = [torch.zeros(world, self.words, dtype=torch.int64, device=self.device) for _ in range(SLOTS)]
         # rank 0: pinned landing area of a gathered report
@@ -275,6 +276,8 @@ class SpectrumGather:
                 if to_host:
                     self.host[k].copy_(self.recv[k], non_blocking=True)
                 if self.dev_copy is not None:
+                    if self.copy_free[k] is not None:
+                        self.comm.wait_event(self.copy_free[k])
                     self.dev_copy[k].copy_(self.recv[k], non_blocking=True)
                 # "interval consumed" in every rank's memory (one launch): the slots may be rewritten
                 addrs = [self._flag_addr(r, SLOTS * self.world + k) for r in range(self.world)]
@@ -299,6 +302,8 @@ class SpectrumGather:
             if to_host and self.rank == 0 and src is not None:
                 self.host[k].copy_(src, non_blocking=True)
             if self.dev_copy is not None:
+                if self.copy_free[k] is not None:
+                    self.comm.wait_event(self.copy_free[k])
                 self.dev_copy[k].copy_(src if src is not None else self.recv[k], non_blocking=True)
             self.gathered[k].record(self.comm)
         self.last_exchange = self.gathered[k]
@@ -332,6 +337,13 @@ class SpectrumGather:
         base = self.dev_copy[k].data_ptr()
         smp = base + (self.hmax * self.n + self.hmax * self.db_count) * 8
         return base, smp, self.world, self.words * 8
+
+    def release_copy(self, k, stream):
+        """rank 0, replicated mode: everything enqueued so far on `stream` (the merge) is the last reader of the
+        private copy of buffer k; the exchange two intervals later waits for it before overwriting the copy"""
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        self.copy_free[k] = ev
 
     def unpack(self, bufs) -> IntervalReport:
         """bufs: int64 [world, words] -> rows in hop order"""
