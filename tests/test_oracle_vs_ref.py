@@ -33,6 +33,18 @@ def test_fix_fft_incl_int16_wrap(ref_oracle, port_oracle):
             assert np.array_equal(ref_oracle.fix_fft(x, m), port_oracle.fix_fft(x, m)), m
 
 
+def test_fix_fft_largest_sizes(ref_oracle, port_oracle):
+    """m = 18..21, the rest of what rtl_power.c:483 allows (the GPU's rounds B and C for N > 2^17 are checked against
+    the restatement at these sizes): a random and an alternating full-scale input each"""
+    rng = np.random.default_rng(3)
+    for m in range(18, 22):
+        ref_oracle.sine_table(m)
+        n = 1 << m
+        for x in (rng.integers(-32768, 32768, 2 * n).astype(np.int16),
+                  (rng.integers(0, 2, 2 * n) * 65535 - 32768).astype(np.int16)):
+            assert np.array_equal(ref_oracle.fix_fft(x, m), port_oracle.fix_fft(x, m)), m
+
+
 def test_filters(ref_oracle, port_oracle):
     rng = np.random.default_rng(2)
     for length in (12, 13, 16, 64, 1000, 16383, 16384):
